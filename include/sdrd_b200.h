@@ -1,0 +1,188 @@
+/*
+ * sdrd_b200.h -- C ABI of libsdrd_b200.so, the B200 (sm_100a) implementation of sdrdaemon's
+ * decimate + FEC hot path.  Plain pointers and sizes only; every entry point states the reference
+ * interface it stands in for (paths relative to f4exb/sdrdaemon v3.1.2).
+ *
+ * Conventions
+ *   - IQ samples are the reference's `IQSample` (include/SDRDaemon.h:52-68): packed little-endian
+ *     {int16 re, int16 im}, 4 bytes; an `IQSampleVector` is passed as (pointer, sample count).
+ *   - "streams" are independent instances of the same reference object (one Downsampler /
+ *     UDPSinkFEC each) processed in one call; stream s starts `stride` samples after stream s-1.
+ *   - All functions return 0 on success and a negative SDRD_E* code on failure;
+ *     sdrd_last_error() returns the message of the calling thread's last failure (the reference
+ *     objects keep `std::string m_error`, include/Downsampler.h:65-76, include/UDPSink.h:85-108).
+ *   - Host entry points take HOST pointers and perform the host<->device copies themselves.
+ *     `_dev` entry points work on the handle's device buffers (for callers that already keep the
+ *     stream in HBM) and take the CUDA stream as `void*` (cudaStream_t, may be NULL).
+ *   - There is no CPU fallback: without a usable sm_100 device every create call fails with
+ *     SDRD_ENODEV.
+ */
+#ifndef SDRD_B200_H
+#define SDRD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDRD_OK 0
+#define SDRD_EINVAL (-1)  /* invalid argument (Downsampler.cpp:39-43,57-61; cm256 count checks) */
+#define SDRD_ENODEV (-2)  /* no CUDA device / wrong architecture */
+#define SDRD_ECUDA (-3)   /* CUDA runtime error, see sdrd_last_error() */
+#define SDRD_ENOMEM (-4)
+#define SDRD_ERANGE (-5)  /* call exceeds the capacity given at create time */
+
+/* Downsampler::fcPos_t, include/Downsampler.h:31-35 */
+#define SDRD_FC_INFRA 0
+#define SDRD_FC_SUPRA 1
+#define SDRD_FC_CENTER 2
+/* which IntHalfbandFilter the reference was built with, include/Decimators.h:56-70 */
+#define SDRD_HB_EO1 0 /* USE_SSE4_1 builds (x86): IntHalfbandFilterEO1<64> */
+#define SDRD_HB_DB 1  /* other builds: IntHalfbandFilterDB<64> (+1 rounding on the centre tap) */
+
+/* Wire format constants, include/UDPSinkFEC.h:34-36,77-121 */
+#define SDRD_UDPSIZE 512
+#define SDRD_NB_ORIGINAL 128
+#define SDRD_BLOCK_BYTES 508
+#define SDRD_SAMPLES_PER_BLOCK 127
+#define SDRD_FRAME_SAMPLES (127 * 127)
+#define SDRD_MAX_FEC 128
+
+const char* sdrd_last_error(void);
+const char* sdrd_version(void);
+/* Number of usable sm_100 devices (0 if none); never fails. */
+int sdrd_device_count(void);
+/* Select the device used by handles created afterwards on this thread (cudaSetDevice). */
+int sdrd_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Decimator: Downsampler + Decimators + IntHalfbandFilter{EO1,DB}<64>
+ *   replaces  Downsampler::Downsampler/configure/process (include/Downsampler.h:42-57,
+ *             sdmnbase/Downsampler.cpp:32-162) and the routines it dispatches to
+ *             (sdmnbase/Decimators.cpp:22-1305), called from sdrdaemonrx.cpp:640.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdrd_dec sdrd_dec;
+
+/* log2_decim 0..6, fcpos SDRD_FC_*, variant SDRD_HB_*; max_in = largest n_in per stream per call. */
+int sdrd_dec_create(sdrd_dec** dec, int log2_decim, int fcpos, int variant, int n_streams, size_t max_in);
+void sdrd_dec_destroy(sdrd_dec* dec);
+/* Forget all filter state (a freshly constructed Decimators, include/Decimators.h:57-62). */
+int sdrd_dec_reset(sdrd_dec* dec);
+/* Downsampler::configure (Downsampler.cpp:32-67): change decim / fcpos between blocks.  Filter
+ * history is kept as the raw input history, so the new cascade continues without a gap. */
+int sdrd_dec_configure(sdrd_dec* dec, int log2_decim, int fcpos);
+int sdrd_dec_log2_decim(const sdrd_dec* dec);
+
+/* Downsampler::process (include/Downsampler.h:57) for n_streams streams at once.
+ *   iq_in   n_in samples per stream, stream pitch in_stride samples (HOST)
+ *   iq_out  receives n_in >> log2_decim samples per stream, pitch out_stride samples (HOST)
+ *   n_out   samples written per stream
+ *   sample_bits  the reference's in/out `sampleSize` (effective bits per component)
+ * Input samples beyond the last whole group of 2^log2_decim are ignored exactly as the
+ * reference's loop bounds do (Decimators.cpp:412). */
+int sdrd_dec_process(sdrd_dec* dec, const int16_t* iq_in, size_t n_in, size_t in_stride, int16_t* iq_out,
+                     size_t out_stride, size_t* n_out, unsigned* sample_bits);
+
+/* Device-resident form.  The caller writes the next n_in samples of every stream to
+ * sdrd_dec_dev_input() (pitch *stride samples) and reads the result from sdrd_dec_dev_output(). */
+void* sdrd_dec_dev_input(sdrd_dec* dec, size_t* stride);
+void* sdrd_dec_dev_output(sdrd_dec* dec, size_t* stride);
+int sdrd_dec_process_dev(sdrd_dec* dec, size_t n_in, size_t* n_out, unsigned* sample_bits, void* cuda_stream);
+/* Number of kernel launches issued by this handle so far (for bench accounting). */
+long long sdrd_dec_launches(const sdrd_dec* dec);
+
+/* ------------------------------------------------------------------------------------------
+ * CM256 (Cauchy MDS GF(256) erasure code), batched over superframes
+ *   replaces  CM256::cm256_encode as called at sdmnbase/UDPSinkFEC.cpp:228-246 and
+ *             CM256::cm256_decode as called at sdmnbase/SDRdaemonFECBuffer.cpp:170-213
+ *             (OriginalCount = 128, BlockBytes = 508).
+ * ------------------------------------------------------------------------------------------ */
+/* originals: n_frames x 128 blocks of 508 bytes, consecutive blocks `block_pitch` bytes apart
+ * (508 for bare payloads, 512 for datagram images pointed at their payload);
+ * recovery: n_frames x recovery_count x 508 bytes, contiguous (the layout cm256_encode writes). */
+int sdrd_cm256_encode(const uint8_t* originals, size_t block_pitch, int n_frames, int recovery_count,
+                      uint8_t* recovery);
+
+/* ------------------------------------------------------------------------------------------
+ * Sender: UDPSinkFEC framing + encode
+ *   replaces  UDPSinkFEC::write (sdmnbase/UDPSinkFEC.cpp:79-191) and the encode half of
+ *             UDPSinkFEC::transmitUDP (:193-256); the datagram images it returns are what the
+ *             reference hands to UDPSocket::SendDataGram (:259-282), in send order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdrd_sink sdrd_sink;
+
+int sdrd_sink_create(sdrd_sink** sink, int n_streams, size_t max_samples);
+void sdrd_sink_destroy(sdrd_sink* sink);
+/* UDPSinkFEC::reset: frame counter, block and sample indices back to zero. */
+int sdrd_sink_reset(sdrd_sink* sink);
+/* UDPSink::setCenterFrequency (already divided to kHz) / setSampleRate / setSampleBytes / setSampleBits */
+int sdrd_sink_set_meta(sdrd_sink* sink, uint32_t center_freq_khz, uint32_t sample_rate, uint8_t sample_bytes,
+                       uint8_t sample_bits);
+/* UDPSinkFEC::setNbBlocksFEC */
+int sdrd_sink_set_nb_fec(sdrd_sink* sink, int nb_fec);
+/* Timestamp written into block 0 of frames started from now on.  Without it the wall clock is read
+ * (gettimeofday, UDPSinkFEC.cpp:95) once per write call. use_fixed = 0 returns to the wall clock. */
+int sdrd_sink_set_time(sdrd_sink* sink, int use_fixed, uint32_t tv_sec, uint32_t tv_usec);
+/* Datagrams per completed frame with the current FEC setting: 128 + nb_fec. */
+int sdrd_sink_blocks_per_frame(const sdrd_sink* sink);
+/* Frames a write of n_samples per stream would complete given the samples already pending. */
+size_t sdrd_sink_frames_for(const sdrd_sink* sink, size_t n_samples);
+
+/* UDPSinkFEC::write for n_streams streams.  iq: n_samples per stream (HOST), pitch `stride` samples.
+ * datagrams (HOST) receives, per stream, the completed frames one after the other, each
+ * (128 + nb_fec) x 512 bytes in send order; stream pitch = frame_capacity frames.
+ * *n_frames = frames completed per stream (identical for all streams). */
+int sdrd_sink_write(sdrd_sink* sink, const int16_t* iq, size_t n_samples, size_t stride, uint8_t* datagrams,
+                    size_t frame_capacity, size_t* n_frames);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused receiver-side pipeline  TestSource -> Downsampler -> UDPSinkFEC  (sdrdaemonrx.cpp:579-663)
+ *   = sdrd_dec_process feeding sdrd_sink_write without leaving HBM.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdrd_rx sdrd_rx;
+
+int sdrd_rx_create(sdrd_rx** rx, int log2_decim, int fcpos, int variant, int n_streams, size_t max_in);
+void sdrd_rx_destroy(sdrd_rx* rx);
+int sdrd_rx_reset(sdrd_rx* rx);
+sdrd_dec* sdrd_rx_dec(sdrd_rx* rx);   /* borrowed */
+sdrd_sink* sdrd_rx_sink(sdrd_rx* rx); /* borrowed: use the sdrd_sink_set_* calls on it */
+/* iq_in as sdrd_dec_process, datagrams / frame_capacity / n_frames as sdrd_sink_write. */
+int sdrd_rx_process(sdrd_rx* rx, const int16_t* iq_in, size_t n_in, size_t in_stride, uint8_t* datagrams,
+                    size_t frame_capacity, size_t* n_frames);
+/* Device-resident form: input at sdrd_dec_dev_input(sdrd_rx_dec(rx)), datagram images left at
+ * sdrd_rx_dev_datagrams() (stream pitch *frame_pitch frames of (128 + nb_fec) x 512 bytes). */
+void* sdrd_rx_dev_datagrams(sdrd_rx* rx, size_t* frame_pitch);
+int sdrd_rx_process_dev(sdrd_rx* rx, size_t n_in, size_t* n_frames, void* cuda_stream);
+long long sdrd_rx_launches(const sdrd_rx* rx);
+
+/* ------------------------------------------------------------------------------------------
+ * Receiver: SDRdaemonFECBuffer decode
+ *   replaces  the store/decode/copy-back part of SDRdaemonFECBuffer::writeAndRead
+ *             (sdmnbase/SDRdaemonFECBuffer.cpp:143-213) batched over frames: for each frame, the
+ *             first min(n_blocks, 128) received datagrams are stored, cm256_decode runs if recovery
+ *             blocks are among them, and blocks 1..127 are returned.
+ * ------------------------------------------------------------------------------------------ */
+#define SDRD_FRAME_INCOMPLETE 0 /* fewer than 128 blocks: missing blocks read as zero (.cpp:109) */
+#define SDRD_FRAME_COMPLETE 1   /* 128 originals, nothing to recover */
+#define SDRD_FRAME_RECOVERED 2  /* cm256_decode ran and succeeded */
+#define SDRD_FRAME_FAILED (-1)  /* cm256_decode refused the block set */
+
+/* superblocks: n_frames x blocks_pitch received 512-byte datagrams in arrival order (HOST);
+ * n_blocks[f] <= blocks_pitch datagrams of frame f are valid;
+ * payload: n_frames x 127 x 508 bytes; block0: n_frames x 508 bytes (meta block) or NULL;
+ * status: n_frames SDRD_FRAME_* codes. */
+int sdrd_fec_decode(const uint8_t* superblocks, size_t blocks_pitch, const int* n_blocks, int n_frames,
+                    uint8_t* payload, uint8_t* block0, int* status);
+/* Device-resident form of the same (all pointers are device pointers). */
+int sdrd_fec_decode_dev(const uint8_t* superblocks, size_t blocks_pitch, const int* n_blocks, int n_frames,
+                        uint8_t* payload, uint8_t* block0, int* status, void* cuda_stream);
+/* Device-resident encode (all pointers are device pointers). */
+int sdrd_cm256_encode_dev(const uint8_t* originals, size_t block_pitch, int n_frames, int recovery_count,
+                          uint8_t* recovery, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDRD_B200_H */

@@ -1,0 +1,478 @@
+/*
+ * fec_kernels.cuh -- K2 (superframe framing + CM256 encode) and K3 (CM256 recover) for sdrdaemon's
+ * 128-block superframes.
+ *
+ *   K2 replaces UDPSinkFEC::write (sdmnbase/UDPSinkFEC.cpp:79-191: 127 samples per block, block 0 =
+ *      meta data, 128 blocks per frame) and CM256::cm256_encode as called from
+ *      UDPSinkFEC::transmitUDP (:228-256).
+ *   K3 replaces the store / cm256_decode / copy-back part of SDRdaemonFECBuffer::writeAndRead
+ *      (sdmnbase/SDRdaemonFECBuffer.cpp:143-213).
+ *
+ * Both are the same computation: R output blocks, each a GF(2^8)-linear combination of the 128
+ * blocks of the frame,  out[r] = XOR_j C[r][j] (x) blk[j]  over 508 payload bytes.  For the encoder C
+ * is the fixed Cauchy matrix; for the decoder C = [A^-1 | A^-1 M] is built per frame from the
+ * erasure pattern (A = Cauchy sub-matrix of the received recovery rows x erased columns).
+ *
+ * One CTA owns one superframe, kept in shared memory as 128 datagram images of 128 words (header
+ * word + 127 payload words).  A constant-times-block product works on 4 packed bytes at a time:
+ * each byte is split 3+3+2 bits, the three partial products come from 8-entry byte tables held in
+ * registers and are looked up with the byte-permute unit (PRMT), 3 PRMT + 2 LOP3 per word.
+ * Warp w handles columns 16w..16w+15 for a block of 16 output rows (64 accumulator registers per
+ * thread: 16 rows x 4 words) and the 8 partial sums meet in shared memory through XOR atomics.
+ * No tensor cores: this is byte-wise table arithmetic, bound by the ALU/PRMT issue rate.
+ */
+#pragma once
+#include "sdrd_platform.cuh"
+
+namespace sdrd {
+namespace fec {
+
+constexpr int NT = 256;
+constexpr int ROW_WORDS = 128;               /* one 512-byte datagram */
+constexpr int IMG_WORDS = 128 * ROW_WORDS;   /* 128 datagrams */
+constexpr int FRAME_SAMPLES = 127 * 127;
+constexpr int RB = 16;                       /* output rows per pass */
+
+struct Tables {
+    const uint4* tabA;      /* [256] */
+    const uint32_t* tabB;   /* [256] */
+    const uint8_t* cauchy;  /* [128][128] encoder matrix */
+    const uint8_t* gfexp;   /* [512] */
+    const uint8_t* gflog;   /* [256] */
+};
+
+/* nibble selectors for PRMT from the 3+3+2-bit digits of four packed bytes */
+SDRD_DEVICE uint32_t pack_digits(uint32_t m)
+{
+    uint32_t t = m | (m >> 4);
+    return __byte_perm(t, 0u, 0x0020u);
+}
+SDRD_DEVICE void selectors(uint32_t x, uint32_t& s0, uint32_t& s1, uint32_t& s2)
+{
+    s0 = pack_digits(x & 0x07070707u);
+    s1 = pack_digits((x >> 3) & 0x07070707u);
+    s2 = pack_digits((x >> 6) & 0x03030303u);
+}
+SDRD_DEVICE uint32_t mul4(uint4 a, uint32_t b, uint32_t s0, uint32_t s1, uint32_t s2)
+{
+    return __byte_perm(a.x, a.y, s0) ^ __byte_perm(a.z, a.w, s1) ^ __byte_perm(b, b, s2);
+}
+
+/* One pass: rows [row0, row0 + nrows) (nrows <= 16) of  out = C * img  accumulated into rec16
+ * (16 x 128 words, zeroed by the caller).  coefT[j * cstride + r] = C[r][j]. */
+SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint8_t* SDRD_RESTRICT coefT, int cstride,
+                             int row0, int nrows, const uint4* SDRD_RESTRICT tabA,
+                             const uint32_t* SDRD_RESTRICT tabB, uint32_t* rec16, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t acc[RB][4];
+#pragma unroll
+    for (int r = 0; r < RB; r++)
+#pragma unroll
+        for (int w = 0; w < 4; w++) acc[r][w] = 0u;
+
+    for (int jj = 0; jj < 16; jj++) {
+        const int j = warp * 16 + jj;
+        uint32_t s0[4], s1[4], s2[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) selectors(img[j * ROW_WORDS + lane + 32 * w], s0[w], s1[w], s2[w]);
+        /* the 16 coefficients of this column for the rows of the pass: one 128-bit load */
+        const uint4 cv = *reinterpret_cast<const uint4*>(coefT + j * cstride + row0);
+        const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            if (r < nrows) {
+                const unsigned c = (cw[r >> 2] >> (8 * (r & 3))) & 0xFFu;
+                const uint4 a = tabA[c];
+                const uint32_t b = tabB[c];
+#pragma unroll
+                for (int w = 0; w < 4; w++) acc[r][w] ^= mul4(a, b, s0[w], s1[w], s2[w]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (r < nrows) {
+#pragma unroll
+            for (int w = 0; w < 4; w++) atomicXor(&rec16[r * ROW_WORDS + lane + 32 * w], acc[r][w]);
+        }
+    }
+}
+
+/* shared-memory carve-up common to both kernels */
+struct Smem {
+    uint32_t* img;    /* [128][128] */
+    uint32_t* rec16;  /* [16][128] */
+    uint4* tabA;      /* [256] */
+    uint32_t* tabB;   /* [256] */
+    uint8_t* coefT;   /* [128][cstride] */
+    uint8_t* extra;
+};
+constexpr size_t SMEM_FIXED = (size_t)IMG_WORDS * 4 + (size_t)RB * ROW_WORDS * 4 + 4096 + 1024;
+SDRD_DEVICE Smem carve(unsigned char* base, int cstride)
+{
+    Smem s;
+    s.img = reinterpret_cast<uint32_t*>(base);
+    s.rec16 = s.img + IMG_WORDS;
+    s.tabA = reinterpret_cast<uint4*>(s.rec16 + RB * ROW_WORDS);
+    s.tabB = reinterpret_cast<uint32_t*>(s.tabA + 256);
+    s.coefT = reinterpret_cast<uint8_t*>(s.tabB + 256);
+    s.extra = s.coefT + 128 * cstride;
+    return s;
+}
+SDRD_DEVICE void load_tables(const Smem& s, const Tables& t, int tid)
+{
+    for (int i = tid; i < 256; i += NT) {
+        s.tabA[i] = t.tabA[i];
+        s.tabB[i] = t.tabB[i];
+    }
+}
+
+/* ============================================================================ encode ==== */
+
+struct EncParams {
+    int mode;  /* 0: frame mode (samples -> datagram images), 1: raw mode (originals -> recovery blocks) */
+    int F;     /* recovery blocks per frame, 0..128 */
+    int cstride; /* F rounded up to a multiple of 16 (>= 16) */
+    /* frame mode */
+    const uint32_t* samples;   /* stream s: samples + s * sample_stride */
+    long long sample_stride;
+    const uint32_t* pending;   /* [S][FRAME_SAMPLES]: samples carried over from earlier calls */
+    int n_pending;
+    uint32_t meta_first[6];    /* block-0 payload (24 bytes) of a frame begun in an earlier call */
+    uint32_t meta_next[6];     /* block-0 payload of frames begun in this call */
+    unsigned frame_index0;     /* frame counter of the first frame completed by this call */
+    uint32_t* dgrams;          /* stream s, frame f: dgrams + s * dgram_stride + f * (128 + F) * 128 */
+    long long dgram_stride;    /* words */
+    /* raw mode */
+    const uint8_t* originals;  /* frame f block j: originals + (f * 128 + j) * block_pitch */
+    long long block_pitch;
+    uint8_t* recovery;         /* frame f row r: recovery + (f * F + r) * 508 */
+    Tables tab;
+};
+
+inline size_t enc_smem_bytes(int cstride) { return SMEM_FIXED + (size_t)128 * cstride; }
+
+SDRD_KERNEL(NT, 2) encode_kernel(EncParams p)
+{
+    SDRD_DYN_SMEM(smem_raw);
+    const int tid = (int)threadIdx.x;
+    const int f = (int)blockIdx.x, s = (int)blockIdx.y;
+    Smem sm = carve(smem_raw, p.cstride);
+    load_tables(sm, p.tab, tid);
+    /* coefficient rows of the Cauchy matrix, transposed so that the 16 rows of a pass are adjacent */
+    for (int k = tid; k < 128 * p.cstride; k += NT) {
+        const int j = k / p.cstride, r = k - j * p.cstride;
+        sm.coefT[k] = r < p.F ? p.tab.cauchy[r * 128 + j] : (uint8_t)0;
+    }
+
+    const unsigned frame_index = (p.frame_index0 + (unsigned)f) & 0xFFFFu;
+    if (p.mode == 0) {
+        /* UDPSinkFEC::write: block 0 = meta data, blocks 1..127 = 127 samples each */
+        const uint32_t* meta = (f == 0 && p.n_pending > 0) ? p.meta_first : p.meta_next;
+        for (int k = tid; k < ROW_WORDS; k += NT) {
+            uint32_t v = 0;
+            if (k == 0) v = frame_index;
+            else if (k <= 6) v = meta[k - 1];
+            sm.img[k] = v;
+        }
+        for (int k = tid; k < 127; k += NT) sm.img[(k + 1) * ROW_WORDS] = frame_index | ((uint32_t)(k + 1) << 16);
+        const uint32_t* src = p.samples + (long long)s * p.sample_stride;
+        const uint32_t* pend = p.pending + (long long)s * FRAME_SAMPLES;
+        const long long g0 = (long long)f * FRAME_SAMPLES - p.n_pending; /* index into this call's samples */
+        for (int k = tid; k < FRAME_SAMPLES; k += NT) {
+            const int b = k / 127, i = k - b * 127;
+            const long long g = g0 + k;
+            sm.img[(b + 1) * ROW_WORDS + 1 + i] = g < 0 ? pend[g + p.n_pending] : src[g];
+        }
+    } else {
+        for (int k = tid; k < 128 * 127; k += NT) {
+            const int j = k / 127, i = k - j * 127;
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(p.originals + ((long long)f * 128 + j) * p.block_pitch);
+            sm.img[j * ROW_WORDS + 1 + i] = row[i];
+        }
+        for (int k = tid; k < 128; k += NT) sm.img[k * ROW_WORDS] = 0u;
+    }
+    __syncthreads();
+
+    uint32_t* out = nullptr;
+    if (p.mode == 0) {
+        out = p.dgrams + (long long)s * p.dgram_stride + (long long)f * (128 + p.F) * ROW_WORDS;
+        /* the 128 original datagrams leave as they are */
+        const uint4* src4 = reinterpret_cast<const uint4*>(sm.img);
+        uint4* dst4 = reinterpret_cast<uint4*>(out);
+        for (int k = tid; k < IMG_WORDS / 4; k += NT) dst4[k] = src4[k];
+    }
+
+    for (int row0 = 0; row0 < p.F; row0 += RB) {
+        const int nrows = p.F - row0 < RB ? p.F - row0 : RB;
+        for (int k = tid; k < RB * ROW_WORDS; k += NT) sm.rec16[k] = 0u;
+        __syncthreads();
+        matvec_pass(sm.img, sm.coefT, p.cstride, row0, nrows, sm.tabA, sm.tabB, sm.rec16, tid);
+        __syncthreads();
+        if (p.mode == 0) {
+            /* recovery datagram = header {frameIndex, blockIndex = 128 + r, filler 0} + payload */
+            for (int k = tid; k < nrows; k += NT)
+                sm.rec16[k * ROW_WORDS] = frame_index | ((uint32_t)(128 + row0 + k) << 16);
+            __syncthreads();
+            const uint4* src4 = reinterpret_cast<const uint4*>(sm.rec16);
+            uint4* dst4 = reinterpret_cast<uint4*>(out + (128 + row0) * ROW_WORDS);
+            for (int k = tid; k < nrows * ROW_WORDS / 4; k += NT) dst4[k] = src4[k];
+        } else {
+            for (int k = tid; k < nrows * 127; k += NT) {
+                const int r = k / 127, i = k - r * 127;
+                uint32_t* row = reinterpret_cast<uint32_t*>(p.recovery + ((long long)f * p.F + row0 + r) * 508);
+                row[i] = sm.rec16[r * ROW_WORDS + 1 + i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* ============================================================================ decode ==== */
+
+constexpr int ST_INCOMPLETE = 0, ST_COMPLETE = 1, ST_RECOVERED = 2, ST_FAILED = -1, ST_NEEDS_BIG = -100;
+
+struct DecParams {
+    const uint32_t* sb;        /* frame f datagram i: sb + (f * blocks_pitch + i) * 128 */
+    long long blocks_pitch;    /* datagrams */
+    const int* n_blocks;       /* [n_frames] */
+    uint32_t* payload;         /* frame f: payload + f * 127 * 127 words (blocks 1..127) */
+    uint32_t* block0;          /* frame f: block0 + f * 127 words, may be null */
+    int* status;               /* [n_frames] */
+    int pass;                  /* 0: frames needing more than DCAP rows are flagged and left; 1: only flagged frames */
+    Tables tab;
+};
+
+template <int DCAP>
+inline size_t dec_smem_bytes()
+{
+    /* coefT [128][DCAP] + aug [DCAP][2*DCAP] + exp/log + small lists */
+    return SMEM_FIXED + (size_t)128 * DCAP + (size_t)DCAP * 2 * DCAP + 512 + 256 + 2048;
+}
+
+SDRD_DEVICE uint8_t gmul(const uint8_t* ex, const uint8_t* lg, uint8_t a, uint8_t b)
+{
+    return (a && b) ? ex[lg[a] + lg[b]] : (uint8_t)0;
+}
+SDRD_DEVICE uint8_t gdiv(const uint8_t* ex, const uint8_t* lg, uint8_t a, uint8_t b)
+{
+    return a ? ex[lg[a] + 255 - lg[b]] : (uint8_t)0;
+}
+
+template <int DCAP>
+SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
+{
+    SDRD_DYN_SMEM(smem_raw);
+    const int tid = (int)threadIdx.x;
+    const int f = (int)blockIdx.x;
+    if (p.pass == 1 && p.status[f] != ST_NEEDS_BIG) return;
+
+    Smem sm = carve(smem_raw, DCAP);
+    uint8_t* aug = sm.extra;                          /* [DCAP][2*DCAP] */
+    uint8_t* gfexp = aug + DCAP * 2 * DCAP;           /* [512] */
+    uint8_t* gflog = gfexp + 512;                     /* [256] */
+    int* lists = reinterpret_cast<int*>(gflog + 256); /* 2048 bytes */
+    int* origRow = lists;                 /* [128] row of the image holding original b, or -1 */
+    int* origCnt = lists + 128;           /* [128] times original b was received */
+    unsigned* recMask = reinterpret_cast<unsigned*>(lists + 256);  /* [4] bit i: datagram i is a recovery block */
+    unsigned* missMask = recMask + 4;                              /* [4] bit b: original b missing */
+    int* flags = lists + 264;             /* [0] duplicate seen, [1] singular */
+    uint8_t* recRowOf = reinterpret_cast<uint8_t*>(lists + 272);   /* [128] k -> image row */
+    uint8_t* recIdxOf = recRowOf + 128;                            /* [128] k -> block index (128..255) */
+    uint8_t* erased = recIdxOf + 128;                              /* [128] c -> erased original index */
+
+    load_tables(sm, p.tab, tid);
+    for (int i = tid; i < 512; i += NT) gfexp[i] = p.tab.gfexp[i];
+    for (int i = tid; i < 256; i += NT) gflog[i] = p.tab.gflog[i];
+
+    int nb = p.n_blocks[f];
+    if (nb > 128) nb = 128; /* blocks beyond the first 128 received are dropped (.cpp:143) */
+    if (nb < 0) nb = 0;
+    {
+        const uint4* src4 = reinterpret_cast<const uint4*>(p.sb + (long long)f * p.blocks_pitch * ROW_WORDS);
+        uint4* dst4 = reinterpret_cast<uint4*>(sm.img);
+        for (int k = tid; k < nb * (ROW_WORDS / 4); k += NT) dst4[k] = src4[k];
+        for (int k = nb * (ROW_WORDS / 4) + tid; k < IMG_WORDS / 4; k += NT) dst4[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid < 128) {
+        origRow[tid] = -1;
+        origCnt[tid] = 0;
+    }
+    if (tid < 8) recMask[tid] = 0u; /* recMask + missMask */
+    if (tid < 2) flags[tid] = 0;
+    __syncthreads();
+
+    /* classify the received datagrams by header.blockIndex (.cpp:143-166) */
+    if (tid < nb) {
+        const int idx = (int)((sm.img[tid * ROW_WORDS] >> 16) & 0xFFu);
+        if (idx < 128) {
+            atomicMax(&origRow[idx], tid); /* a repeated original overwrites the earlier copy */
+            atomicAdd(&origCnt[idx], 1);
+        } else {
+            atomicOr(&recMask[tid >> 5], 1u << (tid & 31));
+        }
+    }
+    __syncthreads();
+    if (tid < 128) {
+        if (origRow[tid] < 0) atomicOr(&missMask[tid >> 5], 1u << (tid & 31));
+        if (origCnt[tid] > 1) flags[0] = 1;
+    }
+    __syncthreads();
+    const int N = __popc(recMask[0]) + __popc(recMask[1]) + __popc(recMask[2]) + __popc(recMask[3]);
+    const int n_missing = __popc(missMask[0]) + __popc(missMask[1]) + __popc(missMask[2]) + __popc(missMask[3]);
+    /* ordered lists: recovery blocks in arrival order, erased originals ascending */
+    if (tid < 128) {
+        const int wq = tid >> 5;
+        const unsigned below = (1u << (tid & 31)) - 1u;
+        int rr = 0, rm = 0;
+        for (int q = 0; q < wq; q++) {
+            rr += __popc(recMask[q]);
+            rm += __popc(missMask[q]);
+        }
+        if (recMask[wq] & (1u << (tid & 31))) {
+            const int k = rr + __popc(recMask[wq] & below);
+            recRowOf[k] = (uint8_t)tid;
+            recIdxOf[k] = (uint8_t)((sm.img[tid * ROW_WORDS] >> 16) & 0xFFu);
+        }
+        if (missMask[wq] & (1u << (tid & 31))) erased[rm + __popc(missMask[wq] & below)] = (uint8_t)tid;
+    }
+    __syncthreads();
+
+    int st;
+    bool do_decode = false;
+    if (nb < 128) st = ST_INCOMPLETE;
+    else if (N == 0) st = ST_COMPLETE;
+    else if (flags[0] || n_missing < N) st = ST_FAILED; /* repeated original: cm256_decode refuses */
+    else if (N > DCAP) st = ST_NEEDS_BIG;
+    else {
+        st = ST_RECOVERED;
+        do_decode = true;
+    }
+
+    if (do_decode) {
+        /* coefficient matrix D [N][128 columns = image rows] */
+        if (N == 1) {
+            /* cm256's single-recovery shortcut: XOR of everything received, whatever the row */
+            for (int k = tid; k < 128 * DCAP; k += NT) sm.coefT[k] = (uint8_t)((k % DCAP) == 0 ? 1 : 0);
+        } else {
+            /* A[k][c] = M[x_k][e_c]; invert by Gauss-Jordan on [A | I] (no pivoting needed: every
+             * leading minor of a Cauchy matrix is non-zero) */
+            const int W2 = 2 * N;
+            for (int k = tid; k < N * W2; k += NT) {
+                const int r = k / W2, c = k - r * W2;
+                uint8_t v;
+                if (c < N) {
+                    const uint8_t x = recIdxOf[r], y = erased[c];
+                    v = gdiv(gfexp, gflog, (uint8_t)(y ^ 128), (uint8_t)(x ^ y));
+                } else {
+                    v = (uint8_t)((c - N) == r ? 1 : 0);
+                }
+                aug[r * W2 + c] = v;
+            }
+            __syncthreads();
+            for (int col = 0; col < N; col++) {
+                const uint8_t piv = aug[col * W2 + col];
+                __syncthreads();
+                if (piv == 0) {
+                    if (tid == 0) flags[1] = 1;
+                    break;
+                }
+                for (int c = tid; c < W2; c += NT) aug[col * W2 + c] = gdiv(gfexp, gflog, aug[col * W2 + c], piv);
+                __syncthreads();
+                for (int k = tid; k < N * W2; k += NT) {
+                    const int r = k / W2, c = k - r * W2;
+                    if (r == col || c == col) continue;
+                    const uint8_t fac = aug[r * W2 + col];
+                    aug[k] ^= gmul(gfexp, gflog, fac, aug[col * W2 + c]);
+                }
+                __syncthreads();
+                for (int r = tid; r < N; r += NT)
+                    if (r != col) aug[r * W2 + col] = 0;
+                __syncthreads();
+            }
+            __syncthreads();
+            if (flags[1]) {
+                st = ST_FAILED;
+                do_decode = false;
+            } else {
+                /* X_c = sum_k Ainv[c][k] * (rec_k ^ sum_o M[x_k][o] * orig_o) */
+                for (int k = tid; k < 128 * N; k += NT) {
+                    const int i = k / N, c = k - i * N; /* image row i, output row c */
+                    const int idx = (int)((sm.img[i * ROW_WORDS] >> 16) & 0xFFu);
+                    uint8_t v = 0;
+                    if (idx >= 128) {
+                        /* which recovery slot is image row i */
+                        const int wq = i >> 5;
+                        int kk = __popc(recMask[wq] & ((1u << (i & 31)) - 1u));
+                        for (int q = 0; q < wq; q++) kk += __popc(recMask[q]);
+                        v = aug[c * W2 + N + kk];
+                    } else if (origRow[idx] == i) {
+                        for (int kk = 0; kk < N; kk++) {
+                            const uint8_t x = recIdxOf[kk];
+                            const uint8_t m = gdiv(gfexp, gflog, (uint8_t)(idx ^ 128), (uint8_t)(x ^ idx));
+                            v ^= gmul(gfexp, gflog, aug[c * W2 + N + kk], m);
+                        }
+                    }
+                    sm.coefT[i * DCAP + c] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    uint32_t* pay = p.payload + (long long)f * 127 * 127;
+    uint32_t* b0 = p.block0 ? p.block0 + (long long)f * 127 : nullptr;
+
+    /* originals that arrived go out as they are; blocks that did not arrive read as zero (.cpp:109) */
+    for (int k = tid; k < 128 * 127; k += NT) {
+        const int b = k / 127, i = k - b * 127;
+        const int row = origRow[b];
+        const uint32_t v = row >= 0 ? sm.img[row * ROW_WORDS + 1 + i] : 0u;
+        if (b == 0) {
+            if (b0) b0[i] = v;
+        } else if (row >= 0 || !do_decode) {
+            pay[(b - 1) * 127 + i] = v;
+        }
+    }
+
+    if (do_decode) {
+        for (int row0 = 0; row0 < N; row0 += RB) {
+            const int nrows = N - row0 < RB ? N - row0 : RB;
+            for (int k = tid; k < RB * ROW_WORDS; k += NT) sm.rec16[k] = 0u;
+            __syncthreads();
+            matvec_pass(sm.img, sm.coefT, DCAP, row0, nrows, sm.tabA, sm.tabB, sm.rec16, tid);
+            __syncthreads();
+            for (int k = tid; k < nrows * 127; k += NT) {
+                const int r = k / 127, i = k - r * 127;
+                const int b = erased[row0 + r];
+                /* The reference copies back only the LAST N descriptors (.cpp:208-213), i.e. it
+                 * assumes the recovery blocks arrived after the originals; a recovery block that
+                 * arrived earlier keeps its result to itself and the erased block stays zero. */
+                const bool copied = (int)recRowOf[row0 + r] >= 128 - N;
+                const uint32_t v = copied ? sm.rec16[r * ROW_WORDS + 1 + i] : 0u;
+                if (b == 0) {
+                    if (b0) b0[i] = v;
+                } else {
+                    pay[(b - 1) * 127 + i] = v;
+                }
+            }
+            __syncthreads();
+        }
+        /* erased originals beyond the N recovered ones stay zero */
+        for (int c = N; c < n_missing; c++) {
+            const int b = erased[c];
+            for (int i = tid; i < 127; i += NT) {
+                if (b == 0) {
+                    if (b0) b0[i] = 0u;
+                } else {
+                    pay[(b - 1) * 127 + i] = 0u;
+                }
+            }
+        }
+    }
+    if (tid == 0) p.status[f] = st;
+}
+
+} /* namespace fec */
+} /* namespace sdrd */

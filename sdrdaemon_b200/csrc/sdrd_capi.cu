@@ -1,0 +1,809 @@
+/*
+ * sdrd_capi.cu -- implementation of the C ABI declared in include/sdrd_b200.h: handle management,
+ * launch geometry and the host<->device plumbing around the kernels in hb_decimate.cuh and
+ * fec_kernels.cuh.  No arithmetic of the hot path happens on the host.
+ *
+ * (The same file is compiled with -DSDRD_EMU by tests/emu to check the host logic and the kernels'
+ * indexing in a container without a GPU; that build is never part of libsdrd_b200.so.)
+ */
+#include "../../include/sdrd_b200.h"
+
+#include "fec_kernels.cuh"
+#include "gf256_host.h"
+#include "hb_decimate.cuh"
+#include "sdrd_rt.cuh"
+
+#include <sys/time.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace sdrd;
+
+#if defined(SDRD_EMU)
+thread_local sdrd_emu::Cta* sdrd_emu::t_cta = nullptr;
+thread_local sdrd_emu::Dim3 sdrd_emu::t_tid;
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+int fail_cuda(const char* what) { return fail(SDRD_ECUDA, std::string(what) + ": " + rt::last_error()); }
+
+#define SDRD_TRY(expr, what)                  \
+    do {                                      \
+        if ((expr) != 0) return fail_cuda(what); \
+    } while (0)
+
+size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+/* raw samples of input history kept per stream: two chunks of the /4-prologue cascade */
+constexpr size_t HISTW = 2 * 4 * (size_t)hb::C0;
+
+/* CRC-32/IEEE (boost::crc_32_type, UDPSinkFEC.cpp:106-109) over the 20 meta bytes -- 20 bytes per
+ * call, host side like the reference */
+uint32_t crc32_ieee(const uint8_t* p, size_t n)
+{
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) {
+        c ^= p[i];
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+    }
+    return c ^ 0xFFFFFFFFu;
+}
+
+/* ---- per-device GF(256) tables ---------------------------------------------------------- */
+struct DeviceTables {
+    fec::Tables t;
+    void* blob = nullptr;
+};
+std::mutex g_tab_mutex;
+DeviceTables g_tables[64];
+bool g_tables_ready[64];
+
+int current_device()
+{
+#if defined(SDRD_EMU)
+    return 0;
+#else
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+#endif
+}
+
+int get_tables(fec::Tables* out)
+{
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) return fail(SDRD_EINVAL, "device index out of range");
+    if (!g_tables_ready[dev]) {
+        struct Blob {
+            uint32_t tabA[256][4];
+            uint32_t tabB[256];
+            uint8_t cauchy[128 * 128];
+            uint8_t ex[512];
+            uint8_t lg[256];
+        };
+        std::vector<uint8_t> hostbuf(sizeof(Blob));
+        Blob* hb = reinterpret_cast<Blob*>(hostbuf.data());
+        gf::MulTables mt;
+        gf::build_mul_tables(mt);
+        memcpy(hb->tabA, mt.tabA, sizeof(mt.tabA));
+        memcpy(hb->tabB, mt.tabB, sizeof(mt.tabB));
+        memcpy(hb->ex, mt.exp, 512);
+        memcpy(hb->lg, mt.log, 256);
+        gf::build_cauchy_matrix(hb->cauchy);
+        void* d = nullptr;
+        if (rt::alloc(&d, sizeof(Blob)) != 0) return fail_cuda("alloc GF tables");
+        if (rt::copy(d, hb, sizeof(Blob), rt::H2D, 0) != 0 || rt::sync(0) != 0) return fail_cuda("upload GF tables");
+        Blob* db = reinterpret_cast<Blob*>(d);
+        g_tables[dev].blob = d;
+        g_tables[dev].t.tabA = reinterpret_cast<const uint4*>(&db->tabA[0][0]);
+        g_tables[dev].t.tabB = &db->tabB[0];
+        g_tables[dev].t.cauchy = &db->cauchy[0];
+        g_tables[dev].t.gfexp = &db->ex[0];
+        g_tables[dev].t.gflog = &db->lg[0];
+        g_tables_ready[dev] = true;
+    }
+    *out = g_tables[dev].t;
+    return 0;
+}
+
+/* the reference's shift rule shared by every decimateN routine (Decimators.cpp:408-409,515) */
+void shift_rule(unsigned ss, int log2_decim, int* norm_shift, int* trunk_shift, unsigned* ss_out)
+{
+    const unsigned thresh = 16u - (unsigned)log2_decim;
+    const unsigned trunk = ss < thresh ? 0u : ss - thresh;
+    const unsigned norm = ss < thresh ? thresh - ss : 0u;
+    *norm_shift = (int)norm;
+    *trunk_shift = (int)trunk;
+    *ss_out = ss + (unsigned)log2_decim - trunk;
+}
+
+template <int M>
+void launch_decimate(const hb::Params& p, int n_seg, int S, rt::stream_t st)
+{
+    SDRD_LAUNCH(hb::decimate_kernel<M>, n_seg, S, hb::NT, hb::smem_bytes(M, p.prologue), st, p);
+}
+
+} /* namespace */
+
+/* ========================================================================================== */
+
+struct sdrd_dec {
+    int log2_decim = 0, fcpos = SDRD_FC_CENTER, variant = SDRD_HB_EO1, S = 1;
+    size_t max_in = 0;
+    uint32_t* d_in = nullptr;    /* [S][in_pitch]: HISTW history words, then the new samples */
+    uint32_t* d_hist = nullptr;  /* [S][HISTW] */
+    uint32_t* d_out = nullptr;   /* [S][out_pitch] */
+    size_t in_pitch = 0, out_pitch = 0;
+    long long consumed = 0;      /* raw samples consumed since reset (saturating) */
+    long long launches = 0;
+    int sms = 148;
+    rt::stream_t stream = 0;
+};
+
+extern "C" const char* sdrd_last_error(void) { return g_err.c_str(); }
+extern "C" const char* sdrd_version(void) { return "sdrd_b200 0.1 (sm_100a)"; }
+extern "C" int sdrd_device_count(void) { return rt::device_count(); }
+extern "C" int sdrd_set_device(int device)
+{
+    if (rt::set_device(device) != 0) return fail_cuda("cudaSetDevice");
+    return 0;
+}
+
+static int check_decim(int log2_decim, int fcpos)
+{
+    if (log2_decim < 0 || log2_decim > 6) return fail(SDRD_EINVAL, "Invalid log2 decimation factor"); /* Downsampler.cpp:39-43 */
+    if (fcpos < 0 || fcpos > 2) return fail(SDRD_EINVAL, "Invalid Fc position index");               /* :57-61 */
+    return 0;
+}
+
+extern "C" int sdrd_dec_create(sdrd_dec** out, int log2_decim, int fcpos, int variant, int n_streams, size_t max_in)
+{
+    if (!out) return fail(SDRD_EINVAL, "null handle pointer");
+    *out = nullptr;
+    if (int rc = check_decim(log2_decim, fcpos)) return rc;
+    if (variant != SDRD_HB_EO1 && variant != SDRD_HB_DB) return fail(SDRD_EINVAL, "Invalid half-band variant");
+    if (n_streams < 1 || max_in < 1) return fail(SDRD_EINVAL, "n_streams and max_in must be positive");
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    sdrd_dec* d = new (std::nothrow) sdrd_dec();
+    if (!d) return fail(SDRD_ENOMEM, "out of host memory");
+    d->log2_decim = log2_decim;
+    d->fcpos = fcpos;
+    d->variant = variant;
+    d->S = n_streams;
+    d->max_in = max_in;
+    d->sms = rt::sm_count();
+    /* the kernel reads whole chunks (up to 4*C0 raw samples with the /4 prologue) */
+    d->in_pitch = HISTW + round_up(max_in, 4 * (size_t)hb::C0) + 4 * (size_t)hb::C0;
+    d->out_pitch = round_up(max_in, 8) + 8;
+    if (rt::alloc((void**)&d->d_in, d->in_pitch * 4 * (size_t)n_streams) != 0 ||
+        rt::alloc((void**)&d->d_hist, HISTW * 4 * (size_t)n_streams) != 0 ||
+        rt::alloc((void**)&d->d_out, d->out_pitch * 4 * (size_t)n_streams) != 0 || rt::stream_create(&d->stream) != 0) {
+        int rc = fail_cuda("allocating decimator buffers");
+        sdrd_dec_destroy(d);
+        return rc;
+    }
+    /* bytes past the valid samples are read by the last chunk (results discarded): keep them defined */
+    rt::fill(d->d_in, 0, d->in_pitch * 4 * (size_t)n_streams, d->stream);
+    if (int rc = sdrd_dec_reset(d)) {
+        sdrd_dec_destroy(d);
+        return rc;
+    }
+    *out = d;
+    return 0;
+}
+
+extern "C" void sdrd_dec_destroy(sdrd_dec* d)
+{
+    if (!d) return;
+    rt::sync(d->stream);
+    rt::release(d->d_in);
+    rt::release(d->d_hist);
+    rt::release(d->d_out);
+    rt::stream_destroy(d->stream);
+    delete d;
+}
+
+extern "C" int sdrd_dec_reset(sdrd_dec* d)
+{
+    if (!d) return fail(SDRD_EINVAL, "null handle");
+    SDRD_TRY(rt::fill(d->d_hist, 0, HISTW * 4 * (size_t)d->S, d->stream), "reset history");
+    SDRD_TRY(rt::sync(d->stream), "reset history");
+    d->consumed = 0;
+    return 0;
+}
+
+extern "C" int sdrd_dec_configure(sdrd_dec* d, int log2_decim, int fcpos)
+{
+    if (!d) return fail(SDRD_EINVAL, "null handle");
+    if (int rc = check_decim(log2_decim, fcpos)) return rc;
+    d->log2_decim = log2_decim;
+    d->fcpos = fcpos;
+    return 0;
+}
+extern "C" int sdrd_dec_log2_decim(const sdrd_dec* d) { return d ? d->log2_decim : -1; }
+extern "C" long long sdrd_dec_launches(const sdrd_dec* d) { return d ? d->launches : 0; }
+
+extern "C" void* sdrd_dec_dev_input(sdrd_dec* d, size_t* stride)
+{
+    if (!d) return nullptr;
+    if (stride) *stride = d->in_pitch;
+    return d->d_in + HISTW;
+}
+extern "C" void* sdrd_dec_dev_output(sdrd_dec* d, size_t* stride)
+{
+    if (!d) return nullptr;
+    if (stride) *stride = d->out_pitch;
+    return d->d_out;
+}
+
+static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_bits, rt::stream_t st)
+{
+    if (n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    const int L = d->log2_decim;
+    unsigned ss = sample_bits ? *sample_bits : 16u;
+    if (ss < 1 || ss > 16) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
+    size_t n_out = 0;
+    size_t consumed_now = 0;
+    const uint32_t* in0 = d->d_in + HISTW;
+
+    /* history of the previous calls in front of the new samples */
+    SDRD_TRY(rt::copy2d(d->d_in, d->in_pitch * 4, d->d_hist, HISTW * 4, HISTW * 4, (size_t)d->S, rt::D2D, st),
+             "restore history");
+
+    if (L == 0) {
+        /* Downsampler.cpp:76-80: copy, then decimate1's left-justification for < 16-bit sources */
+        n_out = n_in;
+        consumed_now = n_in;
+        if (n_in) {
+            hb::PlainParams p{};
+            p.in = in0; p.in_stride = (long long)d->in_pitch;
+            p.out = d->d_out; p.out_stride = (long long)d->out_pitch;
+            p.n_units = (long long)n_in; p.mode = 0;
+            p.norm_shift = ss < 16 ? (int)(16 - ss) : 0;
+            const int gx = (int)std::min<size_t>((n_in + 255) / 256, (size_t)d->sms * 8);
+            SDRD_LAUNCH(hb::plain_kernel, gx, d->S, 256, 0, st, p);
+            d->launches++;
+        }
+        /* sampleSize is left unchanged by decimate1 (Decimators.cpp:22-35) */
+    } else if (d->fcpos != SDRD_FC_CENTER && L <= 2) {
+        int norm, trunk;
+        unsigned ss_out;
+        shift_rule(ss, L, &norm, &trunk, &ss_out);
+        hb::PlainParams p{};
+        p.in = in0; p.in_stride = (long long)d->in_pitch;
+        p.out = d->d_out; p.out_stride = (long long)d->out_pitch;
+        p.supra = d->fcpos == SDRD_FC_SUPRA;
+        p.norm_shift = norm; p.trunk_shift = trunk;
+        const size_t quads = n_in / 4;
+        p.n_units = (long long)quads;
+        if (L == 1) {
+            p.mode = 1;
+            n_out = n_in / 2; /* out.resize(len/2), Decimators.cpp:41 */
+            p.n_zero_tail = (long long)(n_out - 2 * quads);
+        } else {
+            p.mode = 2;
+            n_out = quads;
+        }
+        consumed_now = quads * 4;
+        if (quads || p.n_zero_tail) {
+            const int gx = (int)std::max<size_t>(1, std::min<size_t>((quads + 255) / 256, (size_t)d->sms * 8));
+            SDRD_LAUNCH(hb::plain_kernel, gx, d->S, 256, 0, st, p);
+            d->launches++;
+        }
+        ss = ss_out;
+    } else {
+        const int pro = d->fcpos == SDRD_FC_CENTER ? 0 : (d->fcpos == SDRD_FC_INFRA ? 1 : 2);
+        const int M = pro ? L - 2 : L; /* half-band stages */
+        n_out = n_in >> L;             /* whole groups only, Decimators.cpp:412 */
+        consumed_now = n_out << L;
+        int norm, trunk;
+        unsigned ss_out;
+        shift_rule(ss, L, &norm, &trunk, &ss_out);
+        if (n_out) {
+            hb::Params p{};
+            p.in = in0; p.in_stride = (long long)d->in_pitch;
+            p.out = d->d_out; p.out_stride = (long long)d->out_pitch;
+            p.n_out = (long long)n_out;
+            p.round_add = d->variant == SDRD_HB_DB ? 1 : 0;
+            p.norm_shift = norm; p.trunk_shift = trunk;
+            p.prologue = pro;
+            p.origin = d->consumed / (pro ? 4 : 1);
+            const int out_per_chunk = hb::C0 >> M;
+            const long long total_chunks = ((long long)n_out + out_per_chunk - 1) / out_per_chunk;
+            p.warm_chunks = (61 * ((1 << M) - 1) + hb::C0 - 1) / hb::C0;
+            /* segments: enough CTAs for ~2 full waves at 2 CTAs/SM, but never so short that the
+             * warm-up chunks cost more than ~1/8 of a segment */
+            long long n_seg_max = total_chunks / (8 * p.warm_chunks);
+            if (n_seg_max < 1) n_seg_max = 1;
+            long long want = (4LL * d->sms + d->S - 1) / d->S;
+            long long n_seg = want < n_seg_max ? want : n_seg_max;
+            if (n_seg < 1) n_seg = 1;
+            long long seg_chunks = (total_chunks + n_seg - 1) / n_seg;
+            n_seg = (total_chunks + seg_chunks - 1) / seg_chunks;
+            p.seg_out = (int)(seg_chunks * out_per_chunk);
+            switch (M) {
+                case 1: launch_decimate<1>(p, (int)n_seg, d->S, st); break;
+                case 2: launch_decimate<2>(p, (int)n_seg, d->S, st); break;
+                case 3: launch_decimate<3>(p, (int)n_seg, d->S, st); break;
+                case 4: launch_decimate<4>(p, (int)n_seg, d->S, st); break;
+                case 5: launch_decimate<5>(p, (int)n_seg, d->S, st); break;
+                default: launch_decimate<6>(p, (int)n_seg, d->S, st); break;
+            }
+            d->launches++;
+        }
+        ss = ss_out;
+    }
+    if (!SDRD_LAUNCH_OK()) return fail_cuda("kernel launch");
+
+    /* the last HISTW consumed samples become the next call's history */
+    SDRD_TRY(rt::copy2d(d->d_hist, HISTW * 4, d->d_in + consumed_now, d->in_pitch * 4, HISTW * 4, (size_t)d->S, rt::D2D,
+                        st),
+             "save history");
+    d->consumed += (long long)consumed_now;
+    if (d->consumed > (1LL << 50)) d->consumed = 1LL << 50;
+    if (n_out_p) *n_out_p = n_out;
+    if (sample_bits) *sample_bits = ss;
+    return 0;
+}
+
+extern "C" int sdrd_dec_process_dev(sdrd_dec* d, size_t n_in, size_t* n_out, unsigned* sample_bits, void* cuda_stream)
+{
+    if (!d) return fail(SDRD_EINVAL, "null handle");
+    return dec_run(d, n_in, n_out, sample_bits, (rt::stream_t)cuda_stream);
+}
+
+extern "C" int sdrd_dec_process(sdrd_dec* d, const int16_t* iq_in, size_t n_in, size_t in_stride, int16_t* iq_out,
+                                size_t out_stride, size_t* n_out_p, unsigned* sample_bits)
+{
+    if (!d) return fail(SDRD_EINVAL, "null handle");
+    if ((!iq_in && n_in) || !iq_out) return fail(SDRD_EINVAL, "null sample pointer");
+    if (n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    if (d->S > 1 && in_stride < n_in) return fail(SDRD_EINVAL, "in_stride smaller than n_in");
+    SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, rt::H2D, d->stream),
+             "copy samples to device");
+    size_t n_out = 0;
+    if (int rc = dec_run(d, n_in, &n_out, sample_bits, d->stream)) return rc;
+    if (d->S > 1 && out_stride < n_out) return fail(SDRD_EINVAL, "out_stride smaller than the output length");
+    SDRD_TRY(rt::copy2d(iq_out, out_stride * 4, d->d_out, d->out_pitch * 4, n_out * 4, (size_t)d->S, rt::D2H, d->stream),
+             "copy samples to host");
+    SDRD_TRY(rt::sync(d->stream), "decimate");
+    if (n_out_p) *n_out_p = n_out;
+    return 0;
+}
+
+/* ========================================================================================== */
+/* sender                                                                                      */
+/* ========================================================================================== */
+
+struct sdrd_sink {
+    int S = 1;
+    size_t max_samples = 0;
+    uint32_t* d_samples = nullptr;  /* host-API staging [S][samples_pitch] */
+    size_t samples_pitch = 0;
+    uint32_t* d_pending = nullptr;  /* [S][FRAME_SAMPLES] */
+    int n_pending = 0;
+    uint32_t* d_dgrams = nullptr;
+    size_t dgram_words = 0;         /* allocated words */
+    size_t frame_cap = 0;           /* frames per stream a call can complete */
+    uint32_t center_freq_khz = 0, sample_rate = 0;
+    uint8_t sample_bytes = 2, sample_bits = 16;
+    int nb_fec = 0;
+    bool fixed_time = false;
+    uint32_t tv_sec = 0, tv_usec = 0;
+    uint32_t pending_meta[6] = {0, 0, 0, 0, 0, 0};
+    unsigned frame_count = 0;       /* m_frameCount, uint16 wrap */
+    long long launches = 0;
+    fec::Tables tab;
+    rt::stream_t stream = 0;
+    /* layout of the last completed call */
+    size_t last_frames = 0;
+    size_t last_dgram_stride = 0;
+};
+
+extern "C" int sdrd_sink_create(sdrd_sink** out, int n_streams, size_t max_samples)
+{
+    if (!out) return fail(SDRD_EINVAL, "null handle pointer");
+    *out = nullptr;
+    if (n_streams < 1 || max_samples < 1) return fail(SDRD_EINVAL, "n_streams and max_samples must be positive");
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    sdrd_sink* k = new (std::nothrow) sdrd_sink();
+    if (!k) return fail(SDRD_ENOMEM, "out of host memory");
+    k->S = n_streams;
+    k->max_samples = max_samples;
+    k->samples_pitch = round_up(max_samples, 4);
+    k->frame_cap = (max_samples + fec::FRAME_SAMPLES - 1) / fec::FRAME_SAMPLES + 1;
+    if (get_tables(&k->tab) != 0) {
+        delete k;
+        return SDRD_ECUDA;
+    }
+    if (rt::alloc((void**)&k->d_samples, k->samples_pitch * 4 * (size_t)n_streams) != 0 ||
+        rt::alloc((void**)&k->d_pending, (size_t)fec::FRAME_SAMPLES * 4 * (size_t)n_streams) != 0 ||
+        rt::stream_create(&k->stream) != 0) {
+        int rc = fail_cuda("allocating sink buffers");
+        sdrd_sink_destroy(k);
+        return rc;
+    }
+    *out = k;
+    return 0;
+}
+
+extern "C" void sdrd_sink_destroy(sdrd_sink* k)
+{
+    if (!k) return;
+    rt::sync(k->stream);
+    rt::release(k->d_samples);
+    rt::release(k->d_pending);
+    rt::release(k->d_dgrams);
+    rt::stream_destroy(k->stream);
+    delete k;
+}
+
+extern "C" int sdrd_sink_reset(sdrd_sink* k)
+{
+    if (!k) return fail(SDRD_EINVAL, "null handle");
+    k->n_pending = 0;
+    k->frame_count = 0;
+    return 0;
+}
+extern "C" int sdrd_sink_set_meta(sdrd_sink* k, uint32_t f_khz, uint32_t rate, uint8_t sbytes, uint8_t sbits)
+{
+    if (!k) return fail(SDRD_EINVAL, "null handle");
+    k->center_freq_khz = f_khz;
+    k->sample_rate = rate;
+    k->sample_bytes = sbytes;
+    k->sample_bits = sbits;
+    return 0;
+}
+extern "C" int sdrd_sink_set_nb_fec(sdrd_sink* k, int nb_fec)
+{
+    if (!k) return fail(SDRD_EINVAL, "null handle");
+    if (nb_fec < 0 || nb_fec > SDRD_MAX_FEC) return fail(SDRD_EINVAL, "nb_fec must be 0..128 (128 + nb_fec <= 256 blocks)");
+    k->nb_fec = nb_fec;
+    return 0;
+}
+extern "C" int sdrd_sink_set_time(sdrd_sink* k, int use_fixed, uint32_t tv_sec, uint32_t tv_usec)
+{
+    if (!k) return fail(SDRD_EINVAL, "null handle");
+    k->fixed_time = use_fixed != 0;
+    k->tv_sec = tv_sec;
+    k->tv_usec = tv_usec;
+    return 0;
+}
+extern "C" int sdrd_sink_blocks_per_frame(const sdrd_sink* k) { return k ? 128 + k->nb_fec : 0; }
+extern "C" size_t sdrd_sink_frames_for(const sdrd_sink* k, size_t n)
+{
+    return k ? ((size_t)k->n_pending + n) / fec::FRAME_SAMPLES : 0;
+}
+
+/* MetaDataFEC (include/UDPSinkFEC.h:77-99) as six little-endian words */
+static void build_meta(const sdrd_sink* k, uint32_t out[6])
+{
+    uint32_t sec = k->tv_sec, usec = k->tv_usec;
+    if (!k->fixed_time) {
+        struct timeval tv;
+        gettimeofday(&tv, 0);
+        sec = (uint32_t)tv.tv_sec;
+        usec = (uint32_t)tv.tv_usec;
+    }
+    uint8_t m[24];
+    auto put = [&](int o, uint32_t v) { m[o] = (uint8_t)v; m[o + 1] = (uint8_t)(v >> 8); m[o + 2] = (uint8_t)(v >> 16); m[o + 3] = (uint8_t)(v >> 24); };
+    put(0, k->center_freq_khz);
+    put(4, k->sample_rate);
+    m[8] = k->sample_bytes;
+    m[9] = k->sample_bits;
+    m[10] = SDRD_NB_ORIGINAL;
+    m[11] = (uint8_t)k->nb_fec;
+    put(12, sec);
+    put(16, usec);
+    put(20, crc32_ieee(m, 20));
+    memcpy(out, m, 24);
+}
+
+/* samples: device pointer, stream pitch `stride` words */
+static int sink_run(sdrd_sink* k, const uint32_t* samples, size_t stride, size_t n, size_t* n_frames_p, rt::stream_t st)
+{
+    const size_t total = (size_t)k->n_pending + n;
+    const size_t n_frames = total / fec::FRAME_SAMPLES;
+    const int new_pending = (int)(total % fec::FRAME_SAMPLES);
+    if (n_frames > k->frame_cap) return fail(SDRD_ERANGE, "write completes more frames than the handle was sized for");
+    const int F = k->nb_fec;
+    uint32_t meta_next[6];
+    build_meta(k, meta_next);
+    const size_t frame_words = (size_t)(128 + F) * fec::ROW_WORDS;
+    const size_t dgram_stride = k->frame_cap * frame_words;
+    if (n_frames) {
+        const size_t need = dgram_stride * (size_t)k->S;
+        if (need > k->dgram_words) {
+            rt::sync(st);
+            rt::release(k->d_dgrams);
+            k->d_dgrams = nullptr;
+            k->dgram_words = 0;
+            if (rt::alloc((void**)&k->d_dgrams, need * 4) != 0) return fail_cuda("allocating datagram buffer");
+            k->dgram_words = need;
+        }
+        fec::EncParams p{};
+        p.mode = 0;
+        p.F = F;
+        p.cstride = (int)std::max<size_t>(16, round_up((size_t)F, 16));
+        p.samples = samples;
+        p.sample_stride = (long long)stride;
+        p.pending = k->d_pending;
+        p.n_pending = k->n_pending;
+        memcpy(p.meta_first, k->pending_meta, 24);
+        memcpy(p.meta_next, meta_next, 24);
+        p.frame_index0 = k->frame_count;
+        p.dgrams = k->d_dgrams;
+        p.dgram_stride = (long long)dgram_stride;
+        p.tab = k->tab;
+        SDRD_LAUNCH(fec::encode_kernel, n_frames, k->S, fec::NT, fec::enc_smem_bytes(p.cstride), st, p);
+        k->launches++;
+        if (!SDRD_LAUNCH_OK()) return fail_cuda("encode kernel launch");
+    }
+    /* carry the samples of the unfinished frame (UDPSinkFEC keeps them in m_superBlock / m_txBlocks) */
+    if (n_frames == 0) {
+        SDRD_TRY(rt::copy2d(k->d_pending + k->n_pending, (size_t)fec::FRAME_SAMPLES * 4, samples, stride * 4, n * 4,
+                            (size_t)k->S, rt::D2D, st),
+                 "carry samples");
+        if (k->n_pending == 0 && n > 0) memcpy(k->pending_meta, meta_next, 24);
+    } else {
+        const size_t from = n_frames * fec::FRAME_SAMPLES - (size_t)k->n_pending;
+        SDRD_TRY(rt::copy2d(k->d_pending, (size_t)fec::FRAME_SAMPLES * 4, samples + from, stride * 4, (size_t)new_pending * 4,
+                            (size_t)k->S, rt::D2D, st),
+                 "carry samples");
+        memcpy(k->pending_meta, meta_next, 24);
+    }
+    k->n_pending = new_pending;
+    k->frame_count = (k->frame_count + (unsigned)n_frames) & 0xFFFFu;
+    k->last_frames = n_frames;
+    k->last_dgram_stride = dgram_stride;
+    if (n_frames_p) *n_frames_p = n_frames;
+    return 0;
+}
+
+static int sink_fetch(sdrd_sink* k, uint8_t* datagrams, size_t frame_capacity, size_t n_frames, rt::stream_t st)
+{
+    if (!n_frames) return 0;
+    if (!datagrams) return fail(SDRD_EINVAL, "null datagram buffer");
+    if (frame_capacity < n_frames) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of completed frames");
+    const size_t frame_bytes = (size_t)(128 + k->nb_fec) * SDRD_UDPSIZE;
+    SDRD_TRY(rt::copy2d(datagrams, frame_capacity * frame_bytes, k->d_dgrams, k->last_dgram_stride * 4, n_frames * frame_bytes,
+                        (size_t)k->S, rt::D2H, st),
+             "copy datagrams to host");
+    return 0;
+}
+
+extern "C" int sdrd_sink_write(sdrd_sink* k, const int16_t* iq, size_t n, size_t stride, uint8_t* datagrams,
+                               size_t frame_capacity, size_t* n_frames_p)
+{
+    if (!k) return fail(SDRD_EINVAL, "null handle");
+    if (!iq && n) return fail(SDRD_EINVAL, "null sample pointer");
+    if (n > k->max_samples) return fail(SDRD_ERANGE, "n_samples exceeds the max_samples given at create time");
+    SDRD_TRY(rt::copy2d(k->d_samples, k->samples_pitch * 4, iq, stride * 4, n * 4, (size_t)k->S, rt::H2D, k->stream),
+             "copy samples to device");
+    size_t n_frames = 0;
+    if (int rc = sink_run(k, k->d_samples, k->samples_pitch, n, &n_frames, k->stream)) return rc;
+    if (int rc = sink_fetch(k, datagrams, frame_capacity, n_frames, k->stream)) return rc;
+    SDRD_TRY(rt::sync(k->stream), "sink write");
+    if (n_frames_p) *n_frames_p = n_frames;
+    return 0;
+}
+
+/* ========================================================================================== */
+/* fused rx pipeline                                                                           */
+/* ========================================================================================== */
+
+struct sdrd_rx {
+    sdrd_dec* dec = nullptr;
+    sdrd_sink* sink = nullptr;
+};
+
+extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int variant, int n_streams, size_t max_in)
+{
+    if (!out) return fail(SDRD_EINVAL, "null handle pointer");
+    *out = nullptr;
+    sdrd_rx* r = new (std::nothrow) sdrd_rx();
+    if (!r) return fail(SDRD_ENOMEM, "out of host memory");
+    int rc = sdrd_dec_create(&r->dec, log2_decim, fcpos, variant, n_streams, max_in);
+    if (!rc) rc = sdrd_sink_create(&r->sink, n_streams, max_in);
+    if (rc) {
+        sdrd_rx_destroy(r);
+        return rc;
+    }
+    *out = r;
+    return 0;
+}
+extern "C" void sdrd_rx_destroy(sdrd_rx* r)
+{
+    if (!r) return;
+    sdrd_dec_destroy(r->dec);
+    sdrd_sink_destroy(r->sink);
+    delete r;
+}
+extern "C" int sdrd_rx_reset(sdrd_rx* r)
+{
+    if (!r) return fail(SDRD_EINVAL, "null handle");
+    if (int rc = sdrd_dec_reset(r->dec)) return rc;
+    return sdrd_sink_reset(r->sink);
+}
+extern "C" sdrd_dec* sdrd_rx_dec(sdrd_rx* r) { return r ? r->dec : nullptr; }
+extern "C" sdrd_sink* sdrd_rx_sink(sdrd_rx* r) { return r ? r->sink : nullptr; }
+extern "C" long long sdrd_rx_launches(const sdrd_rx* r) { return r ? r->dec->launches + r->sink->launches : 0; }
+extern "C" void* sdrd_rx_dev_datagrams(sdrd_rx* r, size_t* frame_pitch)
+{
+    if (!r) return nullptr;
+    if (frame_pitch) *frame_pitch = r->sink->frame_cap;
+    return r->sink->d_dgrams;
+}
+
+extern "C" int sdrd_rx_process_dev(sdrd_rx* r, size_t n_in, size_t* n_frames, void* cuda_stream)
+{
+    if (!r) return fail(SDRD_EINVAL, "null handle");
+    rt::stream_t st = (rt::stream_t)cuda_stream;
+    size_t n_out = 0;
+    unsigned ss = 16;
+    if (int rc = dec_run(r->dec, n_in, &n_out, &ss, st)) return rc;
+    return sink_run(r->sink, r->dec->d_out, r->dec->out_pitch, n_out, n_frames, st);
+}
+
+extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, size_t in_stride, uint8_t* datagrams,
+                               size_t frame_capacity, size_t* n_frames_p)
+{
+    if (!r) return fail(SDRD_EINVAL, "null handle");
+    if (!iq_in && n_in) return fail(SDRD_EINVAL, "null sample pointer");
+    sdrd_dec* d = r->dec;
+    if (n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    rt::stream_t st = d->stream;
+    SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, rt::H2D, st),
+             "copy samples to device");
+    size_t n_out = 0, n_frames = 0;
+    unsigned ss = 16;
+    if (int rc = dec_run(d, n_in, &n_out, &ss, st)) return rc;
+    if (int rc = sink_run(r->sink, d->d_out, d->out_pitch, n_out, &n_frames, st)) return rc;
+    if (int rc = sink_fetch(r->sink, datagrams, frame_capacity, n_frames, st)) return rc;
+    SDRD_TRY(rt::sync(st), "rx process");
+    if (n_frames_p) *n_frames_p = n_frames;
+    return 0;
+}
+
+/* ========================================================================================== */
+/* stateless CM256 encode / frame decode                                                       */
+/* ========================================================================================== */
+
+namespace {
+/* grow-only device scratch for the host-pointer entry points */
+struct Scratch {
+    void* p = nullptr;
+    size_t n = 0;
+    int ensure(size_t need)
+    {
+        if (need <= n) return 0;
+        rt::release(p);
+        p = nullptr;
+        n = 0;
+        if (rt::alloc(&p, need) != 0) return -1;
+        n = need;
+        return 0;
+    }
+};
+thread_local Scratch g_scr_a, g_scr_b, g_scr_c;
+} /* namespace */
+
+extern "C" int sdrd_cm256_encode_dev(const uint8_t* originals, size_t block_pitch, int n_frames, int recovery_count,
+                                     uint8_t* recovery, void* cuda_stream)
+{
+    /* cm256_encode's parameter checks */
+    if (recovery_count <= 0 || recovery_count > SDRD_MAX_FEC) return fail(SDRD_EINVAL, "recovery_count must be 1..128");
+    if (n_frames < 0) return fail(SDRD_EINVAL, "negative frame count");
+    if (!originals || !recovery) return fail(SDRD_EINVAL, "null block pointer");
+    if (block_pitch < SDRD_BLOCK_BYTES || (block_pitch & 3)) return fail(SDRD_EINVAL, "block_pitch must be >= 508 and a multiple of 4");
+    if (n_frames == 0) return 0;
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    fec::EncParams p{};
+    if (int rc = get_tables(&p.tab)) return rc;
+    p.mode = 1;
+    p.F = recovery_count;
+    p.cstride = (int)round_up((size_t)recovery_count, 16);
+    p.originals = originals;
+    p.block_pitch = (long long)block_pitch;
+    p.recovery = recovery;
+    rt::stream_t st = (rt::stream_t)cuda_stream;
+    SDRD_LAUNCH(fec::encode_kernel, n_frames, 1, fec::NT, fec::enc_smem_bytes(p.cstride), st, p);
+    if (!SDRD_LAUNCH_OK()) return fail_cuda("encode kernel launch");
+    return 0;
+}
+
+extern "C" int sdrd_cm256_encode(const uint8_t* originals, size_t block_pitch, int n_frames, int recovery_count,
+                                 uint8_t* recovery)
+{
+    if (recovery_count <= 0 || recovery_count > SDRD_MAX_FEC) return fail(SDRD_EINVAL, "recovery_count must be 1..128");
+    if (n_frames < 0) return fail(SDRD_EINVAL, "negative frame count");
+    if (!originals || !recovery) return fail(SDRD_EINVAL, "null block pointer");
+    if (block_pitch < SDRD_BLOCK_BYTES || (block_pitch & 3)) return fail(SDRD_EINVAL, "block_pitch must be >= 508 and a multiple of 4");
+    if (n_frames == 0) return 0;
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    const size_t in_bytes = (size_t)n_frames * 128 * block_pitch;
+    const size_t out_bytes = (size_t)n_frames * (size_t)recovery_count * SDRD_BLOCK_BYTES;
+    if (g_scr_a.ensure(in_bytes) || g_scr_b.ensure(out_bytes)) return fail_cuda("allocating scratch");
+    SDRD_TRY(rt::copy(g_scr_a.p, originals, in_bytes, rt::H2D, 0), "copy originals to device");
+    if (int rc = sdrd_cm256_encode_dev((const uint8_t*)g_scr_a.p, block_pitch, n_frames, recovery_count, (uint8_t*)g_scr_b.p, 0))
+        return rc;
+    SDRD_TRY(rt::copy(recovery, g_scr_b.p, out_bytes, rt::D2H, 0), "copy recovery blocks to host");
+    SDRD_TRY(rt::sync(0), "cm256 encode");
+    return 0;
+}
+
+extern "C" int sdrd_fec_decode_dev(const uint8_t* superblocks, size_t blocks_pitch, const int* n_blocks, int n_frames,
+                                   uint8_t* payload, uint8_t* block0, int* status, void* cuda_stream)
+{
+    if (n_frames < 0) return fail(SDRD_EINVAL, "negative frame count");
+    if (!superblocks || !n_blocks || !payload || !status) return fail(SDRD_EINVAL, "null pointer");
+    if (blocks_pitch < 1) return fail(SDRD_EINVAL, "blocks_pitch must be positive");
+    if (n_frames == 0) return 0;
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    fec::DecParams p{};
+    if (int rc = get_tables(&p.tab)) return rc;
+    p.sb = reinterpret_cast<const uint32_t*>(superblocks);
+    p.blocks_pitch = (long long)blocks_pitch;
+    p.n_blocks = n_blocks;
+    p.payload = reinterpret_cast<uint32_t*>(payload);
+    p.block0 = reinterpret_cast<uint32_t*>(block0);
+    p.status = status;
+    rt::stream_t st = (rt::stream_t)cuda_stream;
+    p.pass = 0;
+    SDRD_LAUNCH(fec::decode_kernel<32>, n_frames, 1, fec::NT, fec::dec_smem_bytes<32>(), st, p);
+    /* frames with more than 32 recovery blocks (flagged by the first pass) take the large-matrix build */
+    p.pass = 1;
+    SDRD_LAUNCH(fec::decode_kernel<128>, n_frames, 1, fec::NT, fec::dec_smem_bytes<128>(), st, p);
+    if (!SDRD_LAUNCH_OK()) return fail_cuda("decode kernel launch");
+    return 0;
+}
+
+extern "C" int sdrd_fec_decode(const uint8_t* superblocks, size_t blocks_pitch, const int* n_blocks, int n_frames,
+                               uint8_t* payload, uint8_t* block0, int* status)
+{
+    if (n_frames < 0) return fail(SDRD_EINVAL, "negative frame count");
+    if (!superblocks || !n_blocks || !payload || !status) return fail(SDRD_EINVAL, "null pointer");
+    if (blocks_pitch < 1) return fail(SDRD_EINVAL, "blocks_pitch must be positive");
+    if (n_frames == 0) return 0;
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    const size_t in_bytes = (size_t)n_frames * blocks_pitch * SDRD_UDPSIZE;
+    const size_t pay_bytes = (size_t)n_frames * 127 * SDRD_BLOCK_BYTES;
+    const size_t b0_bytes = (size_t)n_frames * SDRD_BLOCK_BYTES;
+    const size_t int_bytes = (size_t)n_frames * sizeof(int);
+    /* scratch layout: [superblocks][n_blocks][status] | [payload][block0] */
+    const size_t a_need = round_up(in_bytes, 16) + 2 * round_up(int_bytes, 16);
+    const size_t b_need = round_up(pay_bytes, 16) + round_up(b0_bytes, 16);
+    if (g_scr_a.ensure(a_need) || g_scr_b.ensure(b_need)) return fail_cuda("allocating scratch");
+    uint8_t* d_sb = (uint8_t*)g_scr_a.p;
+    int* d_nb = (int*)(d_sb + round_up(in_bytes, 16));
+    int* d_st = (int*)((uint8_t*)d_nb + round_up(int_bytes, 16));
+    uint8_t* d_pay = (uint8_t*)g_scr_b.p;
+    uint8_t* d_b0 = d_pay + round_up(pay_bytes, 16);
+    SDRD_TRY(rt::copy(d_sb, superblocks, in_bytes, rt::H2D, 0), "copy datagrams to device");
+    SDRD_TRY(rt::copy(d_nb, n_blocks, int_bytes, rt::H2D, 0), "copy block counts to device");
+    if (int rc = sdrd_fec_decode_dev(d_sb, blocks_pitch, d_nb, n_frames, d_pay, d_b0, d_st, 0)) return rc;
+    SDRD_TRY(rt::copy(payload, d_pay, pay_bytes, rt::D2H, 0), "copy payload to host");
+    if (block0) SDRD_TRY(rt::copy(block0, d_b0, b0_bytes, rt::D2H, 0), "copy meta blocks to host");
+    SDRD_TRY(rt::copy(status, d_st, int_bytes, rt::D2H, 0), "copy status to host");
+    SDRD_TRY(rt::sync(0), "fec decode");
+    return 0;
+}

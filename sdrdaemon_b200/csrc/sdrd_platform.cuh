@@ -1,0 +1,181 @@
+/*
+ * sdrd_platform.cuh -- the thin layer the kernels are written against.
+ *
+ * Product build (nvcc, sm_100a): everything below maps 1:1 onto CUDA built-ins and inline PTX
+ * (mbarrier + cp.async.bulk, i.e. the TMA 1-D bulk copy; SASS: UBLKCP / SYNCS).
+ *
+ * Test build (-DSDRD_EMU, plain g++): the SAME kernel sources are compiled for the host and each CTA
+ * is run as a group of std::threads with a std::barrier standing in for __syncthreads() and a
+ * memcpy standing in for the bulk copy.  This exists only so that the indexing / pipelining logic
+ * of the kernels can be checked against the oracle in the GPU-less build container
+ * (tests/emu/).  It is TEST INFRASTRUCTURE: the C-ABI library never contains or calls it, and the
+ * product path has no CPU fallback.
+ */
+#pragma once
+
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(SDRD_EMU)
+/* ------------------------------------------------------------------------------------------- */
+/* host emulation of the handful of CUDA facilities the kernels use                             */
+/* ------------------------------------------------------------------------------------------- */
+#include <atomic>
+#include <barrier>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+struct alignas(8) int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+
+namespace sdrd_emu {
+struct Dim3 { unsigned x = 1, y = 1, z = 1; };
+struct Cta {
+    std::barrier<>* bar;
+    unsigned char* smem;
+    Dim3 blockIdx, blockDim, gridDim;
+};
+extern thread_local Cta* t_cta;
+extern thread_local Dim3 t_tid;
+
+template <class Body>
+void launch(Dim3 grid, unsigned nthreads, size_t smem_bytes, Body body)
+{
+    for (unsigned by = 0; by < grid.y; by++)
+        for (unsigned bx = 0; bx < grid.x; bx++) {
+            std::vector<unsigned char> smem(smem_bytes + 256, (unsigned char)0xA5); /* garbage on purpose */
+            std::barrier<> bar((std::ptrdiff_t)nthreads);
+            Cta cta;
+            cta.bar = &bar;
+            cta.smem = (unsigned char*)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
+            cta.blockIdx = Dim3{bx, by, 1};
+            cta.blockDim = Dim3{nthreads, 1, 1};
+            cta.gridDim = grid;
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nthreads; t++)
+                th.emplace_back([&, t]() {
+                    t_cta = &cta;
+                    t_tid = Dim3{t, 0, 0};
+                    body();
+                });
+            for (auto& x : th) x.join();
+        }
+}
+} /* namespace sdrd_emu */
+
+#define SDRD_DEVICE static inline
+#define SDRD_KERNEL(bounds_threads, bounds_ctas) static void
+#define SDRD_RESTRICT __restrict__
+#define threadIdx (sdrd_emu::t_tid)
+#define blockIdx (sdrd_emu::t_cta->blockIdx)
+#define blockDim (sdrd_emu::t_cta->blockDim)
+#define gridDim (sdrd_emu::t_cta->gridDim)
+#define SDRD_DYN_SMEM(name) unsigned char* name = sdrd_emu::t_cta->smem
+
+static inline void __syncthreads() { sdrd_emu::t_cta->bar->arrive_and_wait(); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned atomicXor(unsigned* a, unsigned v) { return __atomic_fetch_xor(a, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicOr(unsigned* a, unsigned v) { return __atomic_fetch_or(a, v, __ATOMIC_RELAXED); }
+static inline int atomicMax(int* a, int v)
+{
+    int old = __atomic_load_n(a, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline int atomicAdd(int* a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
+{
+    /* PTX prmt, generic mode: nibble bit 3 replicates the sign of the selected byte */
+    uint64_t pool = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned sel = (s >> (4 * i)) & 0xF;
+        unsigned b = (unsigned)(pool >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) b = (b & 0x80) ? 0xFF : 0x00;
+        r |= b << (8 * i);
+    }
+    return r;
+}
+
+namespace sdrd {
+typedef std::atomic<uint64_t> mbar_t; /* completed-phase counter */
+static inline void mbar_init(mbar_t* b, int) { b->store(0, std::memory_order_relaxed); }
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(mbar_t*, uint32_t) {}
+static inline void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, mbar_t* b)
+{
+    memcpy(dst_smem, src_gmem, bytes);
+    b->fetch_add(1, std::memory_order_release);
+}
+static inline void mbar_wait(mbar_t* b, uint32_t parity)
+{
+    while (((uint32_t)b->load(std::memory_order_acquire) & 1u) == parity) std::this_thread::yield();
+}
+} /* namespace sdrd */
+
+#else
+/* ------------------------------------------------------------------------------------------- */
+/* CUDA, sm_100a                                                                                */
+/* ------------------------------------------------------------------------------------------- */
+#include <cuda_runtime.h>
+
+#define SDRD_DEVICE __device__ __forceinline__
+#define SDRD_KERNEL(bounds_threads, bounds_ctas) __global__ void __launch_bounds__(bounds_threads, bounds_ctas)
+#define SDRD_RESTRICT __restrict__
+#define SDRD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+
+namespace sdrd {
+typedef uint64_t mbar_t;
+
+SDRD_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+SDRD_DEVICE void mbar_init(mbar_t* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+/* make the initialised barriers visible to the async (TMA) proxy */
+SDRD_DEVICE void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+SDRD_DEVICE void mbar_arrive_expect_tx(mbar_t* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+/* TMA 1-D bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP.S.G). */
+SDRD_DEVICE void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, mbar_t* b)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(b))
+        : "memory");
+}
+SDRD_DEVICE void mbar_wait(mbar_t* b, uint32_t parity)
+{
+    uint32_t a = smem_u32(b);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+} /* namespace sdrd */
+#endif
+
+namespace sdrd {
+/* arithmetic shift right of a wrapping 32-bit accumulator */
+SDRD_DEVICE int asr32(uint32_t v, int sh) { return ((int)v) >> sh; }
+} /* namespace sdrd */

@@ -1,0 +1,129 @@
+/*
+ * sdrd_rt.cuh -- the few runtime services the host side of the library needs (device memory,
+ * copies, launches), CUDA in the product build, plain host memory under -DSDRD_EMU (tests/emu only,
+ * see sdrd_platform.cuh).
+ */
+#pragma once
+#include "sdrd_platform.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+namespace sdrd {
+namespace rt {
+
+enum CopyKind { H2D, D2H, D2D };
+
+#if defined(SDRD_EMU)
+
+typedef void* stream_t;
+inline bool device_ok(std::string&) { return true; }
+inline int device_count() { return 1; }
+inline int set_device(int) { return 0; }
+inline int sm_count() { return 148; }
+inline int alloc(void** p, size_t n)
+{
+    *p = malloc(n ? n : 1);
+    if (!*p) return -1;
+    memset(*p, 0xCD, n); /* cudaMalloc does not zero either */
+    return 0;
+}
+inline void release(void* p) { free(p); }
+inline int fill(void* p, int v, size_t n, stream_t) { memset(p, v, n); return 0; }
+inline int copy(void* d, const void* s, size_t n, CopyKind, stream_t) { memmove(d, s, n); return 0; }
+inline int copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, CopyKind, stream_t)
+{
+    for (size_t i = 0; i < h; i++) memmove((char*)d + i * dp, (const char*)s + i * sp, w);
+    return 0;
+}
+inline int sync(stream_t) { return 0; }
+inline int stream_create(stream_t* s) { *s = nullptr; return 0; }
+inline void stream_destroy(stream_t) {}
+inline const char* last_error() { return "emu"; }
+
+#define SDRD_LAUNCH(kernel, gx, gy, nthreads, smem, stream, params)                                            \
+    sdrd_emu::launch(sdrd_emu::Dim3{(unsigned)(gx), (unsigned)(gy), 1u}, (unsigned)(nthreads), (size_t)(smem), \
+                     [&]() { kernel(params); })
+#define SDRD_LAUNCH_OK() (true)
+
+#else
+
+typedef cudaStream_t stream_t;
+inline const char* last_error() { return cudaGetErrorString(cudaGetLastError()); }
+inline int device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp pr;
+        if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major == 10) ok++;
+    }
+    return ok;
+}
+inline bool device_ok(std::string& why)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        why = std::string("no CUDA device: ") + last_error();
+        return false;
+    }
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess) {
+        why = std::string("cudaGetDeviceProperties: ") + last_error();
+        return false;
+    }
+    if (pr.major != 10) {
+        char b[160];
+        snprintf(b, sizeof b, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", dev, pr.name,
+                 pr.major, pr.minor);
+        why = b;
+        return false;
+    }
+    return true;
+}
+inline int set_device(int d) { return cudaSetDevice(d) == cudaSuccess ? 0 : -1; }
+inline int sm_count()
+{
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+inline int alloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+inline void release(void* p) { if (p) cudaFree(p); }
+inline int fill(void* p, int v, size_t n, stream_t s) { return cudaMemsetAsync(p, v, n, s) == cudaSuccess ? 0 : -1; }
+inline cudaMemcpyKind kind_of(CopyKind k)
+{
+    return k == H2D ? cudaMemcpyHostToDevice : k == D2H ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+}
+inline int copy(void* d, const void* s, size_t n, CopyKind k, stream_t st)
+{
+    if (!n) return 0;
+    return cudaMemcpyAsync(d, s, n, kind_of(k), st) == cudaSuccess ? 0 : -1;
+}
+inline int copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, CopyKind k, stream_t st)
+{
+    if (!w || !h) return 0;
+    return cudaMemcpy2DAsync(d, dp, s, sp, w, h, kind_of(k), st) == cudaSuccess ? 0 : -1;
+}
+inline int sync(stream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
+inline int stream_create(stream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : -1; }
+inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
+
+#define SDRD_LAUNCH(kernel, gx, gy, nthreads, smem, stream, params)                                       \
+    do {                                                                                                  \
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));           \
+        kernel<<<dim3((unsigned)(gx), (unsigned)(gy), 1), dim3((unsigned)(nthreads), 1, 1), (smem), (stream)>>>(params); \
+    } while (0)
+#define SDRD_LAUNCH_OK() (cudaPeekAtLastError() == cudaSuccess)
+
+#endif
+
+} /* namespace rt */
+} /* namespace sdrd */
