@@ -137,6 +137,14 @@ size_t sdrd_sink_frames_for(const sdrd_sink* sink, size_t n_samples);
 int sdrd_sink_write(sdrd_sink* sink, const int16_t* iq, size_t n_samples, size_t stride, uint8_t* datagrams,
                     size_t frame_capacity, size_t* n_frames);
 
+/* Device-resident form: samples is a DEVICE pointer (stream pitch `stride` samples); the datagram
+ * images stay on the device at sdrd_sink_dev_datagrams() (stream pitch *frame_pitch frames of
+ * (128 + nb_fec) x 512 bytes). */
+int sdrd_sink_write_dev(sdrd_sink* sink, const void* samples, size_t n_samples, size_t stride, size_t* n_frames,
+                        void* cuda_stream);
+void* sdrd_sink_dev_datagrams(sdrd_sink* sink, size_t* frame_pitch);
+long long sdrd_sink_launches(const sdrd_sink* sink);
+
 /* ------------------------------------------------------------------------------------------
  * Fused receiver-side pipeline  TestSource -> Downsampler -> UDPSinkFEC  (sdrdaemonrx.cpp:579-663)
  *   = sdrd_dec_process feeding sdrd_sink_write without leaving HBM.

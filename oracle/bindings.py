@@ -335,3 +335,33 @@ def ref_testsource(n_samples: int, sample_rate: int, delta_phase: float, amplitu
     n = ref(HB_EO1).ref_testsource_read(buf.ctypes.data, n_samples, C.byref(ph), sample_rate, delta_phase, amplitude)
     assert n == n_samples
     return buf, ph.value
+
+
+# ----------------------------------------------------------------------------------------------
+# bench.py CPU legs (the only place outside tests/ and smoke() that may execute the oracle)
+# ----------------------------------------------------------------------------------------------
+
+def cpu_rx_streams(iq: np.ndarray, log2_decim: int, n_fec: int, n_threads: int, fcpos: int = FC_CENTER,
+                   block: int = 65536, prefer_reference: bool = True) -> Tuple[int, int, str]:
+    """Decimate -> pack -> encode every stream of iq (S, n, 2) on n_threads host threads.
+
+    Returns (superframes, digest, kind): kind "reference" when the reference's own Downsampler code
+    (oracle/_ref, EO1 build) did the decimation, "port" when the C restatement did."""
+    a = np.ascontiguousarray(iq, dtype=np.int16)
+    if a.ndim == 2:
+        a = a[None]
+    s, n, _ = a.shape
+    dig = C.c_uint32(0)
+    if prefer_reference and ref_available(HB_EO1):
+        L = ref(HB_EO1)
+        L.ref_rx_streams.restype = C.c_longlong
+        L.ref_rx_streams.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t,
+                                     C.c_size_t, C.POINTER(C.c_uint32)]
+        fr = L.ref_rx_streams(log2_decim, fcpos, n_fec, s, n_threads, a.ctypes.data, n, n, block, C.byref(dig))
+        return int(fr), int(dig.value), "reference"
+    L = lib()
+    L.sdro_rx_streams.restype = C.c_longlong
+    L.sdro_rx_streams.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                  C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32)]
+    fr = L.sdro_rx_streams(log2_decim, fcpos, HB_EO1, n_fec, s, n_threads, a.ctypes.data, n, n, block, C.byref(dig))
+    return int(fr), int(dig.value), "port"

@@ -102,6 +102,66 @@ void ref_ds_process_streams(int log2_decim, int fcpos, int n_streams, int n_thre
     for (auto& t : pool) t.join();
 }
 
+/* Whole Rx hot path on the CPU for bench.py's reference arm: per stream, the reference's
+ * Downsampler::process block by block (sdrdaemonrx.cpp:590-654) feeding the packer + encoder
+ * (oracle sink = UDPSinkFEC::write + cm256_encode restated, since cm256cc itself is not available;
+ * driving the reference's own UDPSinkFEC would add its sockets and usleep pacing).  One std::thread per
+ * stream, n_threads at a time.  Returns the number of superframes produced; *digest = XOR of all
+ * datagram words (keeps the work observable). */
+extern "C" {
+#include "sdrd_oracle.h"
+}
+struct RxAcc { long long frames; uint32_t digest; };
+static void rx_frame_cb(void* user, const uint8_t* dg, int n_blocks, uint16_t)
+{
+    RxAcc* a = (RxAcc*)user;
+    a->frames++;
+    const uint32_t* w = (const uint32_t*)dg;
+    uint32_t d = 0;
+    for (int i = 0; i < n_blocks * 128; i++) d ^= w[i];
+    a->digest ^= d;
+}
+extern "C" long long ref_rx_streams(int log2_decim, int fcpos, int nb_fec, int n_streams, int n_threads,
+                                    const int16_t* iq_in, size_t n_in_per_stream, size_t in_stride, size_t block,
+                                    uint32_t* digest)
+{
+    std::vector<std::thread> pool;
+    std::atomic<int> next(0);
+    std::atomic<long long> frames(0);
+    std::atomic<uint32_t> dig(0);
+    auto work = [&]() {
+        for (;;) {
+            int s = next.fetch_add(1);
+            if (s >= n_streams) return;
+            Downsampler ds((unsigned)log2_decim, (Downsampler::fcPos_t)fcpos);
+            RxAcc acc = {0, 0};
+            sdro_sink* sink = sdro_sink_create(rx_frame_cb, &acc);
+            sdro_sink_set_meta(sink, 435000, 625000, 2, 16);
+            sdro_sink_set_nb_fec(sink, nb_fec);
+            sdro_sink_set_time(sink, 1700000000u, 0);
+            const int16_t* in = iq_in + (size_t)s * in_stride * 2;
+            IQSampleVector vin, vout;
+            size_t done = 0;
+            while (done < n_in_per_stream) {
+                size_t n = n_in_per_stream - done < block ? n_in_per_stream - done : block;
+                vin.resize(n);
+                memcpy((void*)vin.data(), in + 2 * done, n * sizeof(IQSample));
+                unsigned ss = 16;
+                ds.process(ss, vin, vout);
+                sdro_sink_write(sink, (const int16_t*)vout.data(), vout.size());
+                done += n;
+            }
+            sdro_sink_destroy(sink);
+            frames.fetch_add(acc.frames);
+            dig.fetch_xor(acc.digest);
+        }
+    };
+    for (int t = 0; t < n_threads; t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+    if (digest) *digest = dig.load();
+    return frames.load();
+}
+
 /* ------------------------------------------------------------------ FEC buffer ----- */
 
 void* ref_fecbuf_create(void) { return new SDRdaemonFECBuffer(); }

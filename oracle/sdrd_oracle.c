@@ -382,6 +382,7 @@ struct sdro_sink {
     uint32_t tv_sec, tv_usec;
     uint8_t super_block[SDRO_UDPSIZE];             /* m_superBlock */
     uint8_t tx_blocks[256][SDRO_UDPSIZE];          /* one row of m_txBlocks */
+    uint8_t fec[256 * SDRO_BLOCK_BYTES];
     int tx_block_index;                            /* m_txBlockIndex */
     int sample_index;                              /* m_sampleIndex */
     uint16_t frame_count;                          /* m_frameCount */
@@ -389,6 +390,7 @@ struct sdro_sink {
 
 sdro_sink* sdro_sink_create(sdro_frame_cb cb, void* user)
 {
+    gf_init();
     sdro_sink* s = (sdro_sink*)calloc(1, sizeof(*s));
     s->cb = cb;
     s->user = user;
@@ -414,7 +416,7 @@ static void sink_finish_frame(sdro_sink* s)
     if (F > 0) {
         sdro_cm256_params p = {SDRO_NB_ORIGINAL, F, SDRO_BLOCK_BYTES};
         sdro_cm256_block desc[256];
-        static uint8_t fec[256 * SDRO_BLOCK_BYTES];
+        uint8_t* fec = s->fec;           /* transmitUDP's local fecBlocks[256], UDPSinkFEC.cpp:197 */
         for (int i = 0; i < SDRO_NB_ORIGINAL + F; i++) {
             if (i >= SDRO_NB_ORIGINAL) memset(s->tx_blocks[i], 0, SDRO_UDPSIZE); /* filler byte: the
                 reference leaves it uninitialised (:233-243); zero here, masked in comparisons */
@@ -599,4 +601,87 @@ int sdro_decode_frame(const uint8_t* superblocks, int n_blocks, uint8_t* payload
     if (block0) memcpy(block0, b->frame[0], SDRO_BLOCK_BYTES);
     sdro_fecbuf_destroy(b);
     return status;
+}
+
+/* ======================================================================= bench leg ==== */
+/* Whole Rx hot path (decimate -> pack -> encode) for n_streams streams on n_threads POSIX threads:
+ * the "port" CPU baseline of bench.py when the reference build (oracle/_ref) is not available. */
+#include <pthread.h>
+
+typedef struct {
+    int log2_decim, fcpos, variant, nb_fec, n_streams;
+    const int16_t* in;
+    size_t n_in, stride, block;
+    volatile int* next;
+    long long frames;
+    uint32_t digest;
+} rx_job;
+
+typedef struct { long long frames; uint32_t digest; } rx_acc;
+static void rx_cb(void* user, const uint8_t* dg, int n_blocks, uint16_t fi)
+{
+    (void)fi;
+    rx_acc* a = (rx_acc*)user;
+    const uint32_t* w = (const uint32_t*)dg;
+    uint32_t d = 0;
+    for (int i = 0; i < n_blocks * 128; i++) d ^= w[i];
+    a->frames++;
+    a->digest ^= d;
+}
+
+static void* rx_worker(void* arg)
+{
+    rx_job* j = (rx_job*)arg;
+    int16_t* out = (int16_t*)malloc(j->block * 4 + 16);
+    for (;;) {
+        int s = __sync_fetch_and_add(j->next, 1);
+        if (s >= j->n_streams) break;
+        sdro_dec* d = sdro_dec_create(j->log2_decim, j->fcpos, j->variant);
+        rx_acc acc = {0, 0};
+        sdro_sink* k = sdro_sink_create(rx_cb, &acc);
+        sdro_sink_set_meta(k, 435000, 625000, 2, 16);
+        sdro_sink_set_nb_fec(k, j->nb_fec);
+        sdro_sink_set_time(k, 1700000000u, 0);
+        const int16_t* in = j->in + (size_t)s * j->stride * 2;
+        size_t done = 0;
+        while (done < j->n_in) {
+            size_t n = j->n_in - done < j->block ? j->n_in - done : j->block;
+            unsigned ss = 16;
+            size_t no = sdro_dec_process(d, &ss, in + 2 * done, n, out);
+            sdro_sink_write(k, out, no);
+            done += n;
+        }
+        sdro_sink_destroy(k);
+        sdro_dec_destroy(d);
+        j->frames += acc.frames;
+        j->digest ^= acc.digest;
+    }
+    free(out);
+    return NULL;
+}
+
+long long sdro_rx_streams(int log2_decim, int fcpos, int variant, int nb_fec, int n_streams, int n_threads,
+                          const int16_t* iq_in, size_t n_in_per_stream, size_t in_stride, size_t block,
+                          uint32_t* digest)
+{
+    gf_init();
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    pthread_t th[256];
+    rx_job jobs[256];
+    volatile int next = 0;
+    for (int t = 0; t < n_threads; t++) {
+        rx_job j = {log2_decim, fcpos, variant, nb_fec, n_streams, iq_in, n_in_per_stream, in_stride, block, &next, 0, 0};
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, rx_worker, &jobs[t]);
+    }
+    long long frames = 0;
+    uint32_t dg = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(th[t], NULL);
+        frames += jobs[t].frames;
+        dg ^= jobs[t].digest;
+    }
+    if (digest) *digest = dg;
+    return frames;
 }

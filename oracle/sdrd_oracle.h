@@ -120,6 +120,12 @@ void         sdro_fecbuf_current_meta(const sdro_fecbuf* b, uint8_t meta20[20]);
 int sdro_decode_frame(const uint8_t* superblocks, int n_blocks, uint8_t* payload /*127*508*/,
                       uint8_t* block0 /*508, may be NULL*/);
 
+/* bench.py "port" CPU baseline: decimate -> pack -> encode for n_streams streams on n_threads threads.
+ * Returns superframes produced; *digest = XOR of all datagram words. */
+long long sdro_rx_streams(int log2_decim, int fcpos, int variant, int nb_fec, int n_streams, int n_threads,
+                          const int16_t* iq_in, size_t n_in_per_stream, size_t in_stride, size_t block,
+                          uint32_t* digest);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,9 @@ SYMBOLS = [
     ("sdrd_sink_blocks_per_frame", C.c_int, [_P]),
     ("sdrd_sink_frames_for", _SZ, [_P, _SZ]),
     ("sdrd_sink_write", C.c_int, [_P, _P, _SZ, _SZ, _P, _SZ, _SZP]),
+    ("sdrd_sink_write_dev", C.c_int, [_P, _P, _SZ, _SZ, _SZP, _P]),
+    ("sdrd_sink_dev_datagrams", _P, [_P, _SZP]),
+    ("sdrd_sink_launches", C.c_longlong, [_P]),
     ("sdrd_rx_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, _SZ]),
     ("sdrd_rx_destroy", None, [_P]),
     ("sdrd_rx_reset", C.c_int, [_P]),
@@ -273,6 +276,24 @@ class Sink:
 
     def frames_for(self, n: int) -> int:
         return self.lib.sdrd_sink_frames_for(self._h, n)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launches(self) -> int:
+        return self.lib.sdrd_sink_launches(self._h)
+
+    def write_dev(self, dev_ptr: int, n: int, stride: int, stream: int = 0) -> int:
+        nfr = C.c_size_t(0)
+        self.lib.check(self.lib.sdrd_sink_write_dev(self._h, _P(dev_ptr), n, stride, C.byref(nfr), _P(stream)))
+        return nfr.value
+
+    def dev_datagrams(self) -> Tuple[int, int]:
+        st = C.c_size_t(0)
+        p = self.lib.sdrd_sink_dev_datagrams(self._h, C.byref(st))
+        return p, st.value
 
     def write(self, iq: np.ndarray) -> np.ndarray:
         """UDPSinkFEC::write.  Returns the datagrams of the frames this call completed:

@@ -603,6 +603,21 @@ extern "C" int sdrd_sink_write(sdrd_sink* k, const int16_t* iq, size_t n, size_t
     return 0;
 }
 
+extern "C" int sdrd_sink_write_dev(sdrd_sink* k, const void* samples, size_t n, size_t stride, size_t* n_frames,
+                                   void* cuda_stream)
+{
+    if (!k) return fail(SDRD_EINVAL, "null handle");
+    if (!samples && n) return fail(SDRD_EINVAL, "null sample pointer");
+    return sink_run(k, reinterpret_cast<const uint32_t*>(samples), stride, n, n_frames, (rt::stream_t)cuda_stream);
+}
+extern "C" void* sdrd_sink_dev_datagrams(sdrd_sink* k, size_t* frame_pitch)
+{
+    if (!k) return nullptr;
+    if (frame_pitch) *frame_pitch = k->frame_cap;
+    return k->d_dgrams;
+}
+extern "C" long long sdrd_sink_launches(const sdrd_sink* k) { return k ? k->launches : 0; }
+
 /* ========================================================================================== */
 /* fused rx pipeline                                                                           */
 /* ========================================================================================== */

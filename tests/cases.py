@@ -1,0 +1,147 @@
+"""Parity cases shared by the emulation tests (CPU) and the GPU tests: every case drives the library
+through the C ABI (sdrdaemon_b200.capi) and compares with the oracle on the same seeded input."""
+from __future__ import annotations
+
+import numpy as np
+
+from sdrdaemon_b200 import capi
+
+FRAME = 127 * 127
+
+
+def rand_iq(rng, shape_n, bits=16):
+    x = rng.integers(-32768, 32768, size=tuple(shape_n) + (2,), dtype=np.int16)
+    if bits < 16:
+        x = (x >> (16 - bits)).astype(np.int16)
+    return x
+
+
+def tone_iq(n, srate, dfp, power_db=6.0, phase=0.0):
+    """TestSource::read_samples arithmetic (TestSource.cpp:395-416) without its sleep and clamp."""
+    amp = 10.0 ** (-power_db / 20.0)
+    k = np.arange(n, dtype=np.float64)
+    ph = phase + 2.0 * np.pi * dfp / srate * k
+    i = np.float32(amp) * np.cos(ph).astype(np.float32) * np.float32(32768.0)
+    q = np.float32(amp) * np.sin(ph).astype(np.float32) * np.float32(32768.0)
+    return np.stack([i.astype(np.int16), q.astype(np.int16)], axis=1)
+
+
+def input_classes(rng, n):
+    imp = np.zeros((n, 2), np.int16)
+    imp[n // 3] = (32767, -32768)
+    return {
+        "random": rand_iq(rng, (n,)),
+        "tone": tone_iq(n, 2_400_000, 100_000),
+        "impulse": imp,
+        "all_min": np.full((n, 2), -32768, np.int16),
+        "all_max": np.full((n, 2), 32767, np.int16),
+    }
+
+
+def check_decimator(lib, ob, M, fcpos, variant, x, splits, bits=16):
+    """x (S, n, 2); the stream is fed in the pieces given by `splits` (state carried across calls)."""
+    S, n, _ = x.shape
+    d = capi.Decimator(M, fcpos, variant, S, max_in=max(b - a for a, b in zip(splits[:-1], splits[1:])), lib=lib)
+    refs = [ob.Decimator(M, fcpos, variant) for _ in range(S)]
+    for a, b in zip(splits[:-1], splits[1:]):
+        y, ss = d.process(x[:, a:b], bits)
+        for s in range(S):
+            yo, sso = refs[s].process(x[s, a:b], bits)
+            assert ss == sso, f"sample size {ss} != {sso}"
+            assert y[s].shape == yo.shape, (y[s].shape, yo.shape)
+            if not np.array_equal(y[s], yo):
+                bad = np.nonzero((y[s] != yo).any(axis=1))[0]
+                raise AssertionError(f"M={M} fc={fcpos} v={variant} bits={bits} stream {s} piece [{a},{b}): "
+                                     f"{len(bad)} samples differ, first at {bad[:5]}")
+    d.close()
+
+
+def check_sink(lib, ob, F, x, splits):
+    S = x.shape[0]
+    sk = capi.Sink(n_streams=S, max_samples=max(b - a for a, b in zip(splits[:-1], splits[1:])), n_fec=F, lib=lib)
+    refs = [ob.Sink(n_fec=F) for _ in range(S)]
+    got = []
+    for a, b in zip(splits[:-1], splits[1:]):
+        got.append(sk.write(x[:, a:b]))
+        for s in range(S):
+            refs[s].write(x[s, a:b])
+    g = np.concatenate(got, axis=1)
+    for s in range(S):
+        want = np.stack(refs[s].frames) if refs[s].frames else np.zeros((0, 128 + F, 512), np.uint8)
+        assert g[s].shape == want.shape, (g[s].shape, want.shape)
+        assert np.array_equal(g[s], want), f"F={F} stream {s}: datagrams differ"
+    sk.close()
+    return g
+
+
+def make_frames(ob, rng, n_frames, F):
+    x = rand_iq(rng, (FRAME * n_frames,))
+    sk = ob.Sink(n_fec=F)
+    sk.write(x)
+    return x, np.stack(sk.frames)
+
+
+def erasure_cases(rng, frames, F):
+    """A list of per-frame received-datagram index lists exercising every branch of the receiver."""
+    cases = []
+    n = len(frames)
+    for f in range(n):
+        k = f % 12
+        if k == 0:
+            sel = list(range(128))
+        elif k == 1:
+            sel = list(range(100))
+        elif k == 2:
+            sel = [i for i in range(128) if i != 101] + [128]
+        elif k == 3:
+            sel = [i for i in range(128) if i != 5] + [128 + min(3, F - 1)]
+        elif k == 4:
+            ne = min(20, F)
+            er = set(rng.choice(128, ne, replace=False).tolist())
+            sel = [i for i in range(128) if i not in er] + list(range(128, 128 + ne))
+        elif k == 5:
+            ne = min(20, F)
+            er = set(rng.choice(128, ne, replace=False).tolist())
+            sel = [i for i in range(128) if i not in er] + rng.choice(np.arange(128, 128 + F), ne, replace=False).tolist()
+            rng.shuffle(sel)
+            sel = [int(v) for v in sel]
+        elif k == 6:
+            ne = F
+            er = set(rng.choice(np.arange(1, 128), ne - 1, replace=False).tolist()) | {0}
+            sel = [i for i in range(128) if i not in er] + list(range(128, 128 + ne))
+        elif k == 7:
+            sel = list(range(1, 128)) + [3]
+        elif k == 8:
+            sel = list(range(2, 128)) + [3, 128 + min(2, F - 1)]
+        elif k == 9:
+            sel = list(range(128)) + [128, 128 + min(1, F - 1)]
+        elif k == 10:
+            ne = min(16, F)
+            er = set(rng.choice(128, ne, replace=False).tolist())
+            sel = [i for i in range(128) if i not in er] + list(range(128, 128 + ne))
+        else:
+            ne = min(33, F)
+            er = set(rng.choice(128, ne, replace=False).tolist())
+            sel = [i for i in range(128) if i not in er] + list(range(128 + F - ne, 128 + F))
+        cases.append(sel)
+    return cases
+
+
+def pack_received(frames, cases):
+    pitch = max(len(c) for c in cases)
+    sb = np.zeros((len(cases), pitch, 512), np.uint8)
+    nb = np.zeros(len(cases), np.int32)
+    for f, sel in enumerate(cases):
+        sb[f, : len(sel)] = frames[f][sel]
+        nb[f] = len(sel)
+    return sb, nb
+
+
+def check_decode(lib, ob, sb, nb):
+    pay, b0, st = capi.fec_decode(sb, nb, lib=lib)
+    for f in range(len(nb)):
+        so, po, bo = ob.decode_frame(sb[f, : nb[f]])
+        assert st[f] == so, f"frame {f}: status {st[f]} != {so}"
+        assert np.array_equal(pay[f], po), f"frame {f}: payload differs"
+        assert np.array_equal(b0[f], bo), f"frame {f}: block 0 differs"
+    return pay, b0, st

@@ -1,0 +1,89 @@
+"""Kernel logic and library host logic, checked on the CPU through the host emulation build of the
+very same sources (tests/emu): parity with the oracle at small sizes.  The GPU tests repeat these
+cases (and larger ones) on the product library."""
+import numpy as np
+import pytest
+
+import cases
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 6])
+def test_decimator_centre_eo1(emu_lib, oracle, M):
+    rng = np.random.default_rng(100 + M)
+    n = 30000
+    x = cases.rand_iq(rng, (2, n))
+    cases.check_decimator(emu_lib, oracle, M, 2, 0, x, [0, 4096, 4096 + 12345, n])
+
+
+@pytest.mark.parametrize("M,fcpos,variant,bits", [(0, 2, 0, 12), (0, 2, 0, 16), (1, 0, 0, 16), (1, 1, 1, 8), (2, 0, 0, 12),
+                                                  (2, 1, 0, 16), (3, 0, 0, 16), (4, 1, 1, 12), (6, 0, 1, 8), (5, 2, 1, 16),
+                                                  (4, 2, 1, 16), (6, 1, 0, 16)])
+def test_decimator_variants(emu_lib, oracle, M, fcpos, variant, bits):
+    rng = np.random.default_rng(200 + 10 * M + fcpos)
+    n = 24000
+    x = cases.rand_iq(rng, (1, n), bits)
+    cases.check_decimator(emu_lib, oracle, M, fcpos, variant, x, [0, 777, 10000, n], bits)
+
+
+def test_decimator_input_classes(emu_lib, oracle):
+    rng = np.random.default_rng(300)
+    for name, x in cases.input_classes(rng, 16384).items():
+        cases.check_decimator(emu_lib, oracle, 4, 2, 0, x[None], [0, 5000, 16384])
+
+
+def test_decimator_short_and_empty(emu_lib, oracle):
+    rng = np.random.default_rng(301)
+    x = cases.rand_iq(rng, (1, 1000))
+    cases.check_decimator(emu_lib, oracle, 6, 2, 0, x, [0, 10, 10, 70, 135, 1000])  # below one group, empty, ragged
+
+
+@pytest.mark.parametrize("F", [0, 1, 16, 32, 40])
+def test_sink_framing_and_encode(emu_lib, oracle, F):
+    rng = np.random.default_rng(400 + F)
+    n = cases.FRAME * 2 + 700
+    x = cases.rand_iq(rng, (2, n))
+    cases.check_sink(emu_lib, oracle, F, x, [0, 1000, 1000 + cases.FRAME, n])
+
+
+def test_cm256_encode_raw(emu_lib, oracle):
+    from sdrdaemon_b200 import capi
+
+    rng = np.random.default_rng(500)
+    o = rng.integers(0, 256, size=(2, 128, 508), dtype=np.uint8)
+    for F in (1, 7, 32):
+        r = capi.cm256_encode(o, F, lib=emu_lib)
+        want = np.stack([oracle.cm256_encode(o[f], F) for f in range(2)])
+        assert np.array_equal(r, want)
+    with pytest.raises(capi.SdrdError):
+        capi.cm256_encode(o, 0, lib=emu_lib)
+    with pytest.raises(capi.SdrdError):
+        capi.cm256_encode(o, 129, lib=emu_lib)
+
+
+def test_decode_all_branches(emu_lib, oracle):
+    rng = np.random.default_rng(600)
+    F = 40
+    x, frames = cases.make_frames(oracle, rng, 12, F)
+    sel = cases.erasure_cases(rng, frames, F)
+    sb, nb = cases.pack_received(frames, sel)
+    pay, b0, st = cases.check_decode(emu_lib, oracle, sb, nb)
+    assert list(st) == [1, 0, 2, 2, 2, 2, 2, 1, -1, 1, 2, 2]
+    # in-order recoveries return the transmitted samples
+    for f in (0, 2, 4, 6, 10, 11):
+        assert np.array_equal(pay[f].reshape(-1), x[f * cases.FRAME:(f + 1) * cases.FRAME].view(np.uint8).reshape(-1))
+
+
+def test_rx_pipeline(emu_lib, oracle):
+    from sdrdaemon_b200 import capi
+
+    rng = np.random.default_rng(700)
+    M, F, S = 2, 16, 2
+    n = (cases.FRAME + 300) << M
+    x = cases.rand_iq(rng, (S, 2 * n))
+    rx = capi.Rx(M, n_streams=S, max_in=n, n_fec=F, lib=emu_lib)
+    got = np.concatenate([rx.process(x[:, :n]), rx.process(x[:, n:])], axis=1)
+    for s in range(S):
+        y, _ = oracle.Decimator(M).process(x[s])
+        sk = oracle.Sink(n_fec=F)
+        sk.write(y)
+        assert np.array_equal(got[s], np.stack(sk.frames))
