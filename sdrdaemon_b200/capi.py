@@ -108,7 +108,8 @@ def load(path: Optional[str] = None) -> Library:
     if path is not None:
         return Library(path)
     if _default is None:
-        _default = Library()
+        # SDRD_B200_LIB: alternative build of the same library (kernel tuning experiments)
+        _default = Library(os.environ.get("SDRD_B200_LIB") or None)
     return _default
 
 

@@ -36,9 +36,6 @@
 namespace sdrd {
 namespace hb {
 
-constexpr int C0 = 2048;    /* cascade-input samples per chunk */
-constexpr int NT = 256;     /* threads per CTA */
-constexpr int HIST = 4096;  /* raw samples of history kept in front of a stream's input (>= warm-up) */
 constexpr int TAIL = 32;    /* entries (per parity) of the previous chunk kept in front of a slot */
 constexpr int MAX_STAGES = 6;
 
@@ -48,7 +45,7 @@ constexpr int MAX_STAGES = 6;
 constexpr int HB_SHIFT = 13; /* hbShift - 1, EO1.h:145 */
 
 struct Params {
-    const uint32_t* in;    /* stream s, raw sample i (i >= -HIST*prologue_factor): in[s * in_stride + i] */
+    const uint32_t* in;    /* stream s, raw sample i (may be negative: history): in[s * in_stride + i] */
     long long in_stride;   /* words */
     uint32_t* out;         /* out[s * out_stride + n] */
     long long out_stride;  /* words */
@@ -59,33 +56,63 @@ struct Params {
     int norm_shift, trunk_shift;
     int prologue;          /* 0: centred; 1: infradyne /4; 2: supradyne /4 in front of the cascade */
     long long origin;      /* cascade-input samples consumed since reset (only consulted when round_add) */
+    uint32_t steer_zero, steer_one, steer_k32, steer_k256, steer_k8192; /* 0, 1, 32, 256, 8192: see Steer */
 };
 
-SDRD_DEVICE constexpr int stage_base(int m) { return 5 * (TAIL * m + C0 - (C0 >> m)); }
-SDRD_DEVICE constexpr int region_phys(int m) { return ((TAIL + (C0 >> (m + 1))) >> 3) * 10; }
-constexpr int RAW_BYTES = 2 * C0 * 4;
-constexpr int BAR_OFFSET = 4 * RAW_BYTES; /* room for the /4 prologue's 4x larger raw chunks */
-constexpr int STAGE_OFFSET_CEN = RAW_BYTES + 128;
-constexpr int STAGE_OFFSET_PRO = 4 * RAW_BYTES + 128;
+/* Geometry for a chunk of C0 cascade-input samples handled by C0/8 threads. */
+template <int C0>
+struct Geo {
+    static constexpr int NT = C0 / 8;
+    static constexpr int LOG2_2N1 = (C0 == 512 ? 6 : C0 == 1024 ? 7 : 8); /* log2(C0 / 8) */
+    static_assert(C0 == 512 || C0 == 1024 || C0 == 2048, "supported chunk sizes");
+    SDRD_HD static constexpr int stage_base(int m) { return 5 * (TAIL * m + C0 - (C0 >> m)); }
+    SDRD_HD static constexpr int region_phys(int m) { return ((TAIL + (C0 >> (m + 1))) >> 3) * 10; }
+    /* [T | S] region of stage m's output buffer: parity eo (0 = even samples), double-buffer slot */
+    SDRD_HD static int2* region(int2* sbuf, int m, int eo, int slot)
+    {
+        return sbuf + stage_base(m) + (eo * 2 + slot) * region_phys(m);
+    }
+    SDRD_HD static constexpr size_t raw_bytes(int prologue) { return (size_t)2 * (prologue ? 4 : 1) * C0 * 4; }
+    SDRD_HD static constexpr size_t smem_bytes(int M, int prologue)
+    {
+        return raw_bytes(prologue) + 128 + (size_t)(5 * (TAIL * M + C0 - (C0 >> M))) * 8;
+    }
+};
 
-inline constexpr size_t smem_bytes(int M, int prologue)
+/* chunk size used for an M-stage cascade: the last stage's input needs >= TAIL entries per chunk
+ * (C0 >= 32 * 2^M); smaller chunks mean smaller CTAs and more of them per SM */
+#ifndef SDRD_HB_C0_MIN
+#define SDRD_HB_C0_MIN 1024 /* build-time floor, for experiments */
+#endif
+constexpr int chunk_for(int M)
 {
-    return (size_t)(prologue ? STAGE_OFFSET_PRO : STAGE_OFFSET_CEN) + (size_t)(5 * (TAIL * M + C0 - (C0 >> M))) * 8;
+    return (M == 6 || SDRD_HB_C0_MIN >= 2048) ? 2048 : ((M == 5 || SDRD_HB_C0_MIN >= 1024) ? 1024 : 512);
 }
 
-/* [T | S] region of stage m's output buffer: parity eo (0 = even samples), double-buffer slot */
-SDRD_DEVICE int2* region(int2* sbuf, int m, int eo, int slot)
-{
-    return sbuf + stage_base(m) + (eo * 2 + slot) * region_phys(m);
-}
 /* logical entry -> physical entry (8 -> 10 padding) */
 SDRD_DEVICE int phys(int k) { return k + 2 * (k >> 3); }
+
+/* Pipe steering.  The FIR body is issue-bound: per output and component 16 pre-adds + 16
+ * multiply-accumulates.  Left alone, ptxas turns about half of the pre-adds into IMAD.IADD, which
+ * piles them onto the FMA pipe next to the IMADs (measured: fmaheavy 66 % busy, ALU 39 %, long
+ * same-pipe runs).  `Steer` carries run-time constants the compiler cannot fold:
+ *   zero   added as the THIRD operand of a pre-add  -> IADD3 with three sources, ALU pipe only;
+ *   one    multiplier of an add written as IMAD      -> FMA pipe;
+ *   k32, k256, k8192  multipliers of the power-of-two taps / centre tap -> IMAD instead of LEA.
+ * Which taps use which form is fixed below so that ALU and FMA work per output are equal. */
+struct Steer {
+    uint32_t zero, one, k32, k256, k8192;
+};
+
+#ifndef SDRD_HB_FMA_ADD_TAPS
+#define SDRD_HB_FMA_ADD_TAPS 1 /* taps (outermost first) whose pre-add runs on the FMA pipe */
+#endif
 
 /* 8 consecutive outputs n0 .. n0+7 (n0 = 8 i, chunk-local) of one half-band stage.
  * srcE/srcO point at the [T | S] region of the consumed chunk: logical entry TAIL + k is
  * E[k] = x[2k] resp. O[k] = x[2k+1] of the chunk, entries 0..TAIL-1 the previous chunk's tail. */
 SDRD_DEVICE void fir8(const int2* SDRD_RESTRICT srcE, const int2* SDRD_RESTRICT srcO, int i, uint32_t acc0,
-                      int2 (&y)[8])
+                      const Steer st, int2 (&y)[8])
 {
     constexpr int H[16] = SDRD_HB64_TAPS;
     /* y[n] needs O[n-31 .. n] and E[n-15].  Window w[j] = O[n0 - 32 + j], j = 0..39: logical entries
@@ -114,10 +141,19 @@ SDRD_DEVICE void fir8(const int2* SDRD_RESTRICT srcE, const int2* SDRD_RESTRICT 
 #pragma unroll
         for (int t = 0; t < 16; t++) {
             /* O[n - t] = w[32 + r - t], O[n - 31 + t] = w[1 + r + t] */
-            uint32_t sI = (uint32_t)w[32 + r - t].x + (uint32_t)w[1 + r + t].x;
-            uint32_t sQ = (uint32_t)w[32 + r - t].y + (uint32_t)w[1 + r + t].y;
-            aI[r] += sI * (uint32_t)H[t];
-            aQ[r] += sQ * (uint32_t)H[t];
+            const uint32_t aIx = (uint32_t)w[32 + r - t].x, bIx = (uint32_t)w[1 + r + t].x;
+            const uint32_t aQx = (uint32_t)w[32 + r - t].y, bQx = (uint32_t)w[1 + r + t].y;
+            uint32_t sI, sQ;
+            if (t < SDRD_HB_FMA_ADD_TAPS) {
+                sI = mad_lo(aIx, st.one, bIx);
+                sQ = mad_lo(aQx, st.one, bQx);
+            } else {
+                sI = add3(aIx, bIx, st.zero);
+                sQ = add3(aQx, bQx, st.zero);
+            }
+            const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
+            aI[r] = mad_lo(sI, h, aI[r]);
+            aQ[r] = mad_lo(sQ, h, aQ[r]);
         }
     }
     /* centre taps E[n0 - 15 + r]: logical entries 8i + 17 + r -> group i+2 (entries 16..23) and the
@@ -134,8 +170,8 @@ SDRD_DEVICE void fir8(const int2* SDRD_RESTRICT srcE, const int2* SDRD_RESTRICT 
         e[8] = srcE[10 * (i + 3)];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            aI[r] += (uint32_t)e[1 + r].x << HB_SHIFT;
-            aQ[r] += (uint32_t)e[1 + r].y << HB_SHIFT;
+            aI[r] = mad_lo((uint32_t)e[1 + r].x, st.k8192, aI[r]);
+            aQ[r] = mad_lo((uint32_t)e[1 + r].y, st.k8192, aQ[r]);
             y[r] = make_int2(asr32(aI[r], HB_SHIFT), asr32(aQ[r], HB_SHIFT));
         }
     }
@@ -154,9 +190,12 @@ SDRD_DEVICE int2 rot4(uint4 v, int prologue)
     return make_int2(i0 - r1 - i2 + r3, -r0 - i1 + r2 + i3);
 }
 
-template <int M>
-SDRD_KERNEL(NT, 2) decimate_kernel(Params p)
+template <int M, int C0>
+SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
 {
+    typedef Geo<C0> G;
+    constexpr int NT = G::NT;
+    static_assert((C0 >> M) >= TAIL, "chunk too small for this many stages");
     SDRD_DYN_SMEM(smem);
     const int tid = (int)threadIdx.x;
     const int seg = (int)blockIdx.x;
@@ -164,8 +203,8 @@ SDRD_KERNEL(NT, 2) decimate_kernel(Params p)
     const int pro = p.prologue;
     const int raw_per_chunk = pro ? 4 * C0 : C0; /* raw samples feeding one chunk of cascade input */
     uint32_t* raw = reinterpret_cast<uint32_t*>(smem);
-    mbar_t* bars = reinterpret_cast<mbar_t*>(smem + (pro ? 4 * RAW_BYTES : RAW_BYTES));
-    int2* sbuf = reinterpret_cast<int2*>(smem + (pro ? STAGE_OFFSET_PRO : STAGE_OFFSET_CEN));
+    mbar_t* bars = reinterpret_cast<mbar_t*>(smem + G::raw_bytes(pro));
+    int2* sbuf = reinterpret_cast<int2*>(smem + G::raw_bytes(pro) + 128);
 
     constexpr int out_per_chunk = C0 >> M;
     const long long seg_first_out = (long long)seg * p.seg_out;
@@ -180,6 +219,22 @@ SDRD_KERNEL(NT, 2) decimate_kernel(Params p)
     const long long abs0 = p.origin + first_in;
     const uint32_t acc0 = (uint32_t)p.round_add << HB_SHIFT;
     const uint32_t chunk_bytes = (uint32_t)raw_per_chunk * 4u;
+    const Steer steer = {p.steer_zero, p.steer_one, p.steer_k32, p.steer_k256, p.steer_k8192};
+
+    /* ---- this thread's fixed role: FIR task t = tid of every step (stage j+1, outputs 8i..8i+7 of
+     *      the chunk); there are C0/8 * (1 - 2^-M) < NT tasks per step ---- */
+    constexpr int two_n1 = C0 / 8;
+    constexpr int n_tasks = two_n1 - (two_n1 >> M);
+    const bool has_task = tid < n_tasks;
+    const int tj = has_task ? __clz(two_n1 - 1 - tid) - (32 - G::LOG2_2N1) : 0;
+    const int ti = tid - (two_n1 - (two_n1 >> tj));
+    const bool t_final = tj + 1 == M;
+    const int2* const t_srcE = G::region(sbuf, tj, 0, 0);
+    const int2* const t_srcO = G::region(sbuf, tj, 1, 0);
+    const int t_src_slot = G::region_phys(tj);           /* entries between slot 0 and slot 1 */
+    int2* const t_dstE = G::region(sbuf, t_final ? tj : tj + 1, 0, 0) + phys(TAIL + 4 * ti);
+    int2* const t_dstO = G::region(sbuf, t_final ? tj : tj + 1, 1, 0) + phys(TAIL + 4 * ti);
+    const int t_dst_slot = G::region_phys(t_final ? tj : tj + 1);
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -199,10 +254,12 @@ SDRD_KERNEL(NT, 2) decimate_kernel(Params p)
         if (u < NC) {
             mbar_wait(&bars[u & 1], (uint32_t)((u >> 1) & 1));
             const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)(u & 1) * raw_per_chunk);
-            int2* E0 = region(sbuf, 0, 0, u & 1);
-            int2* O0 = region(sbuf, 0, 1, u & 1);
+            int2* E0 = G::region(sbuf, 0, 0, u & 1);
+            int2* O0 = G::region(sbuf, 0, 1, u & 1);
             if (!pro) {
-                for (int q = tid; q < C0 / 4; q += NT) {
+#pragma unroll
+                for (int qq = 0; qq < 2; qq++) {
+                    const int q = tid + qq * NT;
                     uint4 v = r4[q];
                     int ph = phys(TAIL + 2 * q);
                     *reinterpret_cast<int4*>(E0 + ph) = make_int4(s16lo(v.x), s16hi(v.x), s16lo(v.z), s16hi(v.z));
@@ -220,38 +277,31 @@ SDRD_KERNEL(NT, 2) decimate_kernel(Params p)
             }
         }
 
-        /* ---- half-band tasks: stage j+1 consumes stage-j chunk u-1-j ---- */
-        constexpr int n_tasks = 256 - (256 >> M); /* C0/16 * 2 * (1 - 2^-M) */
-        for (int t = tid; t < n_tasks; t += NT) {
-            const int j = __clz(255 - t) - 24;
-            const int i = t - (256 - (256 >> j));
-            const int c = u - 1 - j;
-            if (c < 0 || c >= NC) continue;
+        /* ---- half-band task: stage tj+1 consumes stage-tj chunk u-1-tj ---- */
+        const int c = u - 1 - tj;
+        if (has_task && c >= 0 && c < NC) {
             const int slot = c & 1;
             int2 y[8];
-            fir8(region(sbuf, j, 0, slot), region(sbuf, j, 1, slot), i, acc0, y);
+            fir8(t_srcE + slot * t_src_slot, t_srcO + slot * t_src_slot, ti, acc0, steer, y);
             if (p.round_add) {
                 /* DB: the reference's stages start from all-zero state, but a DB stage maps zero
                  * input to 1; outputs that lie before the stream origin must read as 0. */
-                const long long a = ((abs0 + (long long)c * C0) >> (j + 1)) + 8 * i;
+                const long long a = ((abs0 + (long long)c * C0) >> (tj + 1)) + 8 * ti;
                 if (a < 0) {
 #pragma unroll
                     for (int r = 0; r < 8; r++)
                         if (a + r < 0) y[r] = make_int2(0, 0);
                 }
             }
-            if (j + 1 < M) {
-                int2* dE = region(sbuf, j + 1, 0, slot);
-                int2* dO = region(sbuf, j + 1, 1, slot);
-                const int ph = phys(TAIL + 4 * i);
-                int4* qe = reinterpret_cast<int4*>(dE + ph);
-                int4* qo = reinterpret_cast<int4*>(dO + ph);
+            if (!t_final) {
+                int4* qe = reinterpret_cast<int4*>(t_dstE + slot * t_dst_slot);
+                int4* qo = reinterpret_cast<int4*>(t_dstO + slot * t_dst_slot);
                 qe[0] = make_int4(y[0].x, y[0].y, y[2].x, y[2].y);
                 qe[1] = make_int4(y[4].x, y[4].y, y[6].x, y[6].y);
                 qo[0] = make_int4(y[1].x, y[1].y, y[3].x, y[3].y);
                 qo[1] = make_int4(y[5].x, y[5].y, y[7].x, y[7].y);
             } else if (c >= p.warm_chunks) {
-                const long long n = seg_first_out + (long long)(c - p.warm_chunks) * out_per_chunk + 8 * i;
+                const long long n = seg_first_out + (long long)(c - p.warm_chunks) * out_per_chunk + 8 * ti;
                 uint32_t o[8];
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
@@ -275,11 +325,11 @@ SDRD_KERNEL(NT, 2) decimate_kernel(Params p)
          *      other slot, where the next chunk's consumer expects its history ---- */
         for (int t = tid; t < 32 * M; t += NT) {
             const int j = t >> 5, eo = (t >> 4) & 1, unit = t & 15;
-            const int c = u - 1 - j;
-            if (c < 0 || c >= NC) continue;
+            const int cc = u - 1 - j;
+            if (cc < 0 || cc >= NC) continue;
             const int n = C0 >> (j + 1);
-            const int4* sp = reinterpret_cast<const int4*>(region(sbuf, j, eo, c & 1) + phys(n)); /* entry TAIL+n-32 */
-            int4* dp = reinterpret_cast<int4*>(region(sbuf, j, eo, (c & 1) ^ 1));
+            const int4* sp = reinterpret_cast<const int4*>(G::region(sbuf, j, eo, cc & 1) + phys(n)); /* entry TAIL+n-32 */
+            int4* dp = reinterpret_cast<int4*>(G::region(sbuf, j, eo, (cc & 1) ^ 1));
             /* 4 padded groups of 8 entries: 5 int4 per group, the first 4 carry data */
             dp[(unit >> 2) * 5 + (unit & 3)] = sp[(unit >> 2) * 5 + (unit & 3)];
         }

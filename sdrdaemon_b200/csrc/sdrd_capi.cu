@@ -47,7 +47,8 @@ int fail_cuda(const char* what) { return fail(SDRD_ECUDA, std::string(what) + ":
 size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
 /* raw samples of input history kept per stream: two chunks of the /4-prologue cascade */
-constexpr size_t HISTW = 2 * 4 * (size_t)hb::C0;
+constexpr size_t HISTW = 16384;
+constexpr size_t MAX_CHUNK_RAW = 4 * 2048; /* largest raw chunk the kernel reads: /4 prologue, C0 = 2048 */
 
 /* CRC-32/IEEE (boost::crc_32_type, UDPSinkFEC.cpp:106-109) over the 20 meta bytes -- 20 bytes per
  * call, host side like the reference */
@@ -133,7 +134,8 @@ void shift_rule(unsigned ss, int log2_decim, int* norm_shift, int* trunk_shift, 
 template <int M>
 void launch_decimate(const hb::Params& p, int n_seg, int S, rt::stream_t st)
 {
-    SDRD_LAUNCH(hb::decimate_kernel<M>, n_seg, S, hb::NT, hb::smem_bytes(M, p.prologue), st, p);
+    constexpr int C0 = hb::chunk_for(M);
+    SDRD_LAUNCH((hb::decimate_kernel<M, C0>), n_seg, S, hb::Geo<C0>::NT, hb::Geo<C0>::smem_bytes(M, p.prologue), st, p);
 }
 
 } /* namespace */
@@ -187,7 +189,7 @@ extern "C" int sdrd_dec_create(sdrd_dec** out, int log2_decim, int fcpos, int va
     d->max_in = max_in;
     d->sms = rt::sm_count();
     /* the kernel reads whole chunks (up to 4*C0 raw samples with the /4 prologue) */
-    d->in_pitch = HISTW + round_up(max_in, 4 * (size_t)hb::C0) + 4 * (size_t)hb::C0;
+    d->in_pitch = HISTW + round_up(max_in, MAX_CHUNK_RAW) + MAX_CHUNK_RAW;
     d->out_pitch = round_up(max_in, 8) + 8;
     if (rt::alloc((void**)&d->d_in, d->in_pitch * 4 * (size_t)n_streams) != 0 ||
         rt::alloc((void**)&d->d_hist, HISTW * 4 * (size_t)n_streams) != 0 ||
@@ -322,14 +324,17 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
             p.norm_shift = norm; p.trunk_shift = trunk;
             p.prologue = pro;
             p.origin = d->consumed / (pro ? 4 : 1);
-            const int out_per_chunk = hb::C0 >> M;
+            p.steer_zero = 0; p.steer_one = 1; p.steer_k32 = 32; p.steer_k256 = 256; p.steer_k8192 = 8192;
+            const int C0 = hb::chunk_for(M);
+            const int out_per_chunk = C0 >> M;
             const long long total_chunks = ((long long)n_out + out_per_chunk - 1) / out_per_chunk;
-            p.warm_chunks = (61 * ((1 << M) - 1) + hb::C0 - 1) / hb::C0;
-            /* segments: enough CTAs for ~2 full waves at 2 CTAs/SM, but never so short that the
+            p.warm_chunks = (61 * ((1 << M) - 1) + C0 - 1) / C0;
+            /* segments: enough CTAs for ~2 full waves of resident CTAs, but never so short that the
              * warm-up chunks cost more than ~1/8 of a segment */
             long long n_seg_max = total_chunks / (8 * p.warm_chunks);
             if (n_seg_max < 1) n_seg_max = 1;
-            long long want = (4LL * d->sms + d->S - 1) / d->S;
+            const int ctas_per_sm = 512 / (C0 / 8);
+            long long want = (2LL * ctas_per_sm * d->sms + d->S - 1) / d->S;
             long long n_seg = want < n_seg_max ? want : n_seg_max;
             if (n_seg < 1) n_seg = 1;
             long long seg_chunks = (total_chunks + n_seg - 1) / n_seg;

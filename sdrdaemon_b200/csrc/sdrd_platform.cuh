@@ -71,6 +71,7 @@ void launch(Dim3 grid, unsigned nthreads, size_t smem_bytes, Body body)
 } /* namespace sdrd_emu */
 
 #define SDRD_DEVICE static inline
+#define SDRD_HD inline
 #define SDRD_KERNEL(bounds_threads, bounds_ctas) static void
 #define SDRD_RESTRICT __restrict__
 #define threadIdx (sdrd_emu::t_tid)
@@ -128,6 +129,7 @@ static inline void mbar_wait(mbar_t* b, uint32_t parity)
 #include <cuda_runtime.h>
 
 #define SDRD_DEVICE __device__ __forceinline__
+#define SDRD_HD __host__ __device__ __forceinline__
 #define SDRD_KERNEL(bounds_threads, bounds_ctas) __global__ void __launch_bounds__(bounds_threads, bounds_ctas)
 #define SDRD_RESTRICT __restrict__
 #define SDRD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
@@ -176,6 +178,31 @@ SDRD_DEVICE void mbar_wait(mbar_t* b, uint32_t parity)
 #endif
 
 namespace sdrd {
+/* a + b + c as ONE three-source integer add.  In the CUDA build the two PTX adds are opaque to the
+ * optimiser's reassociation and ptxas fuses them into a single IADD3 R, a, b, c (checked in SASS),
+ * an instruction only the ALU pipe executes -- see Steer in hb_decimate.cuh. */
+SDRD_DEVICE uint32_t add3(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(SDRD_EMU)
+    return a + b + c;
+#else
+    uint32_t t, d;
+    asm("add.u32 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
+    asm("add.u32 %0, %1, %2;" : "=r"(d) : "r"(t), "r"(c));
+    return d;
+#endif
+}
+/* a * b + c kept as a multiply-add (IMAD, FMA pipe) even when b is 1 at run time */
+SDRD_DEVICE uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(SDRD_EMU)
+    return a * b + c;
+#else
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#endif
+}
 /* arithmetic shift right of a wrapping 32-bit accumulator */
 SDRD_DEVICE int asr32(uint32_t v, int sh) { return ((int)v) >> sh; }
 } /* namespace sdrd */

@@ -79,7 +79,7 @@ inline bool device_ok(std::string& why)
         return false;
     }
     if (pr.major != 10) {
-        char b[160];
+        char b[400];
         snprintf(b, sizeof b, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", dev, pr.name,
                  pr.major, pr.minor);
         why = b;
