@@ -45,7 +45,7 @@ struct Tables {
 SDRD_DEVICE uint32_t pack_digits(uint32_t m)
 {
     uint32_t t = m | (m >> 4);
-    return __byte_perm(t, 0u, 0x0020u);
+    return prmt(t, 0u, 0x0020u);
 }
 SDRD_DEVICE void selectors(uint32_t x, uint32_t& s0, uint32_t& s1, uint32_t& s2)
 {
@@ -55,7 +55,7 @@ SDRD_DEVICE void selectors(uint32_t x, uint32_t& s0, uint32_t& s1, uint32_t& s2)
 }
 SDRD_DEVICE uint32_t mul4(uint4 a, uint32_t b, uint32_t s0, uint32_t s1, uint32_t s2)
 {
-    return __byte_perm(a.x, a.y, s0) ^ __byte_perm(a.z, a.w, s1) ^ __byte_perm(b, b, s2);
+    return prmt(a.x, a.y, s0) ^ prmt(a.z, a.w, s1) ^ prmt(b, b, s2);
 }
 
 /* One pass: rows [row0, row0 + nrows) (nrows <= 16) of  out = C * img  accumulated into rec16

@@ -203,6 +203,18 @@ SDRD_DEVICE uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
     return d;
 #endif
 }
+/* PTX prmt (generic mode) without the selector masking __byte_perm() adds: callers guarantee that
+ * bit 3 of every selector nibble is clear.  SASS: one PRMT. */
+SDRD_DEVICE uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel)
+{
+#if defined(SDRD_EMU)
+    return __byte_perm(lo, hi, sel);
+#else
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+#endif
+}
 /* arithmetic shift right of a wrapping 32-bit accumulator */
 SDRD_DEVICE int asr32(uint32_t v, int sh) { return ((int)v) >> sh; }
 } /* namespace sdrd */

@@ -73,6 +73,21 @@ def test_decode_all_branches(emu_lib, oracle):
         assert np.array_equal(pay[f].reshape(-1), x[f * cases.FRAME:(f + 1) * cases.FRAME].view(np.uint8).reshape(-1))
 
 
+def test_golden_through_emulation(emu_lib):
+    """the golden vectors through the emulated library as well (host logic + kernel indexing)"""
+    import golden_cases
+    from sdrdaemon_b200 import capi
+
+    class D:
+        def __init__(self, M, fc, v):
+            self.d = capi.Decimator(M, fc, v, max_in=8192, lib=emu_lib)
+
+        def process(self, x, bits):
+            return self.d.process(x, bits)
+    golden_cases.check_decimator_golden(D)
+    golden_cases.check_fecbuffer_golden(lambda sb: capi.fec_decode(sb[None], [len(sb)], lib=emu_lib)[0][0])
+
+
 def test_rx_pipeline(emu_lib, oracle):
     from sdrdaemon_b200 import capi
 
