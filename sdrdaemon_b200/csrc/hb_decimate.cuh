@@ -20,12 +20,14 @@
  *   - all M stages run software-pipelined ACROSS chunks: in step u the "unpack" work handles chunk u
  *     and stage j+1 handles chunk u-1-j, so every step has ~C0/8 independent FIR tasks and a single
  *     __syncthreads();
- *   - a FIR task produces 8 consecutive outputs of one stage for both I and Q from a 40-entry window
- *     of odd-phase inputs held in registers (pre-add of the symmetric taps, then IMAD with immediate
- *     coefficients: 16 IADD + 16 IMAD per output and component);
- *   - stage buffers are (I,Q) int32 pairs split by sample parity (E = x[2k], O = x[2k+1]) and padded
- *     8 -> 10 entries so that 128-bit shared loads at an 8-entry thread stride are bank-conflict free;
- *     each double-buffer slot is preceded by a 32-entry tail copy of the previous chunk.
+ *   - a FIR task produces 16 consecutive outputs of one stage for ONE component (I or Q) from a
+ *     48-entry window of odd-phase inputs held in registers (pre-add of the symmetric taps, then
+ *     IMAD with immediate coefficients: 16 IADD3 + 16 IMAD per output);
+ *   - stage buffers are int32 planes split by component and by sample parity (E = x[2k],
+ *     O = x[2k+1]), padded 16 -> 20 entries so that 128-bit shared loads at a 16-entry thread stride
+ *     are bank-conflict free; each double-buffer slot is preceded by a 32-entry tail copy of the
+ *     previous chunk; the last stage leaves int32 results in a small staging buffer that the next
+ *     step packs to int16 pairs and stores with 128-bit global writes.
  *
  * This file is single-source: nvcc builds the product kernel, tests/emu builds the same code for
  * the host (see sdrd_platform.cuh).
@@ -63,19 +65,21 @@ struct Params {
 template <int C0>
 struct Geo {
     static constexpr int NT = C0 / 8;
-    static constexpr int LOG2_2N1 = (C0 == 512 ? 6 : C0 == 1024 ? 7 : 8); /* log2(C0 / 8) */
+    static constexpr int LOG2_NT = (C0 == 512 ? 6 : C0 == 1024 ? 7 : 8);
     static_assert(C0 == 512 || C0 == 1024 || C0 == 2048, "supported chunk sizes");
-    SDRD_HD static constexpr int stage_base(int m) { return 5 * (TAIL * m + C0 - (C0 >> m)); }
-    SDRD_HD static constexpr int region_phys(int m) { return ((TAIL + (C0 >> (m + 1))) >> 3) * 10; }
-    /* [T | S] region of stage m's output buffer: parity eo (0 = even samples), double-buffer slot */
-    SDRD_HD static int2* region(int2* sbuf, int m, int eo, int slot)
+    /* all in int32 entries */
+    SDRD_HD static constexpr int stage_base(int m) { return 10 * (TAIL * m + C0 - (C0 >> m)); }
+    SDRD_HD static constexpr int region_phys(int m) { return ((TAIL + (C0 >> (m + 1))) >> 4) * 20; }
+    /* [T | S] region of stage m's output: parity (0 = even samples), component (0 = I), slot */
+    SDRD_HD static int* plane(int* sbuf, int m, int parity, int comp, int slot)
     {
-        return sbuf + stage_base(m) + (eo * 2 + slot) * region_phys(m);
+        return sbuf + stage_base(m) + ((parity * 2 + comp) * 2 + slot) * region_phys(m);
     }
     SDRD_HD static constexpr size_t raw_bytes(int prologue) { return (size_t)2 * (prologue ? 4 : 1) * C0 * 4; }
+    /* raw double buffer | 2 mbarriers | stage planes | last-stage staging [comp][slot][C0 >> M] */
     SDRD_HD static constexpr size_t smem_bytes(int M, int prologue)
     {
-        return raw_bytes(prologue) + 128 + (size_t)(5 * (TAIL * M + C0 - (C0 >> M))) * 8;
+        return raw_bytes(prologue) + 128 + (size_t)(10 * (TAIL * M + C0 - (C0 >> M))) * 4 + (size_t)4 * (C0 >> M) * 4;
     }
 };
 
@@ -89,8 +93,8 @@ constexpr int chunk_for(int M)
     return (M == 6 || SDRD_HB_C0_MIN >= 2048) ? 2048 : ((M == 5 || SDRD_HB_C0_MIN >= 1024) ? 1024 : 512);
 }
 
-/* logical entry -> physical entry (8 -> 10 padding) */
-SDRD_DEVICE int phys(int k) { return k + 2 * (k >> 3); }
+/* logical entry -> physical entry (16 -> 20 padding) */
+SDRD_DEVICE int phys(int k) { return k + 4 * (k >> 4); }
 
 /* Pipe steering.  The FIR body is issue-bound: per output and component 16 pre-adds + 16
  * multiply-accumulates.  Left alone, ptxas turns about half of the pre-adds into IMAD.IADD, which
@@ -108,73 +112,63 @@ struct Steer {
 #define SDRD_HB_FMA_ADD_TAPS 1 /* taps (outermost first) whose pre-add runs on the FMA pipe */
 #endif
 
-/* 8 consecutive outputs n0 .. n0+7 (n0 = 8 i, chunk-local) of one half-band stage.
- * srcE/srcO point at the [T | S] region of the consumed chunk: logical entry TAIL + k is
- * E[k] = x[2k] resp. O[k] = x[2k+1] of the chunk, entries 0..TAIL-1 the previous chunk's tail. */
-SDRD_DEVICE void fir8(const int2* SDRD_RESTRICT srcE, const int2* SDRD_RESTRICT srcO, int i, uint32_t acc0,
-                      const Steer st, int2 (&y)[8])
+/* 16 consecutive outputs n0 .. n0+15 (n0 = 16 i, chunk-local) of one half-band stage, one component.
+ * srcE/srcO point at the [T | S] planes of the consumed chunk: logical entry TAIL + k is
+ * E[k] = x[2k] resp. O[k] = x[2k+1] of the chunk, entries 0..TAIL-1 the previous chunk's tail.
+ * y[n] needs O[n-31 .. n] and E[n-15].
+ * fir16_load fetches the operands (issued at the top of a step so that the shared-memory latency
+ * hides behind the unpack work), fir16_compute does the arithmetic. */
+struct Fir16Regs {
+    uint32_t w[48]; /* w[j] = O[n0 - 32 + j]: logical entries 16i .. 16i+47 = padded groups i .. i+2 */
+    uint32_t e[17]; /* e[j] = E[n0 - 16 + j]: group i+1 and the first entry of group i+2 */
+};
+
+SDRD_DEVICE void fir16_load(const int* SDRD_RESTRICT srcE, const int* SDRD_RESTRICT srcO, int i, Fir16Regs& f)
 {
-    constexpr int H[16] = SDRD_HB64_TAPS;
-    /* y[n] needs O[n-31 .. n] and E[n-15].  Window w[j] = O[n0 - 32 + j], j = 0..39: logical entries
-     * 8i .. 8i+39 = padded groups i .. i+4. */
-    int2 w[40];
-    {
-        const int4* po = reinterpret_cast<const int4*>(srcO + 10 * i);
+    const int4* po = reinterpret_cast<const int4*>(srcO + 20 * i);
 #pragma unroll
-        for (int g = 0; g < 5; g++) {
+    for (int g = 0; g < 3; g++) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                int4 v = po[g * 5 + q];
-                w[g * 8 + 2 * q] = make_int2(v.x, v.y);
-                w[g * 8 + 2 * q + 1] = make_int2(v.z, v.w);
-            }
+        for (int q = 0; q < 4; q++) {
+            int4 v = po[g * 5 + q];
+            f.w[g * 16 + 4 * q] = (uint32_t)v.x;
+            f.w[g * 16 + 4 * q + 1] = (uint32_t)v.y;
+            f.w[g * 16 + 4 * q + 2] = (uint32_t)v.z;
+            f.w[g * 16 + 4 * q + 3] = (uint32_t)v.w;
         }
     }
-    uint32_t aI[8], aQ[8];
+    const int4* pe = reinterpret_cast<const int4*>(srcE + 20 * (i + 1));
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        aI[r] = acc0;
-        aQ[r] = acc0;
+    for (int q = 0; q < 4; q++) {
+        int4 v = pe[q];
+        f.e[4 * q] = (uint32_t)v.x;
+        f.e[4 * q + 1] = (uint32_t)v.y;
+        f.e[4 * q + 2] = (uint32_t)v.z;
+        f.e[4 * q + 3] = (uint32_t)v.w;
     }
+    f.e[16] = (uint32_t)srcE[20 * (i + 2)];
+}
+
+SDRD_DEVICE void fir16_compute(const Fir16Regs& f, uint32_t acc0, const Steer st, int (&y)[16])
+{
+    constexpr int H[16] = SDRD_HB64_TAPS;
+    uint32_t acc[16];
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < 16; r++) acc[r] = acc0;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
 #pragma unroll
         for (int t = 0; t < 16; t++) {
             /* O[n - t] = w[32 + r - t], O[n - 31 + t] = w[1 + r + t] */
-            const uint32_t aIx = (uint32_t)w[32 + r - t].x, bIx = (uint32_t)w[1 + r + t].x;
-            const uint32_t aQx = (uint32_t)w[32 + r - t].y, bQx = (uint32_t)w[1 + r + t].y;
-            uint32_t sI, sQ;
-            if (t < SDRD_HB_FMA_ADD_TAPS) {
-                sI = mad_lo(aIx, st.one, bIx);
-                sQ = mad_lo(aQx, st.one, bQx);
-            } else {
-                sI = add3(aIx, bIx, st.zero);
-                sQ = add3(aQx, bQx, st.zero);
-            }
+            const uint32_t a = f.w[32 + r - t], b = f.w[1 + r + t];
+            const uint32_t sum = t < SDRD_HB_FMA_ADD_TAPS ? mad_lo(a, st.one, b) : add3(a, b, st.zero);
             const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
-            aI[r] = mad_lo(sI, h, aI[r]);
-            aQ[r] = mad_lo(sQ, h, aQ[r]);
+            acc[r] = mad_lo(sum, h, acc[r]);
         }
     }
-    /* centre taps E[n0 - 15 + r]: logical entries 8i + 17 + r -> group i+2 (entries 16..23) and the
-     * first entry of group i+3 */
-    {
-        const int4* pe = reinterpret_cast<const int4*>(srcE + 10 * (i + 2));
-        int2 e[10];
+    /* centre taps E[n0 - 15 + r] = e[1 + r] */
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            int4 v = pe[q];
-            e[2 * q] = make_int2(v.x, v.y);
-            e[2 * q + 1] = make_int2(v.z, v.w);
-        }
-        e[8] = srcE[10 * (i + 3)];
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            aI[r] = mad_lo((uint32_t)e[1 + r].x, st.k8192, aI[r]);
-            aQ[r] = mad_lo((uint32_t)e[1 + r].y, st.k8192, aQ[r]);
-            y[r] = make_int2(asr32(aI[r], HB_SHIFT), asr32(aQ[r], HB_SHIFT));
-        }
-    }
+    for (int r = 0; r < 16; r++) y[r] = asr32(mad_lo(f.e[1 + r], st.k8192, acc[r]), HB_SHIFT);
 }
 
 SDRD_DEVICE int s16lo(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
@@ -204,9 +198,10 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
     const int raw_per_chunk = pro ? 4 * C0 : C0; /* raw samples feeding one chunk of cascade input */
     uint32_t* raw = reinterpret_cast<uint32_t*>(smem);
     mbar_t* bars = reinterpret_cast<mbar_t*>(smem + G::raw_bytes(pro));
-    int2* sbuf = reinterpret_cast<int2*>(smem + G::raw_bytes(pro) + 128);
-
+    int* sbuf = reinterpret_cast<int*>(smem + G::raw_bytes(pro) + 128);
     constexpr int out_per_chunk = C0 >> M;
+    int* fin = sbuf + G::stage_base(M); /* [comp][slot][out_per_chunk] */
+
     const long long seg_first_out = (long long)seg * p.seg_out;
     long long seg_n_out = p.n_out - seg_first_out;
     if (seg_n_out > p.seg_out) seg_n_out = p.seg_out;
@@ -221,20 +216,31 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
     const uint32_t chunk_bytes = (uint32_t)raw_per_chunk * 4u;
     const Steer steer = {p.steer_zero, p.steer_one, p.steer_k32, p.steer_k256, p.steer_k8192};
 
-    /* ---- this thread's fixed role: FIR task t = tid of every step (stage j+1, outputs 8i..8i+7 of
-     *      the chunk); there are C0/8 * (1 - 2^-M) < NT tasks per step ---- */
-    constexpr int two_n1 = C0 / 8;
-    constexpr int n_tasks = two_n1 - (two_n1 >> M);
+    /* ---- this thread's fixed role: FIR task t = tid of every step.  Stage j+1 has (C0/16) >> j tasks
+     *      (first half I, second half Q), C0/8 * (1 - 2^-M) < NT in total ---- */
+    constexpr int n_tasks = NT - (NT >> M);
     const bool has_task = tid < n_tasks;
-    const int tj = has_task ? __clz(two_n1 - 1 - tid) - (32 - G::LOG2_2N1) : 0;
-    const int ti = tid - (two_n1 - (two_n1 >> tj));
+    const int tj = has_task ? __clz(NT - 1 - tid) - (32 - G::LOG2_NT) : 0;
+    const int ta = tid - (NT - (NT >> tj));     /* index within the stage */
+    const int half = (NT >> tj) >> 2;           /* tasks per component: (C0/16 >> tj) / 2 */
+    const int tcomp = ta >= half ? 1 : 0;
+    const int ti = ta - tcomp * half;
     const bool t_final = tj + 1 == M;
-    const int2* const t_srcE = G::region(sbuf, tj, 0, 0);
-    const int2* const t_srcO = G::region(sbuf, tj, 1, 0);
-    const int t_src_slot = G::region_phys(tj);           /* entries between slot 0 and slot 1 */
-    int2* const t_dstE = G::region(sbuf, t_final ? tj : tj + 1, 0, 0) + phys(TAIL + 4 * ti);
-    int2* const t_dstO = G::region(sbuf, t_final ? tj : tj + 1, 1, 0) + phys(TAIL + 4 * ti);
-    const int t_dst_slot = G::region_phys(t_final ? tj : tj + 1);
+    const int* const t_srcE = G::plane(sbuf, tj, 0, tcomp, 0);
+    const int* const t_srcO = G::plane(sbuf, tj, 1, tcomp, 0);
+    const int t_src_slot = G::region_phys(tj);
+    int* t_dstE;
+    int* t_dstO;
+    int t_dst_slot;
+    if (!t_final) {
+        t_dstE = G::plane(sbuf, tj + 1, 0, tcomp, 0) + phys(TAIL + 8 * ti);
+        t_dstO = G::plane(sbuf, tj + 1, 1, tcomp, 0) + phys(TAIL + 8 * ti);
+        t_dst_slot = G::region_phys(tj + 1);
+    } else {
+        t_dstE = fin + tcomp * 2 * out_per_chunk + 16 * ti;
+        t_dstO = t_dstE;
+        t_dst_slot = out_per_chunk;
+    }
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -249,73 +255,97 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
         }
     }
 
-    for (int u = 0; u < NC + M; u++) {
-        /* ---- stage 0: unpack raw chunk u into (I,Q) int32 pairs, split by parity ---- */
+    for (int u = 0; u < NC + M + 1; u++) {
+        /* ---- operands of this step's half-band task (stage tj+1 consumes stage-tj chunk u-1-tj,
+         *      written in the previous step): fetched first, used after the unpack work ---- */
+        const int c = u - 1 - tj;
+        const bool task_on = has_task && c >= 0 && c < NC;
+        const int slot = c & 1;
+        Fir16Regs fr;
+        if (task_on) fir16_load(t_srcE + slot * t_src_slot, t_srcO + slot * t_src_slot, ti, fr);
+
+        /* ---- stage 0: unpack raw chunk u into int32 planes (component x parity) ---- */
+#if defined(SDRD_EXP_NOUNPACK)
+        if (u < 0) {
+#else
         if (u < NC) {
+#endif
             mbar_wait(&bars[u & 1], (uint32_t)((u >> 1) & 1));
             const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)(u & 1) * raw_per_chunk);
-            int2* E0 = G::region(sbuf, 0, 0, u & 1);
-            int2* O0 = G::region(sbuf, 0, 1, u & 1);
+            int* EI = G::plane(sbuf, 0, 0, 0, u & 1);
+            int* EQ = G::plane(sbuf, 0, 0, 1, u & 1);
+            int* OI = G::plane(sbuf, 0, 1, 0, u & 1);
+            int* OQ = G::plane(sbuf, 0, 1, 1, u & 1);
+            /* thread q: cascade inputs 8q .. 8q+7 -> entries 4q .. 4q+3 of each plane */
+            const int ph = phys(TAIL + 4 * tid);
+            int2 x[8];
             if (!pro) {
+                const uint4 v0 = r4[2 * tid], v1 = r4[2 * tid + 1];
+                const uint32_t v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                for (int qq = 0; qq < 2; qq++) {
-                    const int q = tid + qq * NT;
-                    uint4 v = r4[q];
-                    int ph = phys(TAIL + 2 * q);
-                    *reinterpret_cast<int4*>(E0 + ph) = make_int4(s16lo(v.x), s16hi(v.x), s16lo(v.z), s16hi(v.z));
-                    *reinterpret_cast<int4*>(O0 + ph) = make_int4(s16lo(v.y), s16hi(v.y), s16lo(v.w), s16hi(v.w));
-                }
+                for (int k = 0; k < 8; k++) x[k] = make_int2(s16lo(v[k]), s16hi(v[k]));
             } else {
-                /* 16 raw samples -> 4 cascade inputs -> 2 E entries + 2 O entries */
-                for (int q = tid; q < C0 / 4; q += NT) {
-                    int2 a = rot4(r4[4 * q], pro), b = rot4(r4[4 * q + 1], pro);
-                    int2 c = rot4(r4[4 * q + 2], pro), d = rot4(r4[4 * q + 3], pro);
-                    int ph = phys(TAIL + 2 * q);
-                    *reinterpret_cast<int4*>(E0 + ph) = make_int4(a.x, a.y, c.x, c.y);
-                    *reinterpret_cast<int4*>(O0 + ph) = make_int4(b.x, b.y, d.x, d.y);
-                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = rot4(r4[8 * tid + k], pro);
             }
+            *reinterpret_cast<int4*>(EI + ph) = make_int4(x[0].x, x[2].x, x[4].x, x[6].x);
+            *reinterpret_cast<int4*>(EQ + ph) = make_int4(x[0].y, x[2].y, x[4].y, x[6].y);
+            *reinterpret_cast<int4*>(OI + ph) = make_int4(x[1].x, x[3].x, x[5].x, x[7].x);
+            *reinterpret_cast<int4*>(OQ + ph) = make_int4(x[1].y, x[3].y, x[5].y, x[7].y);
         }
 
-        /* ---- half-band task: stage tj+1 consumes stage-tj chunk u-1-tj ---- */
-        const int c = u - 1 - tj;
-        if (has_task && c >= 0 && c < NC) {
-            const int slot = c & 1;
-            int2 y[8];
-            fir8(t_srcE + slot * t_src_slot, t_srcO + slot * t_src_slot, ti, acc0, steer, y);
+        /* ---- half-band task ---- */
+        if (task_on) {
+            int y[16];
+            fir16_compute(fr, acc0, steer, y);
             if (p.round_add) {
                 /* DB: the reference's stages start from all-zero state, but a DB stage maps zero
                  * input to 1; outputs that lie before the stream origin must read as 0. */
-                const long long a = ((abs0 + (long long)c * C0) >> (tj + 1)) + 8 * ti;
+                const long long a = ((abs0 + (long long)c * C0) >> (tj + 1)) + 16 * ti;
                 if (a < 0) {
 #pragma unroll
-                    for (int r = 0; r < 8; r++)
-                        if (a + r < 0) y[r] = make_int2(0, 0);
+                    for (int r = 0; r < 16; r++)
+                        if (a + r < 0) y[r] = 0;
                 }
             }
             if (!t_final) {
                 int4* qe = reinterpret_cast<int4*>(t_dstE + slot * t_dst_slot);
                 int4* qo = reinterpret_cast<int4*>(t_dstO + slot * t_dst_slot);
-                qe[0] = make_int4(y[0].x, y[0].y, y[2].x, y[2].y);
-                qe[1] = make_int4(y[4].x, y[4].y, y[6].x, y[6].y);
-                qo[0] = make_int4(y[1].x, y[1].y, y[3].x, y[3].y);
-                qo[1] = make_int4(y[5].x, y[5].y, y[7].x, y[7].y);
-            } else if (c >= p.warm_chunks) {
-                const long long n = seg_first_out + (long long)(c - p.warm_chunks) * out_per_chunk + 8 * ti;
-                uint32_t o[8];
+                qe[0] = make_int4(y[0], y[2], y[4], y[6]);
+                qe[1] = make_int4(y[8], y[10], y[12], y[14]);
+                qo[0] = make_int4(y[1], y[3], y[5], y[7]);
+                qo[1] = make_int4(y[9], y[11], y[13], y[15]);
+            } else {
+                int4* q = reinterpret_cast<int4*>(t_dstE + slot * t_dst_slot);
+                q[0] = make_int4(y[0], y[1], y[2], y[3]);
+                q[1] = make_int4(y[4], y[5], y[6], y[7]);
+                q[2] = make_int4(y[8], y[9], y[10], y[11]);
+                q[3] = make_int4(y[12], y[13], y[14], y[15]);
+            }
+        }
+
+        /* ---- pack: the last stage's chunk u-1-M (finished in the previous step) -> int16 pairs,
+         *      (y << norm_shift) >> trunk_shift truncated to 16 bits (SDRDaemon.h:59) ---- */
+        {
+            const int c2 = u - 1 - M;
+            if (c2 >= p.warm_chunks && c2 < NC && tid < out_per_chunk / 4) {
+                const int slot = c2 & 1;
+                const int4 vi = *reinterpret_cast<const int4*>(fin + slot * out_per_chunk + 4 * tid);
+                const int4 vq = *reinterpret_cast<const int4*>(fin + (2 + slot) * out_per_chunk + 4 * tid);
+                const int yi[4] = {vi.x, vi.y, vi.z, vi.w}, yq[4] = {vq.x, vq.y, vq.z, vq.w};
+                uint32_t o[4];
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    uint32_t vi = (uint32_t)asr32((uint32_t)y[r].x << p.norm_shift, p.trunk_shift);
-                    uint32_t vq = (uint32_t)asr32((uint32_t)y[r].y << p.norm_shift, p.trunk_shift);
-                    o[r] = (vi & 0xFFFFu) | (vq << 16);
+                for (int r = 0; r < 4; r++) {
+                    uint32_t a = (uint32_t)asr32((uint32_t)yi[r] << p.norm_shift, p.trunk_shift);
+                    uint32_t b = (uint32_t)asr32((uint32_t)yq[r] << p.norm_shift, p.trunk_shift);
+                    o[r] = (a & 0xFFFFu) | (b << 16);
                 }
-                if (n + 8 <= p.n_out) {
-                    uint4* q = reinterpret_cast<uint4*>(dst + n);
-                    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                const long long n = seg_first_out + (long long)(c2 - p.warm_chunks) * out_per_chunk + 4 * tid;
+                if (n + 4 <= p.n_out) {
+                    *reinterpret_cast<uint4*>(dst + n) = make_uint4(o[0], o[1], o[2], o[3]);
                 } else {
 #pragma unroll
-                    for (int r = 0; r < 8; r++)
+                    for (int r = 0; r < 4; r++)
                         if (n + r < p.n_out) dst[n + r] = o[r];
                 }
             }
@@ -323,17 +353,23 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
 
         /* ---- tail copies: last TAIL entries of the chunk consumed in this step -> front of the
          *      other slot, where the next chunk's consumer expects its history ---- */
+#if defined(SDRD_EXP_NOTAIL)
+        for (int t = tid; t < 0; t += NT) {
+#else
         for (int t = tid; t < 32 * M; t += NT) {
-            const int j = t >> 5, eo = (t >> 4) & 1, unit = t & 15;
+#endif
+            const int j = t >> 5, pc = (t >> 3) & 3, unit = t & 7;
             const int cc = u - 1 - j;
             if (cc < 0 || cc >= NC) continue;
             const int n = C0 >> (j + 1);
-            const int4* sp = reinterpret_cast<const int4*>(G::region(sbuf, j, eo, cc & 1) + phys(n)); /* entry TAIL+n-32 */
-            int4* dp = reinterpret_cast<int4*>(G::region(sbuf, j, eo, (cc & 1) ^ 1));
-            /* 4 padded groups of 8 entries: 5 int4 per group, the first 4 carry data */
-            dp[(unit >> 2) * 5 + (unit & 3)] = sp[(unit >> 2) * 5 + (unit & 3)];
+            const int off = 20 * (unit >> 2) + 4 * (unit & 3);
+            const int* sp = G::plane(sbuf, j, pc >> 1, pc & 1, cc & 1) + 20 * (n >> 4) + off; /* entry TAIL+n-32 */
+            int* dp = G::plane(sbuf, j, pc >> 1, pc & 1, (cc & 1) ^ 1) + off;
+            *reinterpret_cast<int4*>(dp) = *reinterpret_cast<const int4*>(sp);
         }
+#if !defined(SDRD_EXP_NOSYNC)
         __syncthreads();
+#endif
         if (tid == 0 && u + 2 < NC) {
             mbar_arrive_expect_tx(&bars[u & 1], chunk_bytes);
             tma_load_1d(raw + (size_t)(u & 1) * raw_per_chunk, src + (size_t)(u + 2) * raw_per_chunk, chunk_bytes,
