@@ -316,12 +316,16 @@ def main():
                "h2d_bytes_per_step": S * n_in * 4, "d2h_bytes_per_step": S * int(nfr.value) * bpf * 512,
                "steps": args.e2e_steps, "api": "sdrd_rx_process (host pointers, pinned)"}
 
-    # trivial gather: one 8-byte digest per rank
+    # the only exchange of the job: one 8-byte digest per stream (sdrdaemon_b200.multi)
+    digests = None
     if world > 1:
+        from sdrdaemon_b200 import multi
+
+        first, count = multi.stream_range(world * S, world, rank)
+        assert count == S
         dg_ptr, _ = sink.dev_datagrams()
-        d = torch.as_tensor(DevView(dg_ptr, 4096), device="cuda").view(torch.int64).sum().reshape(1)
-        outl = [torch.zeros_like(d) for _ in range(world)]
-        dist.all_gather(outl, d)
+        head = torch.as_tensor(DevView(dg_ptr, (128 + N_FEC) * 512), device="cuda").cpu().numpy().reshape(1, -1)
+        digests = multi.gather_digests(multi.datagram_digest(head), world * S, world, rank, device=torch.device("cuda", local))
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -347,6 +351,7 @@ def main():
             },
             "e2e": e2e,
             "gpu_launches": int(launches),
+            "stream_digests": [hex(int(v)) for v in digests] if digests is not None else None,
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": "hb::decimate_kernel<4> (K1)", "achieved": round(achieved, 1), "peak": peak,

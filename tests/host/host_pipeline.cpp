@@ -1,0 +1,143 @@
+/*
+ * host_pipeline.cpp -- drives the C++ host layer (sdrdaemon_b200/host/sdrd_host.hpp) the way the
+ * reference's two mains do (sdrdaemonrx.cpp:579-663 and sdrdaemontx.cpp:448-500), in one process:
+ *
+ *   TestSource -> DataBuffer -> Downsampler::process -> UDPSinkFEC::write ==UDP 127.0.0.1==>
+ *   UDPSourceFEC::read -> DataBuffer -> FileSink (.sdriq)
+ *
+ *   host_pipeline testsource <n_samples> <srate> <dfp> <power_db> <out.raw>
+ *   host_pipeline pipeline <port> <config> <n_blocks> <out.sdriq> <datagrams.bin> [puncture]
+ *       config e.g. "srate=2400000,decim=4,fecblk=16,dfp=100000,power=6,blklen=65536"
+ *
+ * Linked against libsdrd_b200.so on a GPU box, or against tests/emu/libsdrd_emu.so for the CPU-only
+ * check of the host logic.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "../../sdrdaemon_b200/host/sdrd_host.hpp"
+
+using namespace sdrd_b200;
+
+static std::mutex g_tap_mutex;
+static void tap(void* user, const uint8_t* dg, int, int) { fwrite(dg, 1, SDRD_UDPSIZE, (FILE*)user); }
+
+static int run_testsource(int argc, char** argv)
+{
+    if (argc < 7) return 2;
+    int n = atoi(argv[2]), srate = atoi(argv[3]);
+    double dfp = atof(argv[4]), power = atof(argv[5]);
+    std::vector<int16_t> buf(2 * (size_t)n);
+    float phase = 0;
+    int got = 0;
+    float amp = (float)pow(10.0, -power / 20.0);
+    float dphi = (float)(2.0 * M_PI * dfp / (double)srate);
+    TestSource::read_samples(buf.data(), 4 * n, got, phase, srate, dphi, amp, false);
+    FILE* f = fopen(argv[6], "wb");
+    fwrite(buf.data(), 2, buf.size(), f);
+    fclose(f);
+    return 0;
+}
+
+static int run_pipeline(int argc, char** argv)
+{
+    if (argc < 7) return 2;
+    unsigned port = (unsigned)atoi(argv[2]);
+    std::string config = argv[3];
+    int n_blocks = atoi(argv[4]);
+    std::string out_file = argv[5];
+    FILE* dgf = fopen(argv[6], "wb");
+    int puncture = argc > 7 ? atoi(argv[7]) : -1;
+
+    std::atomic_bool stop_rx(false), stop_src(false), stop_file(false);
+
+    /* ---- Tx side of the link (sdrdaemontx): UDPSourceFEC -> FileSink ---- */
+    UDPSourceFEC udp_input("127.0.0.1", port);
+    if (!udp_input) { fprintf(stderr, "UDPSourceFEC: %s\n", udp_input.error().c_str()); return 1; }
+    udp_input.setStopFlag(&stop_rx);
+    FileSink file_sink;
+    DataBuffer<IQSample> sink_buffer;
+    std::string fcfg = "file=" + out_file + ",srate=150000,freq=435000000,stamp=1700000000";
+    if (!file_sink.configure(fcfg)) { fprintf(stderr, "FileSink: %s\n", file_sink.error().c_str()); return 1; }
+    file_sink.start(&sink_buffer, &stop_file);
+    int frames_in = 0, frames_recovered = 0;
+    std::thread rx_thread([&]() {
+        IQSampleVector frame;
+        bool first = true;
+        for (;;) {
+            udp_input.read(frame);
+            if (frame.empty()) break;
+            if (first) { first = false; continue; } /* the empty slot emitted before the first frame */
+            frames_in++;
+            if (udp_input.getLastFrameStatus() == SDRD_FRAME_RECOVERED) frames_recovered++;
+            sink_buffer.push(std::move(frame));
+        }
+        sink_buffer.push_end();
+    });
+
+    /* ---- Rx side (sdrdaemonrx): TestSource -> Downsampler -> UDPSinkFEC ---- */
+    Downsampler dn;
+    if (!dn) { fprintf(stderr, "Downsampler: %s\n", dn.error().c_str()); return 1; }
+    UDPSinkFEC udp_output("127.0.0.1", port);
+    if (!udp_output) { fprintf(stderr, "UDPSinkFEC: %s\n", udp_output.error().c_str()); return 1; }
+    udp_output.setTap(tap, dgf);
+    udp_output.setTimestamp(1700000000u, 0);
+    udp_output.setPuncture(puncture);
+    TestSource src;
+    src.associateDownsampler(&dn);
+    std::string cfg = config + ",pace=0";
+    DeviceSource* srcsdr = &src;
+    if (!srcsdr->configure(cfg)) { fprintf(stderr, "configure: %s\n", srcsdr->error().c_str()); return 1; }
+    DataBuffer<IQSample> source_buffer;
+    srcsdr->start(&source_buffer, &stop_src);
+
+    long long samples_out = 0;
+    for (int blk = 0; blk < n_blocks; blk++) {
+        IQSampleVector iqsamples = source_buffer.pull();
+        if (iqsamples.empty()) break;
+        unsigned int sampleSize = srcsdr->get_sample_bits();
+        udp_output.setCenterFrequency(srcsdr->get_frequency());
+        udp_output.setSampleRate(srcsdr->get_sample_rate() >> dn.getLog2Decimation());
+        udp_output.setNbBlocksFEC((int)srcsdr->get_nb_fec_blocks());
+        udp_output.setTxDelay((int)srcsdr->get_tx_delay());
+        IQSampleVector outsamples;
+        dn.process(sampleSize, iqsamples, outsamples);
+        if (!dn) { fprintf(stderr, "process: %s\n", dn.error().c_str()); return 1; }
+        udp_output.setSampleBytes(2);
+        udp_output.setSampleBits((uint8_t)sampleSize);
+        if (blk == 0) continue; /* sdrdaemonrx.cpp:646-648: the first block is thrown away */
+        samples_out += (long long)outsamples.size();
+        udp_output.write(outsamples);
+        if (!udp_output) { fprintf(stderr, "write: %s\n", udp_output.error().c_str()); return 1; }
+    }
+    stop_src.store(true);
+    while (!source_buffer.pull().empty()) {}
+    srcsdr->stop();
+    /* the receiver hands a frame over when the next one starts: pad with zeros up to the start of
+     * one more frame */
+    {
+        long long rem = samples_out % SDRD_FRAME_SAMPLES;
+        IQSampleVector pad((size_t)(SDRD_FRAME_SAMPLES - rem) + SDRD_FRAME_SAMPLES);
+        udp_output.write(pad);
+    }
+    udp_output.flush();
+    usleep(300000);
+    stop_rx.store(true);
+    rx_thread.join();
+    stop_file.store(true);
+    file_sink.stop();
+    fclose(dgf);
+    char status[64] = "status";
+    udp_input.getStatusMessage(status);
+    printf("samples_out=%lld frames_received=%d frames_recovered=%d %s\n", samples_out, frames_in, frames_recovered, status);
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc >= 2 && std::string(argv[1]) == "testsource") return run_testsource(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "pipeline") return run_pipeline(argc, argv);
+    fprintf(stderr, "usage: host_pipeline testsource|pipeline ...\n");
+    return 2;
+}
