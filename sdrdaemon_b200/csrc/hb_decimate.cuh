@@ -184,7 +184,9 @@ SDRD_DEVICE int2 rot4(uint4 v, int prologue)
     return make_int2(i0 - r1 - i2 + r3, -r0 - i1 + r2 + i3);
 }
 
-template <int M, int C0>
+/* DB = 0: IntHalfbandFilterEO1, DB = 1: IntHalfbandFilterDB (+1 rounding of the centre tap, stage
+ * outputs before the stream origin forced to 0) */
+template <int M, int C0, int DB>
 SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
 {
     typedef Geo<C0> G;
@@ -200,7 +202,7 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
     mbar_t* bars = reinterpret_cast<mbar_t*>(smem + G::raw_bytes(pro));
     int* sbuf = reinterpret_cast<int*>(smem + G::raw_bytes(pro) + 128);
     constexpr int out_per_chunk = C0 >> M;
-    int* fin = sbuf + G::stage_base(M); /* [comp][slot][out_per_chunk] */
+    int* fin = sbuf + G::stage_base(M); /* last stage's results: [comp][slot][parity][out_per_chunk / 2] */
 
     const long long seg_first_out = (long long)seg * p.seg_out;
     long long seg_n_out = p.n_out - seg_first_out;
@@ -212,7 +214,7 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
     const uint32_t* src = p.in + (long long)s * p.in_stride + first_in * (pro ? 4 : 1);
     uint32_t* dst = p.out + (long long)s * p.out_stride;
     const long long abs0 = p.origin + first_in;
-    const uint32_t acc0 = (uint32_t)p.round_add << HB_SHIFT;
+    constexpr uint32_t acc0 = (uint32_t)DB << HB_SHIFT;
     const uint32_t chunk_bytes = (uint32_t)raw_per_chunk * 4u;
     const Steer steer = {p.steer_zero, p.steer_one, p.steer_k32, p.steer_k256, p.steer_k8192};
 
@@ -237,8 +239,9 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
         t_dstO = G::plane(sbuf, tj + 1, 1, tcomp, 0) + phys(TAIL + 8 * ti);
         t_dst_slot = G::region_phys(tj + 1);
     } else {
-        t_dstE = fin + tcomp * 2 * out_per_chunk + 16 * ti;
-        t_dstO = t_dstE;
+        /* last stage: same even/odd split, into the staging buffer [comp][slot][parity][opc/2] */
+        t_dstE = fin + tcomp * 2 * out_per_chunk + 8 * ti;
+        t_dstO = t_dstE + out_per_chunk / 2;
         t_dst_slot = out_per_chunk;
     }
 
@@ -278,27 +281,28 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
             int* OQ = G::plane(sbuf, 0, 1, 1, u & 1);
             /* thread q: cascade inputs 8q .. 8q+7 -> entries 4q .. 4q+3 of each plane */
             const int ph = phys(TAIL + 4 * tid);
-            int2 x[8];
             if (!pro) {
-                const uint4 v0 = r4[2 * tid], v1 = r4[2 * tid + 1];
-                const uint32_t v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = make_int2(s16lo(v[k]), s16hi(v[k]));
+                const uint4 a = r4[2 * tid], b = r4[2 * tid + 1];
+                *reinterpret_cast<int4*>(EI + ph) = make_int4(s16lo(a.x), s16lo(a.z), s16lo(b.x), s16lo(b.z));
+                *reinterpret_cast<int4*>(EQ + ph) = make_int4(s16hi(a.x), s16hi(a.z), s16hi(b.x), s16hi(b.z));
+                *reinterpret_cast<int4*>(OI + ph) = make_int4(s16lo(a.y), s16lo(a.w), s16lo(b.y), s16lo(b.w));
+                *reinterpret_cast<int4*>(OQ + ph) = make_int4(s16hi(a.y), s16hi(a.w), s16hi(b.y), s16hi(b.w));
             } else {
+                int2 x[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) x[k] = rot4(r4[8 * tid + k], pro);
+                *reinterpret_cast<int4*>(EI + ph) = make_int4(x[0].x, x[2].x, x[4].x, x[6].x);
+                *reinterpret_cast<int4*>(EQ + ph) = make_int4(x[0].y, x[2].y, x[4].y, x[6].y);
+                *reinterpret_cast<int4*>(OI + ph) = make_int4(x[1].x, x[3].x, x[5].x, x[7].x);
+                *reinterpret_cast<int4*>(OQ + ph) = make_int4(x[1].y, x[3].y, x[5].y, x[7].y);
             }
-            *reinterpret_cast<int4*>(EI + ph) = make_int4(x[0].x, x[2].x, x[4].x, x[6].x);
-            *reinterpret_cast<int4*>(EQ + ph) = make_int4(x[0].y, x[2].y, x[4].y, x[6].y);
-            *reinterpret_cast<int4*>(OI + ph) = make_int4(x[1].x, x[3].x, x[5].x, x[7].x);
-            *reinterpret_cast<int4*>(OQ + ph) = make_int4(x[1].y, x[3].y, x[5].y, x[7].y);
         }
 
         /* ---- half-band task ---- */
         if (task_on) {
             int y[16];
             fir16_compute(fr, acc0, steer, y);
-            if (p.round_add) {
+            if (DB) {
                 /* DB: the reference's stages start from all-zero state, but a DB stage maps zero
                  * input to 1; outputs that lie before the stream origin must read as 0. */
                 const long long a = ((abs0 + (long long)c * C0) >> (tj + 1)) + 16 * ti;
@@ -308,20 +312,12 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
                         if (a + r < 0) y[r] = 0;
                 }
             }
-            if (!t_final) {
-                int4* qe = reinterpret_cast<int4*>(t_dstE + slot * t_dst_slot);
-                int4* qo = reinterpret_cast<int4*>(t_dstO + slot * t_dst_slot);
-                qe[0] = make_int4(y[0], y[2], y[4], y[6]);
-                qe[1] = make_int4(y[8], y[10], y[12], y[14]);
-                qo[0] = make_int4(y[1], y[3], y[5], y[7]);
-                qo[1] = make_int4(y[9], y[11], y[13], y[15]);
-            } else {
-                int4* q = reinterpret_cast<int4*>(t_dstE + slot * t_dst_slot);
-                q[0] = make_int4(y[0], y[1], y[2], y[3]);
-                q[1] = make_int4(y[4], y[5], y[6], y[7]);
-                q[2] = make_int4(y[8], y[9], y[10], y[11]);
-                q[3] = make_int4(y[12], y[13], y[14], y[15]);
-            }
+            int4* qe = reinterpret_cast<int4*>(t_dstE + slot * t_dst_slot);
+            int4* qo = reinterpret_cast<int4*>(t_dstO + slot * t_dst_slot);
+            qe[0] = make_int4(y[0], y[2], y[4], y[6]);
+            qe[1] = make_int4(y[8], y[10], y[12], y[14]);
+            qo[0] = make_int4(y[1], y[3], y[5], y[7]);
+            qo[1] = make_int4(y[9], y[11], y[13], y[15]);
         }
 
         /* ---- pack: the last stage's chunk u-1-M (finished in the previous step) -> int16 pairs,
@@ -329,10 +325,12 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
         {
             const int c2 = u - 1 - M;
             if (c2 >= p.warm_chunks && c2 < NC && tid < out_per_chunk / 4) {
-                const int slot = c2 & 1;
-                const int4 vi = *reinterpret_cast<const int4*>(fin + slot * out_per_chunk + 4 * tid);
-                const int4 vq = *reinterpret_cast<const int4*>(fin + (2 + slot) * out_per_chunk + 4 * tid);
-                const int yi[4] = {vi.x, vi.y, vi.z, vi.w}, yq[4] = {vq.x, vq.y, vq.z, vq.w};
+                const int sl = c2 & 1;
+                const int* fi = fin + sl * out_per_chunk + 2 * tid;       /* I: even part, odd part at + opc/2 */
+                const int* fq = fi + 2 * out_per_chunk;
+                const int2 ie = *reinterpret_cast<const int2*>(fi), io = *reinterpret_cast<const int2*>(fi + out_per_chunk / 2);
+                const int2 qe = *reinterpret_cast<const int2*>(fq), qo = *reinterpret_cast<const int2*>(fq + out_per_chunk / 2);
+                const int yi[4] = {ie.x, io.x, ie.y, io.y}, yq[4] = {qe.x, qo.x, qe.y, qo.y};
                 uint32_t o[4];
 #pragma unroll
                 for (int r = 0; r < 4; r++) {

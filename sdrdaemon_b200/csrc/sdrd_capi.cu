@@ -135,7 +135,10 @@ template <int M>
 void launch_decimate(const hb::Params& p, int n_seg, int S, rt::stream_t st)
 {
     constexpr int C0 = hb::chunk_for(M);
-    SDRD_LAUNCH((hb::decimate_kernel<M, C0>), n_seg, S, hb::Geo<C0>::NT, hb::Geo<C0>::smem_bytes(M, p.prologue), st, p);
+    if (p.round_add)
+        SDRD_LAUNCH((hb::decimate_kernel<M, C0, 1>), n_seg, S, hb::Geo<C0>::NT, hb::Geo<C0>::smem_bytes(M, p.prologue), st, p);
+    else
+        SDRD_LAUNCH((hb::decimate_kernel<M, C0, 0>), n_seg, S, hb::Geo<C0>::NT, hb::Geo<C0>::smem_bytes(M, p.prologue), st, p);
 }
 
 } /* namespace */
