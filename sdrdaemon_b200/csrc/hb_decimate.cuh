@@ -86,11 +86,12 @@ struct Geo {
 /* chunk size used for an M-stage cascade: the last stage's input needs >= TAIL entries per chunk
  * (C0 >= 32 * 2^M); smaller chunks mean smaller CTAs and more of them per SM */
 #ifndef SDRD_HB_C0_MIN
-#define SDRD_HB_C0_MIN 1024 /* build-time floor, for experiments */
+#define SDRD_HB_C0_MIN 1024 /* build-time floor (1024 or 2048), for experiments */
 #endif
 constexpr int chunk_for(int M)
 {
-    return (M == 6 || SDRD_HB_C0_MIN >= 2048) ? 2048 : ((M == 5 || SDRD_HB_C0_MIN >= 1024) ? 1024 : 512);
+    /* also needed: one tail-copy unit per thread, 32 * M <= C0 / 8 */
+    return (M >= 5 || SDRD_HB_C0_MIN >= 2048) ? 2048 : 1024;
 }
 
 /* logical entry -> physical entry (16 -> 20 padding) */
@@ -258,47 +259,106 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
         }
     }
 
+    /* per-thread constants of the tail copy (thread t copies one 16-byte unit of stage tq's plane) */
+    const bool tail_on = tid < 32 * M;               /* 32 * M <= NT for every supported (M, C0) */
+    const int tq_j = tid >> 5, tq_pc = (tid >> 3) & 3, tq_unit = tid & 7;
+    const int tq_off = 20 * (tq_unit >> 2) + 4 * (tq_unit & 3);
+    const int tq_n = C0 >> (tq_j + 1);
+    const int* const tq_src = G::plane(sbuf, tail_on ? tq_j : 0, tq_pc >> 1, tq_pc & 1, 0) + 20 * (tq_n >> 4) + tq_off;
+    int* const tq_dst = G::plane(sbuf, tail_on ? tq_j : 0, tq_pc >> 1, tq_pc & 1, 0) + tq_off;
+    const int tq_slot = G::region_phys(tail_on ? tq_j : 0);
+    const int ph_unpack = phys(TAIL + 4 * tid);
+    static_assert(32 * M <= NT, "one tail-copy unit per thread");
+
     for (int u = 0; u < NC + M + 1; u++) {
-        /* ---- operands of this step's half-band task (stage tj+1 consumes stage-tj chunk u-1-tj,
-         *      written in the previous step): fetched first, used after the unpack work ---- */
+        /* ================= loads: everything this step reads was written in earlier steps (or by
+         * the TMA), so all shared-memory loads are issued back to back and their latencies overlap */
         const int c = u - 1 - tj;
         const bool task_on = has_task && c >= 0 && c < NC;
         const int slot = c & 1;
         Fir16Regs fr;
         if (task_on) fir16_load(t_srcE + slot * t_src_slot, t_srcO + slot * t_src_slot, ti, fr);
 
-        /* ---- stage 0: unpack raw chunk u into int32 planes (component x parity) ---- */
-#if defined(SDRD_EXP_NOUNPACK)
-        if (u < 0) {
-#else
-        if (u < NC) {
-#endif
+        const int cq = u - 1 - tq_j;
+        const bool tail_now = tail_on && cq >= 0 && cq < NC;
+        int4 tail_v = make_int4(0, 0, 0, 0);
+        if (tail_now) tail_v = *reinterpret_cast<const int4*>(tq_src + (cq & 1) * tq_slot);
+
+        const int c2 = u - 1 - M;
+        const bool pack_now = c2 >= p.warm_chunks && c2 < NC && tid < out_per_chunk / 4;
+        int2 pk_ie = make_int2(0, 0), pk_io = pk_ie, pk_qe = pk_ie, pk_qo = pk_ie;
+        if (pack_now) {
+            const int* fi = fin + (c2 & 1) * out_per_chunk + 2 * tid; /* I: even part, odd part at + opc/2 */
+            const int* fq = fi + 2 * out_per_chunk;
+            pk_ie = *reinterpret_cast<const int2*>(fi);
+            pk_io = *reinterpret_cast<const int2*>(fi + out_per_chunk / 2);
+            pk_qe = *reinterpret_cast<const int2*>(fq);
+            pk_qo = *reinterpret_cast<const int2*>(fq + out_per_chunk / 2);
+        }
+
+        const bool unpack_now = u < NC;
+        uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+        const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)(u & 1) * raw_per_chunk);
+        if (unpack_now) {
             mbar_wait(&bars[u & 1], (uint32_t)((u >> 1) & 1));
-            const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)(u & 1) * raw_per_chunk);
-            int* EI = G::plane(sbuf, 0, 0, 0, u & 1);
-            int* EQ = G::plane(sbuf, 0, 0, 1, u & 1);
-            int* OI = G::plane(sbuf, 0, 1, 0, u & 1);
-            int* OQ = G::plane(sbuf, 0, 1, 1, u & 1);
-            /* thread q: cascade inputs 8q .. 8q+7 -> entries 4q .. 4q+3 of each plane */
-            const int ph = phys(TAIL + 4 * tid);
             if (!pro) {
-                const uint4 a = r4[2 * tid], b = r4[2 * tid + 1];
-                *reinterpret_cast<int4*>(EI + ph) = make_int4(s16lo(a.x), s16lo(a.z), s16lo(b.x), s16lo(b.z));
-                *reinterpret_cast<int4*>(EQ + ph) = make_int4(s16hi(a.x), s16hi(a.z), s16hi(b.x), s16hi(b.z));
-                *reinterpret_cast<int4*>(OI + ph) = make_int4(s16lo(a.y), s16lo(a.w), s16lo(b.y), s16lo(b.w));
-                *reinterpret_cast<int4*>(OQ + ph) = make_int4(s16hi(a.y), s16hi(a.w), s16hi(b.y), s16hi(b.w));
-            } else {
-                int2 x[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = rot4(r4[8 * tid + k], pro);
-                *reinterpret_cast<int4*>(EI + ph) = make_int4(x[0].x, x[2].x, x[4].x, x[6].x);
-                *reinterpret_cast<int4*>(EQ + ph) = make_int4(x[0].y, x[2].y, x[4].y, x[6].y);
-                *reinterpret_cast<int4*>(OI + ph) = make_int4(x[1].x, x[3].x, x[5].x, x[7].x);
-                *reinterpret_cast<int4*>(OQ + ph) = make_int4(x[1].y, x[3].y, x[5].y, x[7].y);
+                ra = r4[2 * tid];
+                rb = r4[2 * tid + 1];
             }
         }
 
-        /* ---- half-band task ---- */
+        /* ================= stage 0: unpack raw chunk u into int32 planes (component x parity);
+         * thread q: cascade inputs 8q .. 8q+7 -> entries 4q .. 4q+3 of each plane */
+        if (unpack_now) {
+            int* EI = G::plane(sbuf, 0, 0, 0, u & 1) + ph_unpack;
+            int* EQ = G::plane(sbuf, 0, 0, 1, u & 1) + ph_unpack;
+            int* OI = G::plane(sbuf, 0, 1, 0, u & 1) + ph_unpack;
+            int* OQ = G::plane(sbuf, 0, 1, 1, u & 1) + ph_unpack;
+            if (!pro) {
+                *reinterpret_cast<int4*>(EI) = make_int4(s16lo(ra.x), s16lo(ra.z), s16lo(rb.x), s16lo(rb.z));
+                *reinterpret_cast<int4*>(EQ) = make_int4(s16hi(ra.x), s16hi(ra.z), s16hi(rb.x), s16hi(rb.z));
+                *reinterpret_cast<int4*>(OI) = make_int4(s16lo(ra.y), s16lo(ra.w), s16lo(rb.y), s16lo(rb.w));
+                *reinterpret_cast<int4*>(OQ) = make_int4(s16hi(ra.y), s16hi(ra.w), s16hi(rb.y), s16hi(rb.w));
+            } else {
+                /* infra/supra-dyne: 4 raw samples -> one cascade input */
+                int2 x[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = rot4(r4[8 * tid + k], pro);
+                *reinterpret_cast<int4*>(EI) = make_int4(x[0].x, x[2].x, x[4].x, x[6].x);
+                *reinterpret_cast<int4*>(EQ) = make_int4(x[0].y, x[2].y, x[4].y, x[6].y);
+                *reinterpret_cast<int4*>(OI) = make_int4(x[1].x, x[3].x, x[5].x, x[7].x);
+                *reinterpret_cast<int4*>(OQ) = make_int4(x[1].y, x[3].y, x[5].y, x[7].y);
+            }
+        }
+
+        /* ================= tail copy: last TAIL entries of the chunk consumed in this step -> front
+         * of the other slot, where the next chunk's consumer expects its history */
+#if !defined(SDRD_EXP_NOTAIL)
+        if (tail_now) *reinterpret_cast<int4*>(tq_dst + ((cq & 1) ^ 1) * tq_slot) = tail_v;
+#endif
+
+        /* ================= pack: the last stage's chunk u-1-M (finished in the previous step) ->
+         * int16 pairs, (y << norm_shift) >> trunk_shift truncated to 16 bits (SDRDaemon.h:59) */
+        if (pack_now) {
+            const int yi[4] = {pk_ie.x, pk_io.x, pk_ie.y, pk_io.y}, yq[4] = {pk_qe.x, pk_qo.x, pk_qe.y, pk_qo.y};
+            uint32_t o[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                uint32_t a = (uint32_t)asr32((uint32_t)yi[r] << p.norm_shift, p.trunk_shift);
+                uint32_t b = (uint32_t)asr32((uint32_t)yq[r] << p.norm_shift, p.trunk_shift);
+                o[r] = (a & 0xFFFFu) | (b << 16);
+            }
+            const long long n = seg_first_out + (long long)(c2 - p.warm_chunks) * out_per_chunk + 4 * tid;
+            if (n + 4 <= p.n_out) {
+                *reinterpret_cast<uint4*>(dst + n) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (n + r < p.n_out) dst[n + r] = o[r];
+            }
+        }
+
+        /* ================= half-band task: stage tj+1, chunk c ================= */
         if (task_on) {
             int y[16];
             fir16_compute(fr, acc0, steer, y);
@@ -320,51 +380,6 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
             qo[1] = make_int4(y[9], y[11], y[13], y[15]);
         }
 
-        /* ---- pack: the last stage's chunk u-1-M (finished in the previous step) -> int16 pairs,
-         *      (y << norm_shift) >> trunk_shift truncated to 16 bits (SDRDaemon.h:59) ---- */
-        {
-            const int c2 = u - 1 - M;
-            if (c2 >= p.warm_chunks && c2 < NC && tid < out_per_chunk / 4) {
-                const int sl = c2 & 1;
-                const int* fi = fin + sl * out_per_chunk + 2 * tid;       /* I: even part, odd part at + opc/2 */
-                const int* fq = fi + 2 * out_per_chunk;
-                const int2 ie = *reinterpret_cast<const int2*>(fi), io = *reinterpret_cast<const int2*>(fi + out_per_chunk / 2);
-                const int2 qe = *reinterpret_cast<const int2*>(fq), qo = *reinterpret_cast<const int2*>(fq + out_per_chunk / 2);
-                const int yi[4] = {ie.x, io.x, ie.y, io.y}, yq[4] = {qe.x, qo.x, qe.y, qo.y};
-                uint32_t o[4];
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    uint32_t a = (uint32_t)asr32((uint32_t)yi[r] << p.norm_shift, p.trunk_shift);
-                    uint32_t b = (uint32_t)asr32((uint32_t)yq[r] << p.norm_shift, p.trunk_shift);
-                    o[r] = (a & 0xFFFFu) | (b << 16);
-                }
-                const long long n = seg_first_out + (long long)(c2 - p.warm_chunks) * out_per_chunk + 4 * tid;
-                if (n + 4 <= p.n_out) {
-                    *reinterpret_cast<uint4*>(dst + n) = make_uint4(o[0], o[1], o[2], o[3]);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; r++)
-                        if (n + r < p.n_out) dst[n + r] = o[r];
-                }
-            }
-        }
-
-        /* ---- tail copies: last TAIL entries of the chunk consumed in this step -> front of the
-         *      other slot, where the next chunk's consumer expects its history ---- */
-#if defined(SDRD_EXP_NOTAIL)
-        for (int t = tid; t < 0; t += NT) {
-#else
-        for (int t = tid; t < 32 * M; t += NT) {
-#endif
-            const int j = t >> 5, pc = (t >> 3) & 3, unit = t & 7;
-            const int cc = u - 1 - j;
-            if (cc < 0 || cc >= NC) continue;
-            const int n = C0 >> (j + 1);
-            const int off = 20 * (unit >> 2) + 4 * (unit & 3);
-            const int* sp = G::plane(sbuf, j, pc >> 1, pc & 1, cc & 1) + 20 * (n >> 4) + off; /* entry TAIL+n-32 */
-            int* dp = G::plane(sbuf, j, pc >> 1, pc & 1, (cc & 1) ^ 1) + off;
-            *reinterpret_cast<int4*>(dp) = *reinterpret_cast<const int4*>(sp);
-        }
 #if !defined(SDRD_EXP_NOSYNC)
         __syncthreads();
 #endif
