@@ -34,10 +34,28 @@ if ROOT not in sys.path:
 
 import numpy as np
 
-M_LOG2 = 4
-N_FEC = 16
 FRAME_SAMPLES = 127 * 127
-FRAME_IN = FRAME_SAMPLES << M_LOG2  # 258064 input samples per superframe
+# BASELINE.json configs; 2 is the headline (default), the others are optional extra measurements
+WORKLOADS = {
+    2: dict(M=4, F=16, S=1, frames=592, rate=10_000_000,
+            name="config2: 10 Msps int16 IQ stream, decimate-by-16 centred (4 half-band stages), 128+16 FEC"),
+    3: dict(M=5, F=32, S=256, frames=8, rate=20_000_000,
+            name="config3: 256 streams @ 20 Msps, decimate-by-32, 128+32 FEC"),
+    5: dict(M=6, F=32, S=256, frames=2, rate=61_440_000,
+            name="config5 (per-GPU shard): 256 streams @ 61.44 Msps, decimate-by-64, 128+32 FEC"),
+}
+M_LOG2, N_FEC, N_STREAMS = 4, 16, 1
+FRAME_IN = FRAME_SAMPLES << M_LOG2  # input samples per superframe (258064 at decimate-by-16)
+
+
+def select_workload(cfg: int, frames=None):
+    global M_LOG2, N_FEC, N_STREAMS, FRAME_IN
+    w = dict(WORKLOADS[cfg])
+    if frames:
+        w["frames"] = frames
+    M_LOG2, N_FEC, N_STREAMS = w["M"], w["F"], w["S"]
+    FRAME_IN = FRAME_SAMPLES << M_LOG2
+    return w
 METRIC = "Msamples/s IQ through decimate+FEC"
 UNIT = "Msamples/s"
 
@@ -131,10 +149,10 @@ def cpu_leg(seconds: float, cores: int):
     dt = time.perf_counter() - t0
     assert fr == cores * frames, (fr, cores, frames)
     msps = x.shape[0] * x.shape[1] / dt / 1e6
-    sample = (f"{cores} streams x {frames} superframes ({cores * frames * FRAME_IN} samples) of config 2, one stream per "
+    sample = (f"{cores} streams x {frames} superframes ({cores * frames * FRAME_IN} samples) of the workload, one stream per "
               f"thread, 65536-sample blocks; decimator = reference Decimators.cpp (EO1/SSE4.1 build), FEC = restated "
               f"CM256 scalar tables" if kind == "reference" else
-              f"{cores} streams x {frames} superframes of config 2; C restatement (oracle port)")
+              f"{cores} streams x {frames} superframes of the workload; C restatement (oracle port)")
     return {"value": round(msps, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, dt
 
 
@@ -161,11 +179,95 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "config2: 10 Msps int16 IQ, decimate-by-16 centred, 128+16 FEC (CPU, bounded sample per step)"},
+        "config": {"workload": WORKLOADS[args.config]["name"] + " (reference CPU path, bounded sample per step)",
+                   "log2_decim": M_LOG2, "n_fec": N_FEC},
         "cpu_baseline": base,
         "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_decode(args):
+    """BASELINE config 4: 4096 superframes, 20 of 128 blocks erased (F = 32), recover on the GPU."""
+    import ctypes as C
+
+    import torch
+
+    from sdrdaemon_b200 import capi
+
+    if args.impl == "reference":
+        from oracle import bindings as ob
+
+        rng = np.random.default_rng(0xFEC0)
+        nf, F = 64, 32
+        x = rng.integers(-32768, 32768, size=(nf * FRAME_SAMPLES, 2), dtype=np.int16)
+        sk = ob.Sink(n_fec=F)
+        sk.write(x)
+        frames = np.stack(sk.frames)
+        sbs = []
+        for f in range(nf):
+            keep = np.ones(128, bool)
+            keep[rng.permutation(128)[:20]] = False
+            sbs.append(np.concatenate([frames[f, :128][keep], frames[f, 128:148]]))
+        t0 = time.perf_counter()
+        for sb in sbs:
+            ob.decode_frame(sb)
+        dt = time.perf_counter() - t0
+        v = nf / dt / 1e6
+        print(json.dumps({"impl": "reference", "metric": "Msuperframes/s recovered (20/128 erasures)", "value": round(v, 6),
+                          "unit": "Msuperframes/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "higher_is_better": True,
+                          "config": {"workload": "config4 (reference-shaped CPU decode, 1 thread, 64 frames)"},
+                          "cpu_baseline": {"value": round(v, 6), "unit": "Msuperframes/s", "cores": 1, "kind": "port",
+                                           "sample": "64 superframes, SDRdaemonFECBuffer logic + restated CM256"}}), flush=True)
+        return
+    lib = capi.load()
+    torch.cuda.set_device(0)
+    rng = np.random.default_rng(0xFEC0)
+    nf, F = 4096, 32
+    x = rng.integers(-32768, 32768, size=(1, nf * FRAME_SAMPLES, 2), dtype=np.int16)
+    sk = capi.Sink(max_samples=nf * FRAME_SAMPLES, n_fec=F)
+    frames = sk.write(x)[0]
+    sb = np.zeros((nf, 128, 512), np.uint8)
+    for f in range(nf):
+        keep = np.ones(128, bool)
+        keep[rng.permutation(128)[:20]] = False
+        sb[f, :108] = frames[f, :128][keep]
+        sb[f, 108:] = frames[f, 128:148]
+    d_sb = torch.from_numpy(sb).cuda()
+    d_nb = torch.full((nf,), 128, dtype=torch.int32, device="cuda")
+    d_pay = torch.empty((nf, 127, 508), dtype=torch.uint8, device="cuda")
+    d_b0 = torch.empty((nf, 508), dtype=torch.uint8, device="cuda")
+    d_st = torch.empty((nf,), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.Stream()
+
+    def step():
+        lib.check(lib.sdrd_fec_decode_dev(d_sb.data_ptr(), 128, d_nb.data_ptr(), nf, d_pay.data_ptr(), d_b0.data_ptr(),
+                                          d_st.data_ptr(), C.c_void_p(stream.cuda_stream)))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    stream.synchronize()
+    ok = bool((d_st == 2).all()) and bool((d_pay.cpu().numpy() == frames[:, 1:128, 4:]).all())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = min(args.steps, 200)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, peak_src = measured_peaks()
+    alg = nf * (128 * 512 + 127 * 508)
+    print(json.dumps({"metric": "Msuperframes/s recovered (20/128 erasures)", "value": round(nf / ms / 1e3, 3),
+                      "unit": "Msuperframes/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
+                      "higher_is_better": True, "dtype": "u8 (GF(2^8))", "data": "synthetic",
+                      "config": {"workload": "config4: 4096 superframes, 20/128 random erasures, F=32, bit-exact recover",
+                                 "parity": "all frames recovered == transmitted" if ok else "MISMATCH"},
+                      "gpu_launches": 2 * steps,
+                      "roofline": {"bound": "hbm", "kernel": "fec::decode_kernel<32> (K3)", "achieved": round(alg / ms / 1e6, 1),
+                                   "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": None,
+                                   "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                                   "note": "K3 is ALU-pipe bound (PRMT/LOP3 table arithmetic), see DESIGN.md"}}), flush=True)
 
 
 class DevView:
@@ -181,11 +283,16 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--frames", type=int, default=592, help="superframes per step per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json config (2 = headline)")
+    ap.add_argument("--frames", type=int, default=0, help="superframes per stream per step (default: per config)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    if args.config == 4:
+        return run_decode(args)
+    work = select_workload(args.config, args.frames or None)
+    args.frames = work["frames"]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -205,15 +312,19 @@ def main():
     lib = capi.load()
     lib.check(lib.sdrd_set_device(local))
 
-    S = 1
+    S = N_STREAMS
     n_in = args.frames * FRAME_IN
-    rx = capi.Rx(M_LOG2, n_streams=S, max_in=n_in, n_fec=N_FEC, sample_rate=625000)
+    out_rate = work["rate"] >> M_LOG2
+    rx = capi.Rx(M_LOG2, n_streams=S, max_in=n_in, n_fec=N_FEC, sample_rate=out_rate)
     dec_h, sink = rx.dec_handle, rx.sink
     in_ptr, in_stride = rx.dev_input()
-    dev_in = torch.as_tensor(DevView(in_ptr, n_in * 4), device="cuda").view(torch.int16)
+    # zero-copy view of the handle's input buffer: row s = stream s (pitch in_stride samples)
+    dev_all = torch.as_tensor(DevView(in_ptr, ((S - 1) * in_stride + n_in) * 4), device="cuda").view(torch.int16)
+    dev_in = torch.as_strided(dev_all, (S, n_in * 2), (in_stride * 2, 1))
     g = torch.Generator(device="cuda")
     g.manual_seed(0x5D12DAE0 + rank)
-    dev_in.copy_(torch.randint(-32768, 32768, (n_in * 2,), dtype=torch.int16, device="cuda", generator=g))
+    for s0 in range(S):  # per stream: keeps the temporary small
+        dev_in[s0].copy_(torch.randint(-32768, 32768, (n_in * 2,), dtype=torch.int16, device="cuda", generator=g))
     torch.cuda.synchronize()
 
     stream = torch.cuda.Stream()
@@ -244,9 +355,9 @@ def main():
         dg_ptr, _ = sink.dev_datagrams()
         bpf = 128 + N_FEC
         dg0 = torch.as_tensor(DevView(dg_ptr, 2 * bpf * 512), device="cuda").cpu().numpy().reshape(2, bpf, 512)
-        x0 = dev_in[: 2 * 2 * FRAME_IN].cpu().numpy().reshape(-1, 2)
+        x0 = dev_in[0, : 2 * 2 * FRAME_IN].cpu().numpy().reshape(-1, 2)
         y0, _ = ob.Decimator(M_LOG2).process(x0)
-        osk = ob.Sink(n_fec=N_FEC, sample_rate=625000)
+        osk = ob.Sink(n_fec=N_FEC, sample_rate=out_rate)
         osk.write(y0)
         parity = "frames 0-1 bit-exact vs oracle" if np.array_equal(dg0, np.stack(osk.frames)) else "MISMATCH vs oracle"
     except Exception as e:  # the oracle is only the checker; its absence must not stop the measurement
@@ -290,7 +401,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_in = torch.empty((S, n_in, 2), dtype=torch.int16).pin_memory()
-        host_in.copy_(dev_in.view(S, n_in, 2).cpu())
+        host_in.copy_(dev_in.reshape(S, n_in, 2).cpu())
         bpf = 128 + N_FEC
         host_out = torch.empty((S, args.frames + 1, bpf, 512), dtype=torch.uint8).pin_memory()
         nfr = C.c_size_t(0)
@@ -344,8 +455,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {
-                "workload": f"config2: 10 Msps int16 IQ stream, decimate-by-16 centred (4 half-band stages), 128+16 FEC, "
-                            f"{args.frames} superframes ({n_in} samples, {n_in * 4 / 1e6:.0f} MB) per step per GPU",
+                "workload": f"{work['name']}, {args.frames} superframes per stream "
+                            f"({S * n_in} samples, {S * n_in * 4 / 1e6:.0f} MB) per step per GPU",
                 "log2_decim": M_LOG2, "n_fec": N_FEC, "streams_per_gpu": S, "frames_per_step": args.frames,
                 "l2": "inputs larger than L2 (no flush needed)", "parity": parity,
             },
@@ -354,7 +465,7 @@ def main():
             "stream_digests": [hex(int(v)) for v in digests] if digests is not None else None,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "hb::decimate_kernel<4> (K1)", "achieved": round(achieved, 1), "peak": peak,
+                "bound": "hbm", "kernel": f"hb::decimate_kernel<{M_LOG2}> (K1)", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "k1_ms_per_launch": round(k1_ms, 4), "algorithmic_bytes_per_launch": int(k1_bytes),
                 "whole_step": {"algorithmic_bytes": int(step_bytes), "achieved": round(step_bytes / (ms / args.steps * 1e-3) / 1e9, 1),

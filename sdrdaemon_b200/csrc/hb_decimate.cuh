@@ -172,6 +172,11 @@ SDRD_DEVICE void fir16_compute(const Fir16Regs& f, uint32_t acc0, const Steer st
     for (int r = 0; r < 16; r++) y[r] = asr32(mad_lo(f.e[1 + r], st.k8192, acc[r]), HB_SHIFT);
 }
 
+template <bool B>
+struct BoolTag {
+    static constexpr bool value = B;
+};
+
 SDRD_DEVICE int s16lo(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
 SDRD_DEVICE int s16hi(uint32_t v) { return ((int)v) >> 16; }
 
@@ -270,22 +275,25 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
     const int ph_unpack = phys(TAIL + 4 * tid);
     static_assert(32 * M <= NT, "one tail-copy unit per thread");
 
-    for (int u = 0; u < NC + M + 1; u++) {
+    /* One pipeline step.  CK = true: fill / drain steps, every role checks whether its chunk exists;
+     * CK = false: steady state (warm + M + 1 <= u < NC), all roles are live and no check is evaluated. */
+    auto step = [&](const int u, auto checked) {
+        constexpr bool CK = decltype(checked)::value;
         /* ================= loads: everything this step reads was written in earlier steps (or by
          * the TMA), so all shared-memory loads are issued back to back and their latencies overlap */
         const int c = u - 1 - tj;
-        const bool task_on = has_task && c >= 0 && c < NC;
+        const bool task_on = has_task && (!CK || (c >= 0 && c < NC));
         const int slot = c & 1;
         Fir16Regs fr;
         if (task_on) fir16_load(t_srcE + slot * t_src_slot, t_srcO + slot * t_src_slot, ti, fr);
 
         const int cq = u - 1 - tq_j;
-        const bool tail_now = tail_on && cq >= 0 && cq < NC;
+        const bool tail_now = tail_on && (!CK || (cq >= 0 && cq < NC));
         int4 tail_v = make_int4(0, 0, 0, 0);
         if (tail_now) tail_v = *reinterpret_cast<const int4*>(tq_src + (cq & 1) * tq_slot);
 
         const int c2 = u - 1 - M;
-        const bool pack_now = c2 >= p.warm_chunks && c2 < NC && tid < out_per_chunk / 4;
+        const bool pack_now = tid < out_per_chunk / 4 && (!CK || (c2 >= p.warm_chunks && c2 < NC));
         int2 pk_ie = make_int2(0, 0), pk_io = pk_ie, pk_qe = pk_ie, pk_qo = pk_ie;
         if (pack_now) {
             const int* fi = fin + (c2 & 1) * out_per_chunk + 2 * tid; /* I: even part, odd part at + opc/2 */
@@ -296,7 +304,7 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
             pk_qo = *reinterpret_cast<const int2*>(fq + out_per_chunk / 2);
         }
 
-        const bool unpack_now = u < NC;
+        const bool unpack_now = !CK || u < NC;
         uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
         const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)(u & 1) * raw_per_chunk);
         if (unpack_now) {
@@ -388,7 +396,13 @@ SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
             tma_load_1d(raw + (size_t)(u & 1) * raw_per_chunk, src + (size_t)(u + 2) * raw_per_chunk, chunk_bytes,
                         &bars[u & 1]);
         }
-    }
+    };
+
+    const int u_steady = p.warm_chunks + M + 1;
+    int u = 0;
+    for (; u < u_steady && u < NC + M + 1; u++) step(u, BoolTag<true>());
+    for (; u < NC; u++) step(u, BoolTag<false>());
+    for (; u < NC + M + 1; u++) step(u, BoolTag<true>());
 }
 
 /* ------------------------------------------------------------------------------------------
