@@ -3,6 +3,7 @@
 // warp-instructions per cycle per SM for several warps-per-SM settings.  Build:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o fir16_issue fir16_issue.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "../../sdrdaemon_b200/csrc/hb_decimate.cuh"
 using namespace sdrd; using namespace sdrd::hb;
@@ -37,13 +38,13 @@ __global__ void __launch_bounds__(128, 4) k(const uint32_t* in, uint32_t* out, i
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-int main()
+int main(int argc, char** argv)
 {
     uint32_t *in, *out; long long* cyc;
     cudaMalloc(&in, 65536 * 4); cudaMalloc(&out, 148 * 16 * 128 * 4); cudaMalloc(&cyc, 148 * 16 * 8);
     cudaMemset(in, 0x5A, 65536 * 4);
     Steer st = {0, 1, 32, 256, 8192};
-    int iters = 2000;
+    int iters = argc > 1 ? atoi(argv[1]) : 2000;
     for (int ctas_per_sm : {1, 2, 3, 4}) {
         int grid = 148 * ctas_per_sm;
         k<<<grid, 128>>>(in, out, 10, st, cyc);
@@ -57,8 +58,8 @@ int main()
         double avg = 0; for (int i = 0; i < grid; i++) avg += h[i]; avg /= grid;
         // instructions per iteration per warp: 16 outputs * (16 add + 16 mad + 1 centre + 1 shift) + ~20
         double inst = 562;
-        printf("warps/SM=%2d  ms=%.3f  cycles/iter/warp=%.1f  est. IPC/SM=%.2f (of 4)  [%s]\n", ctas_per_sm * 4, ms,
-               avg / iters, ctas_per_sm * 4 * inst / (avg / iters), cudaGetErrorString(cudaGetLastError()));
+        printf("warps/SM=%2d  ms=%.3f  cycles/iter/warp=%.1f  IPC/SM by clock64=%.2f  clock64 rate=%.0f MHz  IPC/SM by wall time at 1965 MHz=%.2f  [%s]\n", ctas_per_sm * 4, ms,
+               avg / iters, ctas_per_sm * 4 * inst / (avg / iters), avg / (ms * 1e3), ctas_per_sm * 4 * inst * iters / (ms * 1e-3) / 1965e6, cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }
