@@ -81,6 +81,8 @@ void launch(Dim3 grid, unsigned nthreads, size_t smem_bytes, Body body)
 #define SDRD_DYN_SMEM(name) unsigned char* name = sdrd_emu::t_cta->smem
 
 static inline void __syncthreads() { sdrd_emu::t_cta->bar->arrive_and_wait(); }
+/* kernels that use it run one warp per CTA, so the CTA barrier stands in for the warp barrier */
+#define SDRD_SYNCWARP() sdrd_emu::t_cta->bar->arrive_and_wait()
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned atomicXor(unsigned* a, unsigned v) { return __atomic_fetch_xor(a, v, __ATOMIC_RELAXED); }
@@ -133,6 +135,7 @@ static inline void mbar_wait(mbar_t* b, uint32_t parity)
 #define SDRD_KERNEL(bounds_threads, bounds_ctas) __global__ void __launch_bounds__(bounds_threads, bounds_ctas)
 #define SDRD_RESTRICT __restrict__
 #define SDRD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define SDRD_SYNCWARP() __syncwarp()
 
 namespace sdrd {
 typedef uint64_t mbar_t;
