@@ -1,4 +1,4 @@
-// fir16_issue.cu -- how fast can one SM issue the FIR body of hb_decimate.cuh when nothing else is in
+// fir16_issue.cu -- how fast can one SM issue a half-band FIR body (taps and steering of hb_decimate.cuh) when nothing else is in
 // the way (no shared memory, no barriers)?  Runs fir16_compute from registers in a loop and reports
 // warp-instructions per cycle per SM for several warps-per-SM settings.  Build:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o fir16_issue fir16_issue.cu
@@ -7,6 +7,36 @@
 #include <cuda_runtime.h>
 #include "../../sdrdaemon_b200/csrc/hb_decimate.cuh"
 using namespace sdrd; using namespace sdrd::hb;
+
+// the FIR body of K1 in its 16-output form (K1 itself now runs it as 32-output tasks in four groups of 8)
+struct Fir16Regs {
+    uint32_t w[48]; /* w[j] = O[n0 - 32 + j]: logical entries 16i .. 16i+47 = padded groups i .. i+2 */
+    uint32_t e[17]; /* e[j] = E[n0 - 16 + j]: group i+1 and the first entry of group i+2 */
+};
+
+SDRD_DEVICE void fir16_compute(const Fir16Regs& f, uint32_t acc0, const Steer st, int (&y)[16])
+{
+    constexpr int H[16] = SDRD_HB64_TAPS;
+    uint32_t acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) acc[r] = acc0;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            /* O[n - t] = w[32 + r - t], O[n - 31 + t] = w[1 + r + t] */
+            const uint32_t a = f.w[32 + r - t], b = f.w[1 + r + t];
+            const uint32_t sum = t < SDRD_HB_FMA_ADD_TAPS ? mad_lo(a, st.one, b) : add3(a, b, st.zero);
+            const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
+            acc[r] = mad_lo(sum, h, acc[r]);
+        }
+    }
+    /* centre taps E[n0 - 15 + r] = e[1 + r] */
+#pragma unroll
+    for (int r = 0; r < 16; r++) y[r] = asr32(mad_lo(f.e[1 + r], st.k8192, acc[r]), HB_SHIFT);
+}
+
+
 
 __global__ void __launch_bounds__(128, 4) k(const uint32_t* in, uint32_t* out, int iters, Steer st, long long* cyc)
 {

@@ -13,21 +13,30 @@
  * With prologue = 1/2 the cascade is fed by the infra/supra-dyne rotate-and-sum-of-four
  * (Decimators.cpp:337-367 and siblings): log2 decimation = M + 2.
  *
- * Design (B200, HBM/ALU streaming kernel, no tensor cores):
- *   - one CTA walks one SEGMENT of one stream's time axis, chunk by chunk (C0 raw samples), so the
- *     61*(2^M-1)-sample filter warm-up is paid once per segment, not once per tile;
- *   - raw chunks arrive through the TMA 1-D bulk copy (cp.async.bulk + mbarrier), double buffered;
- *   - all M stages run software-pipelined ACROSS chunks: in step u the "unpack" work handles chunk u
- *     and stage j+1 handles chunk u-1-j, so every step has ~C0/8 independent FIR tasks and a single
- *     __syncthreads();
- *   - a FIR task produces 16 consecutive outputs of one stage for ONE component (I or Q) from a
- *     48-entry window of odd-phase inputs held in registers (pre-add of the symmetric taps, then
- *     IMAD with immediate coefficients: 16 IADD3 + 16 IMAD per output);
- *   - stage buffers are int32 planes split by component and by sample parity (E = x[2k],
- *     O = x[2k+1]), padded 16 -> 20 entries so that 128-bit shared loads at a 16-entry thread stride
- *     are bank-conflict free; each double-buffer slot is preceded by a 32-entry tail copy of the
- *     previous chunk; the last stage leaves int32 results in a small staging buffer that the next
- *     step packs to int16 pairs and stores with 128-bit global writes.
+ * Design (B200; an instruction-issue / shared-memory bound streaming kernel, no tensor cores):
+ * one WARP (a 32-thread CTA) walks one segment of one stream through all M stages.
+ *
+ *   - a step consumes WC0 = 512 cascade-input samples (2 KB, one TMA bulk copy, double buffered) and
+ *     every lane owns one FIR task of 32 outputs x one component for the life of the warp:
+ *         lanes  0-15  stage 1 (8 tasks per component)      lanes 24-27  stage 3
+ *         lanes 16-23  stage 2                              lanes 28-29  stage 4
+ *         lanes 30-31  stage 5 on every 2nd step (32 outputs need two chunks) and, on the steps in
+ *                      between, stage 6 on every 4th
+ *     so 30 of 32 lanes (M = 4) .. 31.5 of 32 (M = 6) do FIR work in every step and there is no
+ *     CTA-wide barrier anywhere: the stages are software-pipelined across steps (stage j works on the
+ *     chunk unpacked j steps earlier) and a step is  loads | __syncwarp | arithmetic + stores |
+ *     __syncwarp.  Warps drift apart freely, which is what keeps the four schedulers of an SM fed
+ *     (12 resident warps per SM: 3 per scheduler, <= 168 registers);
+ *   - a task of 32 outputs reads a window of 64 odd-phase + 33 even-phase inputs (3 words per output;
+ *     a 16-output task needs 4): shared-memory bandwidth (128 B/clk/SM) is the second limit of this
+ *     kernel right behind instruction issue, see DESIGN.md;
+ *   - because every load of a step precedes every store, a stage buffer is a single linear region
+ *     [32 history entries | the step's new entries] per (stage, component, parity) -- no double
+ *     buffer; a few lanes shift the last 32 entries down after the consumers have read them;
+ *   - regions are padded 32 -> 36 words and placed at chosen residues mod 32 words so that the eight
+ *     lanes of every quarter-warp hit eight different 16-byte bank groups on every LDS.128 / STS.128;
+ *   - the last stage leaves int32 results in a small staging area that the next step packs to int16
+ *     pairs, one output per lane, coalesced.
  *
  * This file is single-source: nvcc builds the product kernel, tests/emu builds the same code for
  * the host (see sdrd_platform.cuh).
@@ -37,9 +46,6 @@
 
 namespace sdrd {
 namespace hb {
-
-constexpr int TAIL = 32;    /* entries (per parity) of the previous chunk kept in front of a slot */
-constexpr int MAX_STAGES = 6;
 
 /* HBFIRFilterTraits<64>::hbCoeffs as integers (sdmnbase/HBFilterTraits.cpp:210-228, Q14, truncated
  * toward zero), outermost tap first; centre tap is 1 << 13. */
@@ -61,42 +67,6 @@ struct Params {
     uint32_t steer_zero, steer_one, steer_k32, steer_k256, steer_k8192; /* 0, 1, 32, 256, 8192: see Steer */
 };
 
-/* Geometry for a chunk of C0 cascade-input samples handled by C0/8 threads. */
-template <int C0>
-struct Geo {
-    static constexpr int NT = C0 / 8;
-    static constexpr int LOG2_NT = (C0 == 512 ? 6 : C0 == 1024 ? 7 : 8);
-    static_assert(C0 == 512 || C0 == 1024 || C0 == 2048, "supported chunk sizes");
-    /* all in int32 entries */
-    SDRD_HD static constexpr int stage_base(int m) { return 10 * (TAIL * m + C0 - (C0 >> m)); }
-    SDRD_HD static constexpr int region_phys(int m) { return ((TAIL + (C0 >> (m + 1))) >> 4) * 20; }
-    /* [T | S] region of stage m's output: parity (0 = even samples), component (0 = I), slot */
-    SDRD_HD static int* plane(int* sbuf, int m, int parity, int comp, int slot)
-    {
-        return sbuf + stage_base(m) + ((parity * 2 + comp) * 2 + slot) * region_phys(m);
-    }
-    SDRD_HD static constexpr size_t raw_bytes(int prologue) { return (size_t)2 * (prologue ? 4 : 1) * C0 * 4; }
-    /* raw double buffer | 2 mbarriers | stage planes | last-stage staging [comp][slot][C0 >> M] */
-    SDRD_HD static constexpr size_t smem_bytes(int M, int prologue)
-    {
-        return raw_bytes(prologue) + 128 + (size_t)(10 * (TAIL * M + C0 - (C0 >> M))) * 4 + (size_t)4 * (C0 >> M) * 4;
-    }
-};
-
-/* chunk size used for an M-stage cascade: the last stage's input needs >= TAIL entries per chunk
- * (C0 >= 32 * 2^M); smaller chunks mean smaller CTAs and more of them per SM */
-#ifndef SDRD_HB_C0_MIN
-#define SDRD_HB_C0_MIN 1024 /* build-time floor (1024 or 2048), for experiments */
-#endif
-constexpr int chunk_for(int M)
-{
-    /* also needed: one tail-copy unit per thread, 32 * M <= C0 / 8 */
-    return (M >= 5 || SDRD_HB_C0_MIN >= 2048) ? 2048 : 1024;
-}
-
-/* logical entry -> physical entry (16 -> 20 padding) */
-SDRD_DEVICE int phys(int k) { return k + 4 * (k >> 4); }
-
 /* Pipe steering.  The FIR body is issue-bound: per output and component 16 pre-adds + 16
  * multiply-accumulates.  Left alone, ptxas turns about half of the pre-adds into IMAD.IADD, which
  * piles them onto the FMA pipe next to the IMADs (measured: fmaheavy 66 % busy, ALU 39 %, long
@@ -113,70 +83,6 @@ struct Steer {
 #define SDRD_HB_FMA_ADD_TAPS 1 /* taps (outermost first) whose pre-add runs on the FMA pipe */
 #endif
 
-/* 16 consecutive outputs n0 .. n0+15 (n0 = 16 i, chunk-local) of one half-band stage, one component.
- * srcE/srcO point at the [T | S] planes of the consumed chunk: logical entry TAIL + k is
- * E[k] = x[2k] resp. O[k] = x[2k+1] of the chunk, entries 0..TAIL-1 the previous chunk's tail.
- * y[n] needs O[n-31 .. n] and E[n-15].
- * fir16_load fetches the operands (issued at the top of a step so that the shared-memory latency
- * hides behind the unpack work), fir16_compute does the arithmetic. */
-struct Fir16Regs {
-    uint32_t w[48]; /* w[j] = O[n0 - 32 + j]: logical entries 16i .. 16i+47 = padded groups i .. i+2 */
-    uint32_t e[17]; /* e[j] = E[n0 - 16 + j]: group i+1 and the first entry of group i+2 */
-};
-
-SDRD_DEVICE void fir16_load(const int* SDRD_RESTRICT srcE, const int* SDRD_RESTRICT srcO, int i, Fir16Regs& f)
-{
-    const int4* po = reinterpret_cast<const int4*>(srcO + 20 * i);
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            int4 v = po[g * 5 + q];
-            f.w[g * 16 + 4 * q] = (uint32_t)v.x;
-            f.w[g * 16 + 4 * q + 1] = (uint32_t)v.y;
-            f.w[g * 16 + 4 * q + 2] = (uint32_t)v.z;
-            f.w[g * 16 + 4 * q + 3] = (uint32_t)v.w;
-        }
-    }
-    const int4* pe = reinterpret_cast<const int4*>(srcE + 20 * (i + 1));
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        int4 v = pe[q];
-        f.e[4 * q] = (uint32_t)v.x;
-        f.e[4 * q + 1] = (uint32_t)v.y;
-        f.e[4 * q + 2] = (uint32_t)v.z;
-        f.e[4 * q + 3] = (uint32_t)v.w;
-    }
-    f.e[16] = (uint32_t)srcE[20 * (i + 2)];
-}
-
-SDRD_DEVICE void fir16_compute(const Fir16Regs& f, uint32_t acc0, const Steer st, int (&y)[16])
-{
-    constexpr int H[16] = SDRD_HB64_TAPS;
-    uint32_t acc[16];
-#pragma unroll
-    for (int r = 0; r < 16; r++) acc[r] = acc0;
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-#pragma unroll
-        for (int t = 0; t < 16; t++) {
-            /* O[n - t] = w[32 + r - t], O[n - 31 + t] = w[1 + r + t] */
-            const uint32_t a = f.w[32 + r - t], b = f.w[1 + r + t];
-            const uint32_t sum = t < SDRD_HB_FMA_ADD_TAPS ? mad_lo(a, st.one, b) : add3(a, b, st.zero);
-            const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
-            acc[r] = mad_lo(sum, h, acc[r]);
-        }
-    }
-    /* centre taps E[n0 - 15 + r] = e[1 + r] */
-#pragma unroll
-    for (int r = 0; r < 16; r++) y[r] = asr32(mad_lo(f.e[1 + r], st.k8192, acc[r]), HB_SHIFT);
-}
-
-template <bool B>
-struct BoolTag {
-    static constexpr bool value = B;
-};
-
 SDRD_DEVICE int s16lo(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
 SDRD_DEVICE int s16hi(uint32_t v) { return ((int)v) >> 16; }
 
@@ -190,219 +96,428 @@ SDRD_DEVICE int2 rot4(uint4 v, int prologue)
     return make_int2(i0 - r1 - i2 + r3, -r0 - i1 + r2 + i3);
 }
 
-/* DB = 0: IntHalfbandFilterEO1, DB = 1: IntHalfbandFilterDB (+1 rounding of the centre tap, stage
- * outputs before the stream origin forced to 0) */
-template <int M, int C0, int DB>
-SDRD_KERNEL((C0 / 8), (512 / (C0 / 8))) decimate_kernel(Params p)
+#ifndef SDRD_K1_RAW_BUFS
+#define SDRD_K1_RAW_BUFS 2 /* 2: chunks arrive two steps ahead; 1: the next chunk is requested as soon as this one is in registers */
+#endif
+constexpr int WC0 = 512; /* cascade-input samples per step */
+constexpr int WNB = SDRD_K1_RAW_BUFS;
+constexpr int BLK = 36;  /* 32 entries + 4 words of padding */
+
+/* logical entry -> word offset inside a region */
+SDRD_HD constexpr int wphys(int k) { return k + 4 * (k >> 5); }
+/* logical entries of the region holding stage m's output (m = 0: the unpacked input), one parity, one
+ * component: 32 history + what one consumer step reads as new (m >= 4: two producer steps' worth) */
+SDRD_HD constexpr int wregion_entries(int m) { return m <= 3 ? 32 + (256 >> m) : 64; }
+SDRD_HD constexpr int wregion_words(int m) { return wregion_entries(m) / 32 * BLK; }
+/* start of a region modulo 32 words (a multiple of 4 words = one 16-byte bank group), chosen so that
+ * the mixed quarter-warps 16-23 (stage 2: 4 I + 4 Q tasks) and 24-31 (stages 3..6) are conflict free
+ * both when they load their windows and when they store their results */
+SDRD_HD constexpr int wresidue(int m, int comp)
 {
-    typedef Geo<C0> G;
-    constexpr int NT = G::NT;
-    static_assert((C0 >> M) >= TAIL, "chunk too small for this many stages");
+    return 4 * (m == 0 ? 0 : m == 1 ? (comp ? 4 : 0) : m == 2 ? (comp ? 2 : 0) : m == 3 ? (comp ? 5 : 4) : (comp ? 7 : 6));
+}
+/* word offset of region (m, parity, comp) from the start of the plane area; m = 6 gives the total */
+SDRD_HD constexpr int wplane_off(int m, int parity, int comp)
+{
+    int off = 0;
+    for (int mm = 0; mm < 6; mm++)
+        for (int pp = 0; pp < 2; pp++)
+            for (int cc = 0; cc < 2; cc++) {
+                const int r = wresidue(mm, cc);
+                off += ((r - off) % 32 + 32) % 32;
+                if (mm == m && pp == parity && cc == comp) return off;
+                off += wregion_words(mm);
+            }
+    return off;
+}
+SDRD_HD constexpr int wfin_n(int M) { return (WC0 >> M) > 32 ? (WC0 >> M) : 32; } /* outputs per pack event */
+SDRD_HD constexpr int wfin_stride(int M) { return wfin_n(M) + 4; }                  /* words between the I and Q results */
+SDRD_HD constexpr int wmacro(int M) { return M <= 4 ? 1 : 1 << (M - 4); }           /* steps per pack event */
+/* steps between unpacking the first chunk of a pack event and packing its outputs */
+SDRD_HD constexpr int wdelay(int M) { return M <= 4 ? M + 1 : (M == 5 ? 7 : 10); }
+SDRD_HD constexpr int wraw_words(int PRO) { return PRO ? 4 * WC0 : WC0; }
+/* raw double buffer | 2 mbarriers | regions of stages 0..M-1 | 8 words | last stage's results */
+SDRD_HD constexpr size_t wsmem_bytes(int M, int PRO)
+{
+    return (size_t)WNB * wraw_words(PRO) * 4 + 128 + (size_t)(wplane_off(M, 0, 0) + 40) * 4 + (size_t)2 * wfin_stride(M) * 4;
+}
+/* warm-up chunks in front of a segment: >= 61 * (2^M - 1) samples, whole pack events */
+SDRD_HD constexpr int wwarm_chunks(int M)
+{
+    return ((61 * ((1 << M) - 1) + WC0 - 1) / WC0 + wmacro(M) - 1) / wmacro(M) * wmacro(M);
+}
+
+/* 32 consecutive outputs n0 .. n0+31 of one half-band stage, one component.  srcO/srcE point at the
+ * task's first 32-entry block of the consumed regions: w[j] = O[n0 - 32 + j], e[j] = E[n0 - 16 + j]. */
+struct Fir32Regs {
+    uint32_t w[64];
+    uint32_t e[33];
+};
+
+SDRD_DEVICE void fir32_load(const int* SDRD_RESTRICT srcE, const int* SDRD_RESTRICT srcO, Fir32Regs& f)
+{
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        const int4* po = reinterpret_cast<const int4*>(srcO + BLK * b);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            int4 v = po[q];
+            f.w[32 * b + 4 * q] = (uint32_t)v.x;
+            f.w[32 * b + 4 * q + 1] = (uint32_t)v.y;
+            f.w[32 * b + 4 * q + 2] = (uint32_t)v.z;
+            f.w[32 * b + 4 * q + 3] = (uint32_t)v.w;
+        }
+    }
+    /* entries 16 .. 31 of the first block, 0 .. 16 of the second */
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int4 v = *reinterpret_cast<const int4*>(srcE + (q < 4 ? 16 + 4 * q : BLK + 4 * (q - 4)));
+        f.e[4 * q] = (uint32_t)v.x;
+        f.e[4 * q + 1] = (uint32_t)v.y;
+        f.e[4 * q + 2] = (uint32_t)v.z;
+        f.e[4 * q + 3] = (uint32_t)v.w;
+    }
+    f.e[32] = (uint32_t)srcE[BLK + 16];
+}
+
+/* outputs 16 h .. 16 h + 15 of the task (h = 0, 1) */
+template <int HALF>
+SDRD_DEVICE void fir32_half(const Fir32Regs& f, uint32_t acc0, const Steer st, int (&y)[16])
+{
+    constexpr int H[16] = SDRD_HB64_TAPS;
+    uint32_t acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) acc[r] = acc0;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            const uint32_t a = f.w[16 * HALF + 32 + r - t], b = f.w[16 * HALF + 1 + r + t];
+            const uint32_t sum = t < SDRD_HB_FMA_ADD_TAPS ? mad_lo(a, st.one, b) : add3(a, b, st.zero);
+            const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
+            acc[r] = mad_lo(sum, h, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; r++) y[r] = asr32(mad_lo(f.e[16 * HALF + 1 + r], st.k8192, acc[r]), HB_SHIFT);
+}
+
+
+#ifndef SDRD_K1_WARPS_PER_SM
+#define SDRD_K1_WARPS_PER_SM 12 /* resident warps per SM the register budget is set for */
+#endif
+#ifndef SDRD_K1_PIPELINED
+#define SDRD_K1_PIPELINED 1
+#endif
+/* The same 32 outputs in an explicitly software-pipelined order: four groups of 8 outputs, and inside a
+ * group, tap by tap, the multiply-accumulate of tap t for output j followed by the pre-add of tap t + 1
+ * for the same output.  Every IMAD then reads a sum that was produced 15 instructions earlier and an
+ * accumulator written 16 instructions earlier, FMA- and ALU-pipe instructions alternate strictly, and
+ * only 8 + 8 registers are live besides the window -- a schedule ptxas keeps, instead of one it has to
+ * find under register pressure (it does not always: see DESIGN.md, K1 history). */
+template <int DB>
+SDRD_DEVICE void fir32_pipelined(const Fir32Regs& f, const Steer st, long long a0, int* SDRD_RESTRICT dE, int* SDRD_RESTRICT dO)
+{
+    constexpr int H[16] = SDRD_HB64_TAPS;
+    constexpr uint32_t acc0 = (uint32_t)DB << HB_SHIFT;
+    uint32_t tmp[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) tmp[j] = SDRD_HB_FMA_ADD_TAPS > 0 ? mad_lo(f.w[32 + j], st.one, f.w[1 + j]) : add3(f.w[32 + j], f.w[1 + j], st.zero);
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                acc[j] = mad_lo(tmp[j], h, t == 0 ? acc0 : acc[j]);
+                /* pre-add of the next tap (or of tap 0 of the next group) */
+                const int gn = t < 15 ? g : g + 1, tn = t < 15 ? t + 1 : 0;
+                if (gn < 4) {
+                    const uint32_t a = f.w[8 * gn + 32 + j - tn], b = f.w[8 * gn + 1 + j + tn];
+                    tmp[j] = tn < SDRD_HB_FMA_ADD_TAPS ? mad_lo(a, st.one, b) : add3(a, b, st.zero);
+                }
+            }
+        }
+        int y[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) y[j] = asr32(mad_lo(f.e[8 * g + 1 + j], st.k8192, acc[j]), HB_SHIFT);
+        if (DB && a0 + 8 * g < 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (a0 + 8 * g + j < 0) y[j] = 0;
+        }
+        reinterpret_cast<int4*>(dE)[g] = make_int4(y[0], y[2], y[4], y[6]);
+        reinterpret_cast<int4*>(dO)[g] = make_int4(y[1], y[3], y[5], y[7]);
+    }
+}
+
+template <int M, int DB, int PRO>
+SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
+{
+    static_assert(M >= 1 && M <= 6, "1..6 half-band stages");
+    constexpr int FN = wfin_n(M);
+    constexpr int FS = wfin_stride(M);
+    constexpr int MACRO = wmacro(M);
+    constexpr int DELAY = wdelay(M);
+    constexpr int OPL = FN / 32; /* outputs a lane packs per event */
+    constexpr int RAWW = wraw_words(PRO);
     SDRD_DYN_SMEM(smem);
-    const int tid = (int)threadIdx.x;
+    const int lane = (int)threadIdx.x;
     const int seg = (int)blockIdx.x;
     const int s = (int)blockIdx.y;
-    const int pro = p.prologue;
-    const int raw_per_chunk = pro ? 4 * C0 : C0; /* raw samples feeding one chunk of cascade input */
     uint32_t* raw = reinterpret_cast<uint32_t*>(smem);
-    mbar_t* bars = reinterpret_cast<mbar_t*>(smem + G::raw_bytes(pro));
-    int* sbuf = reinterpret_cast<int*>(smem + G::raw_bytes(pro) + 128);
-    constexpr int out_per_chunk = C0 >> M;
-    int* fin = sbuf + G::stage_base(M); /* last stage's results: [comp][slot][parity][out_per_chunk / 2] */
+    mbar_t* bars = reinterpret_cast<mbar_t*>(smem + (size_t)WNB * RAWW * 4);
+    int* planes = reinterpret_cast<int*>(smem + (size_t)WNB * RAWW * 4 + 128);
+    int* fin = planes + wplane_off(M, 0, 0) + 8; /* residue 8 words: the last stage's stores miss the others' banks */
 
     const long long seg_first_out = (long long)seg * p.seg_out;
     long long seg_n_out = p.n_out - seg_first_out;
     if (seg_n_out > p.seg_out) seg_n_out = p.seg_out;
-    const int data_chunks = (int)((seg_n_out + out_per_chunk - 1) / out_per_chunk);
-    const int NC = p.warm_chunks + data_chunks;
-    /* cascade-input index (relative to this call's first new sample) of chunk 0 */
-    const long long first_in = (seg_first_out << M) - (long long)p.warm_chunks * C0;
-    const uint32_t* src = p.in + (long long)s * p.in_stride + first_in * (pro ? 4 : 1);
-    uint32_t* dst = p.out + (long long)s * p.out_stride;
+    constexpr int warm_macro = wwarm_chunks(M) / MACRO;
+    const int n_macro = warm_macro + (int)((seg_n_out + FN - 1) / FN);
+    const int NC = n_macro * MACRO; /* chunks to unpack */
+    const int u_last = (n_macro - 1) * MACRO + DELAY;
+    const long long first_in = (seg_first_out << M) - (long long)wwarm_chunks(M) * WC0;
+    const uint32_t* src = p.in + (long long)s * p.in_stride + first_in * (PRO ? 4 : 1);
+    uint32_t* dst = p.out + (long long)s * p.out_stride + seg_first_out - (long long)warm_macro * FN;
+    const long long seg_room = p.n_out - seg_first_out + (long long)warm_macro * FN; /* valid: index < seg_room */
     const long long abs0 = p.origin + first_in;
     constexpr uint32_t acc0 = (uint32_t)DB << HB_SHIFT;
-    const uint32_t chunk_bytes = (uint32_t)raw_per_chunk * 4u;
+    constexpr uint32_t chunk_bytes = (uint32_t)RAWW * 4u;
     const Steer steer = {p.steer_zero, p.steer_one, p.steer_k32, p.steer_k256, p.steer_k8192};
 
-    /* ---- this thread's fixed role: FIR task t = tid of every step.  Stage j+1 has (C0/16) >> j tasks
-     *      (first half I, second half Q), C0/8 * (1 - 2^-M) < NT in total ---- */
-    constexpr int n_tasks = NT - (NT >> M);
-    const bool has_task = tid < n_tasks;
-    const int tj = has_task ? __clz(NT - 1 - tid) - (32 - G::LOG2_NT) : 0;
-    const int ta = tid - (NT - (NT >> tj));     /* index within the stage */
-    const int half = (NT >> tj) >> 2;           /* tasks per component: (C0/16 >> tj) / 2 */
-    const int tcomp = ta >= half ? 1 : 0;
-    const int ti = ta - tcomp * half;
-    const bool t_final = tj + 1 == M;
-    const int* const t_srcE = G::plane(sbuf, tj, 0, tcomp, 0);
-    const int* const t_srcO = G::plane(sbuf, tj, 1, tcomp, 0);
-    const int t_src_slot = G::region_phys(tj);
-    int* t_dstE;
-    int* t_dstO;
-    int t_dst_slot;
-    if (!t_final) {
-        t_dstE = G::plane(sbuf, tj + 1, 0, tcomp, 0) + phys(TAIL + 8 * ti);
-        t_dstO = G::plane(sbuf, tj + 1, 1, tcomp, 0) + phys(TAIL + 8 * ti);
-        t_dst_slot = G::region_phys(tj + 1);
+    /* ---- this lane's FIR task: source stage tm (0 = unpacked input), component, task index ---- */
+    int tm, tcomp, ti;
+    if (lane < 16)      { tm = 0; tcomp = lane >> 3;       ti = lane & 7; }
+    else if (lane < 24) { tm = 1; tcomp = (lane >> 2) & 1; ti = lane & 3; }
+    else if (lane < 28) { tm = 2; tcomp = (lane >> 1) & 1; ti = lane & 1; }
+    else if (lane < 30) { tm = 3; tcomp = lane & 1;        ti = 0; }
+    else                { tm = 4; tcomp = lane & 1;        ti = 0; }
+    const bool has_task = tm < M;
+    const bool sub_rate = lane >= 30; /* only meaningful when M >= 5 */
+    if (!has_task) tm = 0;
+    const int* srcE = planes + wplane_off(tm, 0, tcomp) + BLK * ti;
+    const int* srcO = planes + wplane_off(tm, 1, tcomp) + BLK * ti;
+    int* dstE;
+    int* dstO;
+    if (tm + 1 < M) {
+        dstE = planes + wplane_off(tm + 1, 0, tcomp) + wphys(32 + 16 * ti);
+        dstO = planes + wplane_off(tm + 1, 1, tcomp) + wphys(32 + 16 * ti);
     } else {
-        /* last stage: same even/odd split, into the staging buffer [comp][slot][parity][opc/2] */
-        t_dstE = fin + tcomp * 2 * out_per_chunk + 8 * ti;
-        t_dstO = t_dstE + out_per_chunk / 2;
-        t_dst_slot = out_per_chunk;
+        dstE = fin + tcomp * FS + 16 * ti;
+        dstO = dstE + FN / 2;
+    }
+    /* M = 6: lanes 30/31 alternate between stage 5 (regions 4 -> 5) and stage 6 (regions 5 -> fin) */
+    const int* srcE_b = planes + wplane_off(M == 6 ? 5 : 0, 0, tcomp);
+    const int* srcO_b = planes + wplane_off(M == 6 ? 5 : 0, 1, tcomp);
+    int* dstE_b = fin + tcomp * FS;
+    int* dstO_b = dstE_b + FN / 2;
+    /* producers of regions 4 and 5 fill them in two halves of 16 entries */
+    const bool dst_halves_4 = M >= 5 && (lane == 28 || lane == 29);
+    const bool dst_halves_5 = M == 6 && sub_rate;
+
+    /* ---- tail shift: 16-byte unit t of the 24 * M (per region pair: O 8 units, E the upper 4) ---- */
+    constexpr int TSLOTS = (24 * M + 31) / 32;
+    const int* tl_src[TSLOTS];
+    int tl_back[TSLOTS]; /* words from source to destination */
+    int tl_m[TSLOTS];
+#pragma unroll
+    for (int k = 0; k < TSLOTS; k++) {
+        const int t = lane + 32 * k;
+        const bool on = t < 24 * M;
+        const int m = on ? t / 24 : 0, r = t % 24;
+        const int comp = r / 12, rr = r % 12;
+        const int parity = rr < 8 ? 1 : 0;
+        const int unit = parity ? rr : 4 + (rr - 8);
+        tl_back[k] = (wregion_entries(m) - 32) / 32 * BLK;
+        tl_src[k] = planes + wplane_off(m, parity, comp) + 4 * unit + tl_back[k];
+        tl_m[k] = on ? m : -1;
     }
 
-    if (tid == 0) {
+    /* ---- unpack (no prologue): lane q reads 16-byte unit 32 k + q of the raw chunk, k = 0..3: samples
+     *      4 (32 k + q) .. + 3 -> entries 64 k + 2 q, + 1 of the four stage-0 regions.
+     *      (/4 prologue: lane q turns raw unit 32 k + q, k = 0..15, into cascade input 32 k + q) ---- */
+    int* const up = planes + (PRO ? wphys(32 + (lane >> 1)) : wphys(32 + 2 * lane));
+    constexpr int UP_EI = wplane_off(0, 0, 0), UP_EQ = wplane_off(0, 0, 1), UP_OI = wplane_off(0, 1, 0), UP_OQ = wplane_off(0, 1, 1);
+
+    /* ---- pack: lane l packs outputs OPL*l .. OPL*l+OPL-1 of an event; output r of a component sits at
+     *      fin[r even ? r/2 : FN/2 + r/2] ---- */
+    const int* const pk = fin + (OPL == 1 ? ((lane & 1) ? FN / 2 + (lane >> 1) : (lane >> 1)) : lane * (OPL / 2));
+
+    if (lane == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int c = 0; c < 2 && c < NC; c++) {
+        for (int c = 0; c < WNB && c < NC; c++) {
             mbar_arrive_expect_tx(&bars[c], chunk_bytes);
-            tma_load_1d(raw + (size_t)c * raw_per_chunk, src + (size_t)c * raw_per_chunk, chunk_bytes, &bars[c]);
+            tma_load_1d(raw + (size_t)c * RAWW, src + (size_t)c * RAWW, chunk_bytes, &bars[c]);
         }
     }
+    SDRD_SYNCWARP();
 
-    /* per-thread constants of the tail copy (thread t copies one 16-byte unit of stage tq's plane) */
-    const bool tail_on = tid < 32 * M;               /* 32 * M <= NT for every supported (M, C0) */
-    const int tq_j = tid >> 5, tq_pc = (tid >> 3) & 3, tq_unit = tid & 7;
-    const int tq_off = 20 * (tq_unit >> 2) + 4 * (tq_unit & 3);
-    const int tq_n = C0 >> (tq_j + 1);
-    const int* const tq_src = G::plane(sbuf, tail_on ? tq_j : 0, tq_pc >> 1, tq_pc & 1, 0) + 20 * (tq_n >> 4) + tq_off;
-    int* const tq_dst = G::plane(sbuf, tail_on ? tq_j : 0, tq_pc >> 1, tq_pc & 1, 0) + tq_off;
-    const int tq_slot = G::region_phys(tail_on ? tq_j : 0);
-    const int ph_unpack = phys(TAIL + 4 * tid);
-    static_assert(32 * M <= NT, "one tail-copy unit per thread");
-
-    /* One pipeline step.  CK = true: fill / drain steps, every role checks whether its chunk exists;
-     * CK = false: steady state (warm + M + 1 <= u < NC), all roles are live and no check is evaluated. */
-    auto step = [&](const int u, auto checked) {
-        constexpr bool CK = decltype(checked)::value;
-        /* ================= loads: everything this step reads was written in earlier steps (or by
-         * the TMA), so all shared-memory loads are issued back to back and their latencies overlap */
-        const int c = u - 1 - tj;
-        const bool task_on = has_task && (!CK || (c >= 0 && c < NC));
-        const int slot = c & 1;
-        Fir16Regs fr;
-        if (task_on) fir16_load(t_srcE + slot * t_src_slot, t_srcO + slot * t_src_slot, ti, fr);
-
-        const int cq = u - 1 - tq_j;
-        const bool tail_now = tail_on && (!CK || (cq >= 0 && cq < NC));
-        int4 tail_v = make_int4(0, 0, 0, 0);
-        if (tail_now) tail_v = *reinterpret_cast<const int4*>(tq_src + (cq & 1) * tq_slot);
-
-        const int c2 = u - 1 - M;
-        const bool pack_now = tid < out_per_chunk / 4 && (!CK || (c2 >= p.warm_chunks && c2 < NC));
-        int2 pk_ie = make_int2(0, 0), pk_io = pk_ie, pk_qe = pk_ie, pk_qo = pk_ie;
-        if (pack_now) {
-            const int* fi = fin + (c2 & 1) * out_per_chunk + 2 * tid; /* I: even part, odd part at + opc/2 */
-            const int* fq = fi + 2 * out_per_chunk;
-            pk_ie = *reinterpret_cast<const int2*>(fi);
-            pk_io = *reinterpret_cast<const int2*>(fi + out_per_chunk / 2);
-            pk_qe = *reinterpret_cast<const int2*>(fq);
-            pk_qo = *reinterpret_cast<const int2*>(fq + out_per_chunk / 2);
-        }
-
-        const bool unpack_now = !CK || u < NC;
-        uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
-        const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)(u & 1) * raw_per_chunk);
-        if (unpack_now) {
-            mbar_wait(&bars[u & 1], (uint32_t)((u >> 1) & 1));
-            if (!pro) {
-                ra = r4[2 * tid];
-                rb = r4[2 * tid + 1];
+    for (int u = 0; u <= u_last; u++) {
+        /* ================= phase A: every shared-memory read of the step ================= */
+        bool task_on = has_task;
+        const int* sE = srcE;
+        const int* sO = srcO;
+        int* dE = dstE;
+        int* dO = dstO;
+        int c_first = u - 1 - tm; /* first chunk this task's outputs come from (DB origin test) */
+        int t_stage = tm + 1;
+        if (M >= 5) {
+            if (sub_rate) {
+                const bool run_a = (u & 1) == 0;           /* stage 5 */
+                const bool run_b = M == 6 && (u & 3) == 1; /* stage 6 */
+                task_on = run_a || run_b;
+                if (run_b) { sE = srcE_b; sO = srcO_b; dE = dstE_b; dO = dstO_b; c_first = u - 9; t_stage = 6; }
+                else { c_first = u - 6; }
+                if (dst_halves_5 && run_a && (((u >> 1) & 1) == 0)) { dE += 16; dO += 16; } /* pair (u-6)/2 odd */
             }
+            if (dst_halves_4 && (u & 1)) { dE += 16; dO += 16; } /* chunk u-4 odd */
         }
+        Fir32Regs fr;
+        if (task_on) fir32_load(sE, sO, fr);
 
-        /* ================= stage 0: unpack raw chunk u into int32 planes (component x parity);
-         * thread q: cascade inputs 8q .. 8q+7 -> entries 4q .. 4q+3 of each plane */
-        if (unpack_now) {
-            int* EI = G::plane(sbuf, 0, 0, 0, u & 1) + ph_unpack;
-            int* EQ = G::plane(sbuf, 0, 0, 1, u & 1) + ph_unpack;
-            int* OI = G::plane(sbuf, 0, 1, 0, u & 1) + ph_unpack;
-            int* OQ = G::plane(sbuf, 0, 1, 1, u & 1) + ph_unpack;
-            if (!pro) {
-                *reinterpret_cast<int4*>(EI) = make_int4(s16lo(ra.x), s16lo(ra.z), s16lo(rb.x), s16lo(rb.z));
-                *reinterpret_cast<int4*>(EQ) = make_int4(s16hi(ra.x), s16hi(ra.z), s16hi(rb.x), s16hi(rb.z));
-                *reinterpret_cast<int4*>(OI) = make_int4(s16lo(ra.y), s16lo(ra.w), s16lo(rb.y), s16lo(rb.w));
-                *reinterpret_cast<int4*>(OQ) = make_int4(s16hi(ra.y), s16hi(ra.w), s16hi(rb.y), s16hi(rb.w));
-            } else {
-                /* infra/supra-dyne: 4 raw samples -> one cascade input */
-                int2 x[8];
+        int4 tl_v[TSLOTS];
+        bool tl_on[TSLOTS];
 #pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = rot4(r4[8 * tid + k], pro);
-                *reinterpret_cast<int4*>(EI) = make_int4(x[0].x, x[2].x, x[4].x, x[6].x);
-                *reinterpret_cast<int4*>(EQ) = make_int4(x[0].y, x[2].y, x[4].y, x[6].y);
-                *reinterpret_cast<int4*>(OI) = make_int4(x[1].x, x[3].x, x[5].x, x[7].x);
-                *reinterpret_cast<int4*>(OQ) = make_int4(x[1].y, x[3].y, x[5].y, x[7].y);
-            }
+        for (int k = 0; k < TSLOTS; k++) {
+            tl_on[k] = tl_m[k] >= 0 && (M <= 4 || tl_m[k] <= 3 || (tl_m[k] == 4 ? (u & 1) == 0 : (u & 3) == 1));
+            tl_v[k] = make_int4(0, 0, 0, 0);
+            if (tl_on[k]) tl_v[k] = *reinterpret_cast<const int4*>(tl_src[k]);
         }
 
-        /* ================= tail copy: last TAIL entries of the chunk consumed in this step -> front
-         * of the other slot, where the next chunk's consumer expects its history */
-#if !defined(SDRD_EXP_NOTAIL)
-        if (tail_now) *reinterpret_cast<int4*>(tq_dst + ((cq & 1) ^ 1) * tq_slot) = tail_v;
-#endif
-
-        /* ================= pack: the last stage's chunk u-1-M (finished in the previous step) ->
-         * int16 pairs, (y << norm_shift) >> trunk_shift truncated to 16 bits (SDRDaemon.h:59) */
-        if (pack_now) {
-            const int yi[4] = {pk_ie.x, pk_io.x, pk_ie.y, pk_io.y}, yq[4] = {pk_qe.x, pk_qo.x, pk_qe.y, pk_qo.y};
-            uint32_t o[4];
+        const int ev = u - DELAY; /* pack event e = ev / MACRO when ev is a non-negative multiple of MACRO */
+        const bool pack_now = ev >= warm_macro * MACRO && (MACRO == 1 || (ev & (MACRO - 1)) == 0);
+        int pki[OPL], pkq[OPL];
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                uint32_t a = (uint32_t)asr32((uint32_t)yi[r] << p.norm_shift, p.trunk_shift);
-                uint32_t b = (uint32_t)asr32((uint32_t)yq[r] << p.norm_shift, p.trunk_shift);
-                o[r] = (a & 0xFFFFu) | (b << 16);
-            }
-            const long long n = seg_first_out + (long long)(c2 - p.warm_chunks) * out_per_chunk + 4 * tid;
-            if (n + 4 <= p.n_out) {
-                *reinterpret_cast<uint4*>(dst + n) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int j = 0; j < OPL; j++) pki[j] = pkq[j] = 0;
+        if (pack_now) {
+            if (OPL == 1) {
+                pki[0] = pk[0];
+                pkq[0] = pk[FS];
             } else {
 #pragma unroll
-                for (int r = 0; r < 4; r++)
-                    if (n + r < p.n_out) dst[n + r] = o[r];
-            }
-        }
-
-        /* ================= half-band task: stage tj+1, chunk c ================= */
-        if (task_on) {
-            int y[16];
-            fir16_compute(fr, acc0, steer, y);
-            if (DB) {
-                /* DB: the reference's stages start from all-zero state, but a DB stage maps zero
-                 * input to 1; outputs that lie before the stream origin must read as 0. */
-                const long long a = ((abs0 + (long long)c * C0) >> (tj + 1)) + 16 * ti;
-                if (a < 0) {
-#pragma unroll
-                    for (int r = 0; r < 16; r++)
-                        if (a + r < 0) y[r] = 0;
+                for (int j = 0; j < OPL; j++) { /* output OPL*l + j: even -> entry (OPL*l + j)/2, odd -> FN/2 + .. */
+                    const int idx = (j & 1) ? FN / 2 + (j >> 1) : (j >> 1);
+                    pki[j] = pk[idx];
+                    pkq[j] = pk[FS + idx];
                 }
             }
-            int4* qe = reinterpret_cast<int4*>(t_dstE + slot * t_dst_slot);
-            int4* qo = reinterpret_cast<int4*>(t_dstO + slot * t_dst_slot);
-            qe[0] = make_int4(y[0], y[2], y[4], y[6]);
-            qe[1] = make_int4(y[8], y[10], y[12], y[14]);
-            qo[0] = make_int4(y[1], y[3], y[5], y[7]);
-            qo[1] = make_int4(y[9], y[11], y[13], y[15]);
         }
 
-#if !defined(SDRD_EXP_NOSYNC)
-        __syncthreads();
+        const bool unpack_now = u < NC;
+        uint4 rw[4];
+        int2 x[16];
+        if (unpack_now) {
+            const int rb = WNB == 2 ? (u & 1) : 0;
+            mbar_wait(&bars[rb], (uint32_t)((WNB == 2 ? (u >> 1) : u) & 1));
+            const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)rb * RAWW);
+            if (!PRO) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) rw[k] = r4[32 * k + lane];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = rot4(r4[32 * k + lane], p.prologue);
+            }
+        }
+        SDRD_SYNCWARP();
+        if (WNB == 1 && lane == 0 && u + 1 < NC) { /* every lane holds its part of chunk u in registers */
+            mbar_arrive_expect_tx(&bars[0], chunk_bytes);
+            tma_load_1d(raw, src + (size_t)(u + 1) * RAWW, chunk_bytes, &bars[0]);
+        }
+
+        /* ================= phase B: arithmetic and every shared-memory write of the step ========= */
+#pragma unroll
+        for (int k = 0; k < TSLOTS; k++)
+            if (tl_on[k]) *reinterpret_cast<int4*>(const_cast<int*>(tl_src[k]) - tl_back[k]) = tl_v[k];
+
+        if (unpack_now) {
+            if (!PRO) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) { /* entries 64 k + 2 q, + 1: two 32-entry blocks further per k */
+                    int* o = up + 2 * BLK * k;
+                    *reinterpret_cast<int2*>(o + UP_EI) = make_int2(s16lo(rw[k].x), s16lo(rw[k].z));
+                    *reinterpret_cast<int2*>(o + UP_EQ) = make_int2(s16hi(rw[k].x), s16hi(rw[k].z));
+                    *reinterpret_cast<int2*>(o + UP_OI) = make_int2(s16lo(rw[k].y), s16lo(rw[k].w));
+                    *reinterpret_cast<int2*>(o + UP_OQ) = make_int2(s16hi(rw[k].y), s16hi(rw[k].w));
+                }
+            } else {
+                /* cascade input 32 k + q: parity q & 1, entry 16 k + (q >> 1): half a block further per k */
+                int* oi = up + ((lane & 1) ? UP_OI : UP_EI);
+                int* oq = up + ((lane & 1) ? UP_OQ : UP_EQ);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    oi[(k >> 1) * BLK + (k & 1) * 16] = x[k].x;
+                    oq[(k >> 1) * BLK + (k & 1) * 16] = x[k].y;
+                }
+            }
+        }
+
+        if (pack_now) {
+            /* (y << norm_shift) >> trunk_shift truncated to 16 bits (Decimators.cpp:408-409, SDRDaemon.h:59) */
+            uint32_t o[OPL];
+#pragma unroll
+            for (int j = 0; j < OPL; j++) {
+                const uint32_t a = (uint32_t)asr32((uint32_t)pki[j] << p.norm_shift, p.trunk_shift);
+                const uint32_t b = (uint32_t)asr32((uint32_t)pkq[j] << p.norm_shift, p.trunk_shift);
+                o[j] = (a & 0xFFFFu) | (b << 16);
+            }
+            const long long n = (long long)(ev / MACRO) * FN + lane * OPL; /* relative to dst */
+            if (n + OPL <= seg_room) {
+                if (OPL == 1) {
+                    dst[n] = o[0];
+                } else if (OPL == 2) {
+                    *reinterpret_cast<uint2*>(dst + n) = make_uint2(o[0], o[OPL - 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j + 3 < OPL; j += 4)
+                        *reinterpret_cast<uint4*>(dst + n + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < OPL; j++)
+                    if (n + j < seg_room) dst[n + j] = o[j];
+            }
+        }
+
+        if (task_on) {
+            /* DB: the reference's stages start from all-zero state, but a DB stage maps zero input to 1;
+             * outputs that lie before the stream origin must read as 0. */
+            const long long a0 = DB ? ((abs0 + (long long)c_first * WC0) >> t_stage) + 32 * ti : 0;
+#if SDRD_K1_PIPELINED
+            fir32_pipelined<DB>(fr, steer, a0, dE, dO);
+#else
+            int y[16];
+            fir32_half<0>(fr, acc0, steer, y);
+            if (DB && a0 < 0) {
+#pragma unroll
+                for (int r = 0; r < 16; r++)
+                    if (a0 + r < 0) y[r] = 0;
+            }
+            reinterpret_cast<int4*>(dE)[0] = make_int4(y[0], y[2], y[4], y[6]);
+            reinterpret_cast<int4*>(dE)[1] = make_int4(y[8], y[10], y[12], y[14]);
+            reinterpret_cast<int4*>(dO)[0] = make_int4(y[1], y[3], y[5], y[7]);
+            reinterpret_cast<int4*>(dO)[1] = make_int4(y[9], y[11], y[13], y[15]);
+            fir32_half<1>(fr, acc0, steer, y);
+            if (DB && a0 + 16 < 0) {
+#pragma unroll
+                for (int r = 0; r < 16; r++)
+                    if (a0 + 16 + r < 0) y[r] = 0;
+            }
+            reinterpret_cast<int4*>(dE)[2] = make_int4(y[0], y[2], y[4], y[6]);
+            reinterpret_cast<int4*>(dE)[3] = make_int4(y[8], y[10], y[12], y[14]);
+            reinterpret_cast<int4*>(dO)[2] = make_int4(y[1], y[3], y[5], y[7]);
+            reinterpret_cast<int4*>(dO)[3] = make_int4(y[9], y[11], y[13], y[15]);
 #endif
-        if (tid == 0 && u + 2 < NC) {
-            mbar_arrive_expect_tx(&bars[u & 1], chunk_bytes);
-            tma_load_1d(raw + (size_t)(u & 1) * raw_per_chunk, src + (size_t)(u + 2) * raw_per_chunk, chunk_bytes,
-                        &bars[u & 1]);
         }
-    };
-
-    const int u_steady = p.warm_chunks + M + 1;
-    int u = 0;
-    for (; u < u_steady && u < NC + M + 1; u++) step(u, BoolTag<true>());
-    for (; u < NC; u++) step(u, BoolTag<false>());
-    for (; u < NC + M + 1; u++) step(u, BoolTag<true>());
+        SDRD_SYNCWARP();
+        if (WNB == 2 && lane == 0 && u + 2 < NC) {
+            mbar_arrive_expect_tx(&bars[u & 1], chunk_bytes);
+            tma_load_1d(raw + (size_t)(u & 1) * RAWW, src + (size_t)(u + 2) * RAWW, chunk_bytes, &bars[u & 1]);
+        }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -10,7 +10,7 @@
 
 #include "fec_kernels.cuh"
 #include "gf256_host.h"
-#include "hb_decimate_warp.cuh"
+#include "hb_decimate.cuh"
 #include "sdrd_rt.cuh"
 
 #include <sys/time.h>
@@ -131,17 +131,6 @@ void shift_rule(unsigned ss, int log2_decim, int* norm_shift, int* trunk_shift, 
     *ss_out = ss + (unsigned)log2_decim - trunk;
 }
 
-template <int M>
-void launch_decimate(const hb::Params& p, int n_seg, int S, rt::stream_t st)
-{
-    constexpr int C0 = hb::chunk_for(M);
-    if (p.round_add)
-        SDRD_LAUNCH((hb::decimate_kernel<M, C0, 1>), n_seg, S, hb::Geo<C0>::NT, hb::Geo<C0>::smem_bytes(M, p.prologue), st, p);
-    else
-        SDRD_LAUNCH((hb::decimate_kernel<M, C0, 0>), n_seg, S, hb::Geo<C0>::NT, hb::Geo<C0>::smem_bytes(M, p.prologue), st, p);
-}
-
-
 template <int M, int PRO>
 void launch_decimate_warp2(const hb::Params& p, int n_seg, int S, rt::stream_t st)
 {
@@ -157,16 +146,6 @@ void launch_decimate_warp(const hb::Params& p, int n_seg, int S, rt::stream_t st
         if (p.prologue) return launch_decimate_warp2<M, 1>(p, n_seg, S, st);
     }
     launch_decimate_warp2<M, 0>(p, n_seg, S, st);
-}
-
-/* A/B switch for experiments: SDRD_K1=cta selects the CTA-wide form of K1 (hb_decimate.cuh) */
-bool k1_use_cta_form()
-{
-    static const bool v = [] {
-        const char* e = getenv("SDRD_K1");
-        return e && strcmp(e, "cta") == 0;
-    }();
-    return v;
 }
 
 } /* namespace */
@@ -356,57 +335,31 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
             p.prologue = pro;
             p.origin = d->consumed / (pro ? 4 : 1);
             p.steer_zero = 0; p.steer_one = 1; p.steer_k32 = 32; p.steer_k256 = 256; p.steer_k8192 = 8192;
-            if (!k1_use_cta_form()) {
-                /* warp-private form: one warp per segment, segments sized for ONE wave of resident warps
-                 * (all segments are equally long, so there is no tail), but never so short that the
-                 * warm-up costs more than ~1/8 of a segment */
-                const int FN = hb::wfin_n(M);
-                const long long total_ev = ((long long)n_out + FN - 1) / FN;
-                const long long warm_ev = hb::wwarm_chunks(M) / hb::wmacro(M);
-                long long n_seg_max = total_ev / (8 * warm_ev);
-                if (n_seg_max < 1) n_seg_max = 1;
-                const size_t smem = hb::wsmem_bytes(M, pro ? 1 : 0);
-                long long resident = (long long)((227 * 1024) / (smem + 1024));
-                if (resident > 12) resident = 12;
-                long long want = resident * d->sms / d->S;
-                if (want < 1) want = 1;
-                long long n_seg = want < n_seg_max ? want : n_seg_max;
-                const long long seg_ev = (total_ev + n_seg - 1) / n_seg;
-                n_seg = (total_ev + seg_ev - 1) / seg_ev;
-                p.seg_out = (int)(seg_ev * FN);
-                p.warm_chunks = hb::wwarm_chunks(M);
-                switch (M) {
-                    case 1: launch_decimate_warp<1>(p, (int)n_seg, d->S, st); break;
-                    case 2: launch_decimate_warp<2>(p, (int)n_seg, d->S, st); break;
-                    case 3: launch_decimate_warp<3>(p, (int)n_seg, d->S, st); break;
-                    case 4: launch_decimate_warp<4>(p, (int)n_seg, d->S, st); break;
-                    case 5: launch_decimate_warp<5>(p, (int)n_seg, d->S, st); break;
-                    default: launch_decimate_warp<6>(p, (int)n_seg, d->S, st); break;
-                }
-            } else {
-                const int C0 = hb::chunk_for(M);
-                const int out_per_chunk = C0 >> M;
-                const long long total_chunks = ((long long)n_out + out_per_chunk - 1) / out_per_chunk;
-                p.warm_chunks = (61 * ((1 << M) - 1) + C0 - 1) / C0;
-                /* segments: enough CTAs for ~2 full waves of resident CTAs, but never so short that the
-                 * warm-up chunks cost more than ~1/8 of a segment */
-                long long n_seg_max = total_chunks / (8 * p.warm_chunks);
-                if (n_seg_max < 1) n_seg_max = 1;
-                const int ctas_per_sm = 512 / (C0 / 8);
-                long long want = (2LL * ctas_per_sm * d->sms + d->S - 1) / d->S;
-                long long n_seg = want < n_seg_max ? want : n_seg_max;
-                if (n_seg < 1) n_seg = 1;
-                long long seg_chunks = (total_chunks + n_seg - 1) / n_seg;
-                n_seg = (total_chunks + seg_chunks - 1) / seg_chunks;
-                p.seg_out = (int)(seg_chunks * out_per_chunk);
-                switch (M) {
-                    case 1: launch_decimate<1>(p, (int)n_seg, d->S, st); break;
-                    case 2: launch_decimate<2>(p, (int)n_seg, d->S, st); break;
-                    case 3: launch_decimate<3>(p, (int)n_seg, d->S, st); break;
-                    case 4: launch_decimate<4>(p, (int)n_seg, d->S, st); break;
-                    case 5: launch_decimate<5>(p, (int)n_seg, d->S, st); break;
-                    default: launch_decimate<6>(p, (int)n_seg, d->S, st); break;
-                }
+            /* one warp per segment, segments sized for ONE wave of resident warps
+             * (all segments are equally long, so there is no tail), but never so short that the
+             * warm-up costs more than ~1/8 of a segment */
+            const int FN = hb::wfin_n(M);
+            const long long total_ev = ((long long)n_out + FN - 1) / FN;
+            const long long warm_ev = hb::wwarm_chunks(M) / hb::wmacro(M);
+            long long n_seg_max = total_ev / (8 * warm_ev);
+            if (n_seg_max < 1) n_seg_max = 1;
+            const size_t smem = hb::wsmem_bytes(M, pro ? 1 : 0);
+            long long resident = (long long)((227 * 1024) / (smem + 1024));
+            if (resident > SDRD_K1_WARPS_PER_SM) resident = SDRD_K1_WARPS_PER_SM;
+            long long want = resident * d->sms / d->S;
+            if (want < 1) want = 1;
+            long long n_seg = want < n_seg_max ? want : n_seg_max;
+            const long long seg_ev = (total_ev + n_seg - 1) / n_seg;
+            n_seg = (total_ev + seg_ev - 1) / seg_ev;
+            p.seg_out = (int)(seg_ev * FN);
+            p.warm_chunks = hb::wwarm_chunks(M);
+            switch (M) {
+                case 1: launch_decimate_warp<1>(p, (int)n_seg, d->S, st); break;
+                case 2: launch_decimate_warp<2>(p, (int)n_seg, d->S, st); break;
+                case 3: launch_decimate_warp<3>(p, (int)n_seg, d->S, st); break;
+                case 4: launch_decimate_warp<4>(p, (int)n_seg, d->S, st); break;
+                case 5: launch_decimate_warp<5>(p, (int)n_seg, d->S, st); break;
+                default: launch_decimate_warp<6>(p, (int)n_seg, d->S, st); break;
             }
             d->launches++;
         }
