@@ -285,12 +285,16 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json config (2 = headline)")
     ap.add_argument("--frames", type=int, default=0, help="superframes per stream per step (default: per config)")
+    ap.add_argument("--log2-decim", type=int, default=0, help="experiments: override the workload's log2 decimation")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.config == 4:
         return run_decode(args)
+    if args.log2_decim:
+        WORKLOADS[args.config] = dict(WORKLOADS[args.config], M=args.log2_decim,
+                                      name=WORKLOADS[args.config]["name"] + f" [log2_decim overridden to {args.log2_decim}]")
     work = select_workload(args.config, args.frames or None)
     args.frames = work["frames"]
     if args.impl == "reference":

@@ -24,15 +24,16 @@
  *                      between, stage 6 on every 4th
  *     so 30 of 32 lanes (M = 4) .. 31.5 of 32 (M = 6) do FIR work in every step and there is no
  *     CTA-wide barrier anywhere: the stages are software-pipelined across steps (stage j works on the
- *     chunk unpacked j steps earlier) and a step is  loads | __syncwarp | arithmetic + stores |
- *     __syncwarp.  Warps drift apart freely, which is what keeps the four schedulers of an SM fed
- *     (12 resident warps per SM: 3 per scheduler, <= 168 registers);
+ *     chunk unpacked j steps earlier) and a step is  window loads + arithmetic | __syncwarp | stores |
+ *     __syncwarp : every read of a stage region precedes every write of the step, so a region is a
+ *     single linear buffer [32 history entries | the step's new entries] per (stage, component, parity)
+ *     -- no double buffer; a few lanes shift the last 32 entries down after the consumers have read
+ *     them.  Warps drift apart freely, which is what keeps the four schedulers of an SM fed (12 resident
+ *     warps per SM: 3 per scheduler, <= 168 registers, ~17 KB of shared memory each at M = 4);
  *   - a task of 32 outputs reads a window of 64 odd-phase + 33 even-phase inputs (3 words per output;
  *     a 16-output task needs 4): shared-memory bandwidth (128 B/clk/SM) is the second limit of this
- *     kernel right behind instruction issue, see DESIGN.md;
- *   - because every load of a step precedes every store, a stage buffer is a single linear region
- *     [32 history entries | the step's new entries] per (stage, component, parity) -- no double
- *     buffer; a few lanes shift the last 32 entries down after the consumers have read them;
+ *     kernel right behind instruction issue, see DESIGN.md.  The window streams through registers in
+ *     four groups of 8 outputs (fir32_stream);
  *   - regions are padded 32 -> 36 words and placed at chosen residues mod 32 words so that the eight
  *     lanes of every quarter-warp hit eight different 16-byte bank groups on every LDS.128 / STS.128;
  *   - the last stage leaves int32 results in a small staging area that the next step packs to int16
@@ -96,11 +97,7 @@ SDRD_DEVICE int2 rot4(uint4 v, int prologue)
     return make_int2(i0 - r1 - i2 + r3, -r0 - i1 + r2 + i3);
 }
 
-#ifndef SDRD_K1_RAW_BUFS
-#define SDRD_K1_RAW_BUFS 2 /* 2: chunks arrive two steps ahead; 1: the next chunk is requested as soon as this one is in registers */
-#endif
 constexpr int WC0 = 512; /* cascade-input samples per step */
-constexpr int WNB = SDRD_K1_RAW_BUFS;
 constexpr int BLK = 36;  /* 32 entries + 4 words of padding */
 
 /* logical entry -> word offset inside a region */
@@ -139,7 +136,7 @@ SDRD_HD constexpr int wraw_words(int PRO) { return PRO ? 4 * WC0 : WC0; }
 /* raw double buffer | 2 mbarriers | regions of stages 0..M-1 | 8 words | last stage's results */
 SDRD_HD constexpr size_t wsmem_bytes(int M, int PRO)
 {
-    return (size_t)WNB * wraw_words(PRO) * 4 + 128 + (size_t)(wplane_off(M, 0, 0) + 40) * 4 + (size_t)2 * wfin_stride(M) * 4;
+    return (size_t)2 * wraw_words(PRO) * 4 + 128 + (size_t)(wplane_off(M, 0, 0) + 40) * 4 + (size_t)2 * wfin_stride(M) * 4;
 }
 /* warm-up chunks in front of a segment: >= 61 * (2^M - 1) samples, whole pack events */
 SDRD_HD constexpr int wwarm_chunks(int M)
@@ -147,84 +144,46 @@ SDRD_HD constexpr int wwarm_chunks(int M)
     return ((61 * ((1 << M) - 1) + WC0 - 1) / WC0 + wmacro(M) - 1) / wmacro(M) * wmacro(M);
 }
 
-/* 32 consecutive outputs n0 .. n0+31 of one half-band stage, one component.  srcO/srcE point at the
- * task's first 32-entry block of the consumed regions: w[j] = O[n0 - 32 + j], e[j] = E[n0 - 16 + j]. */
-struct Fir32Regs {
-    uint32_t w[64];
-    uint32_t e[33];
-};
-
-SDRD_DEVICE void fir32_load(const int* SDRD_RESTRICT srcE, const int* SDRD_RESTRICT srcO, Fir32Regs& f)
-{
-#pragma unroll
-    for (int b = 0; b < 2; b++) {
-        const int4* po = reinterpret_cast<const int4*>(srcO + BLK * b);
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            int4 v = po[q];
-            f.w[32 * b + 4 * q] = (uint32_t)v.x;
-            f.w[32 * b + 4 * q + 1] = (uint32_t)v.y;
-            f.w[32 * b + 4 * q + 2] = (uint32_t)v.z;
-            f.w[32 * b + 4 * q + 3] = (uint32_t)v.w;
-        }
-    }
-    /* entries 16 .. 31 of the first block, 0 .. 16 of the second */
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        int4 v = *reinterpret_cast<const int4*>(srcE + (q < 4 ? 16 + 4 * q : BLK + 4 * (q - 4)));
-        f.e[4 * q] = (uint32_t)v.x;
-        f.e[4 * q + 1] = (uint32_t)v.y;
-        f.e[4 * q + 2] = (uint32_t)v.z;
-        f.e[4 * q + 3] = (uint32_t)v.w;
-    }
-    f.e[32] = (uint32_t)srcE[BLK + 16];
-}
-
-/* outputs 16 h .. 16 h + 15 of the task (h = 0, 1) */
-template <int HALF>
-SDRD_DEVICE void fir32_half(const Fir32Regs& f, uint32_t acc0, const Steer st, int (&y)[16])
-{
-    constexpr int H[16] = SDRD_HB64_TAPS;
-    uint32_t acc[16];
-#pragma unroll
-    for (int r = 0; r < 16; r++) acc[r] = acc0;
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-#pragma unroll
-        for (int t = 0; t < 16; t++) {
-            const uint32_t a = f.w[16 * HALF + 32 + r - t], b = f.w[16 * HALF + 1 + r + t];
-            const uint32_t sum = t < SDRD_HB_FMA_ADD_TAPS ? mad_lo(a, st.one, b) : add3(a, b, st.zero);
-            const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
-            acc[r] = mad_lo(sum, h, acc[r]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 16; r++) y[r] = asr32(mad_lo(f.e[16 * HALF + 1 + r], st.k8192, acc[r]), HB_SHIFT);
-}
-
-
 #ifndef SDRD_K1_WARPS_PER_SM
 #define SDRD_K1_WARPS_PER_SM 12 /* resident warps per SM the register budget is set for */
 #endif
-#ifndef SDRD_K1_PIPELINED
-#define SDRD_K1_PIPELINED 1
-#endif
-/* The same 32 outputs in an explicitly software-pipelined order: four groups of 8 outputs, and inside a
- * group, tap by tap, the multiply-accumulate of tap t for output j followed by the pre-add of tap t + 1
- * for the same output.  Every IMAD then reads a sum that was produced 15 instructions earlier and an
- * accumulator written 16 instructions earlier, FMA- and ALU-pipe instructions alternate strictly, and
- * only 8 + 8 registers are live besides the window -- a schedule ptxas keeps, instead of one it has to
- * find under register pressure (it does not always: see DESIGN.md, K1 history). */
+/* 32 consecutive outputs n0 .. n0+31 of one stage and component, from the regions the task's pointers
+ * address: w[j] = O[n0 - 32 + j], e[j] = E[n0 - 16 + j].  Four groups of 8 outputs; group g needs
+ * w[1 + 8g .. 39 + 8g] and e[1 + 8g .. 8 + 8g], so the operands of group g + 1 (2 + 2 vector loads) are
+ * requested while group g is being computed and at most ~50 window registers are live.  Inside a group
+ * the order is explicit: tap by tap, the multiply-accumulate of tap t for output j followed by the
+ * pre-add of tap t + 1 for the same output, so that FMA- and ALU-pipe instructions alternate and every
+ * IMAD reads operands produced ~16 instructions earlier. */
+SDRD_DEVICE void fir32_ld4(const int* p, uint32_t* d)
+{
+    const int4 v = *reinterpret_cast<const int4*>(p);
+    d[0] = (uint32_t)v.x; d[1] = (uint32_t)v.y; d[2] = (uint32_t)v.z; d[3] = (uint32_t)v.w;
+}
+/* 16-byte unit k of the window: w[4k .. 4k+3] resp. e[4k .. 4k+3] (e[0] is entry 16 of the first block) */
+SDRD_DEVICE const int* fir32_w_unit(const int* srcO, int k) { return srcO + (k < 8 ? 4 * k : BLK + 4 * (k - 8)); }
+SDRD_DEVICE const int* fir32_e_unit(const int* srcE, int k) { return srcE + (k < 4 ? 16 + 4 * k : BLK + 4 * (k - 4)); }
+
 template <int DB>
-SDRD_DEVICE void fir32_pipelined(const Fir32Regs& f, const Steer st, long long a0, int* SDRD_RESTRICT dE, int* SDRD_RESTRICT dO)
+SDRD_DEVICE void fir32_stream(const int* SDRD_RESTRICT srcE, const int* SDRD_RESTRICT srcO, const Steer st, long long a0, int (&y)[32])
 {
     constexpr int H[16] = SDRD_HB64_TAPS;
     constexpr uint32_t acc0 = (uint32_t)DB << HB_SHIFT;
-    uint32_t tmp[8], acc[8];
+    uint32_t w[64], e[36], tmp[8], acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) tmp[j] = SDRD_HB_FMA_ADD_TAPS > 0 ? mad_lo(f.w[32 + j], st.one, f.w[1 + j]) : add3(f.w[32 + j], f.w[1 + j], st.zero);
+    for (int k = 0; k < 10; k++) fir32_ld4(fir32_w_unit(srcO, k), &w[4 * k]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) fir32_ld4(fir32_e_unit(srcE, k), &e[4 * k]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) tmp[j] = SDRD_HB_FMA_ADD_TAPS > 0 ? mad_lo(w[32 + j], st.one, w[1 + j]) : add3(w[32 + j], w[1 + j], st.zero);
 #pragma unroll
     for (int g = 0; g < 4; g++) {
+        if (g < 3) { /* what group g + 1 adds to the window */
+            fir32_ld4(fir32_w_unit(srcO, 10 + 2 * g), &w[40 + 8 * g]);
+            fir32_ld4(fir32_w_unit(srcO, 11 + 2 * g), &w[44 + 8 * g]);
+            fir32_ld4(fir32_e_unit(srcE, 3 + 2 * g), &e[12 + 8 * g]);
+            if (g < 2) fir32_ld4(fir32_e_unit(srcE, 4 + 2 * g), &e[16 + 8 * g]);
+            else e[32] = (uint32_t)srcE[BLK + 16];
+        }
 #pragma unroll
         for (int t = 0; t < 16; t++) {
             const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
@@ -234,21 +193,20 @@ SDRD_DEVICE void fir32_pipelined(const Fir32Regs& f, const Steer st, long long a
                 /* pre-add of the next tap (or of tap 0 of the next group) */
                 const int gn = t < 15 ? g : g + 1, tn = t < 15 ? t + 1 : 0;
                 if (gn < 4) {
-                    const uint32_t a = f.w[8 * gn + 32 + j - tn], b = f.w[8 * gn + 1 + j + tn];
+                    const uint32_t a = w[8 * gn + 32 + j - tn], b = w[8 * gn + 1 + j + tn];
                     tmp[j] = tn < SDRD_HB_FMA_ADD_TAPS ? mad_lo(a, st.one, b) : add3(a, b, st.zero);
                 }
             }
         }
-        int y[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) y[j] = asr32(mad_lo(f.e[8 * g + 1 + j], st.k8192, acc[j]), HB_SHIFT);
+        for (int j = 0; j < 8; j++) y[8 * g + j] = asr32(mad_lo(e[8 * g + 1 + j], st.k8192, acc[j]), HB_SHIFT);
         if (DB && a0 + 8 * g < 0) {
+            /* DB: the reference's stages start from all-zero state, but a DB stage maps zero input to 1;
+             * outputs that lie before the stream origin must read as 0. */
 #pragma unroll
             for (int j = 0; j < 8; j++)
-                if (a0 + 8 * g + j < 0) y[j] = 0;
+                if (a0 + 8 * g + j < 0) y[8 * g + j] = 0;
         }
-        reinterpret_cast<int4*>(dE)[g] = make_int4(y[0], y[2], y[4], y[6]);
-        reinterpret_cast<int4*>(dO)[g] = make_int4(y[1], y[3], y[5], y[7]);
     }
 }
 
@@ -267,8 +225,8 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
     const int seg = (int)blockIdx.x;
     const int s = (int)blockIdx.y;
     uint32_t* raw = reinterpret_cast<uint32_t*>(smem);
-    mbar_t* bars = reinterpret_cast<mbar_t*>(smem + (size_t)WNB * RAWW * 4);
-    int* planes = reinterpret_cast<int*>(smem + (size_t)WNB * RAWW * 4 + 128);
+    mbar_t* bars = reinterpret_cast<mbar_t*>(smem + (size_t)2 * RAWW * 4);
+    int* planes = reinterpret_cast<int*>(smem + (size_t)2 * RAWW * 4 + 128);
     int* fin = planes + wplane_off(M, 0, 0) + 8; /* residue 8 words: the last stage's stores miss the others' banks */
 
     const long long seg_first_out = (long long)seg * p.seg_out;
@@ -283,7 +241,6 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
     uint32_t* dst = p.out + (long long)s * p.out_stride + seg_first_out - (long long)warm_macro * FN;
     const long long seg_room = p.n_out - seg_first_out + (long long)warm_macro * FN; /* valid: index < seg_room */
     const long long abs0 = p.origin + first_in;
-    constexpr uint32_t acc0 = (uint32_t)DB << HB_SHIFT;
     constexpr uint32_t chunk_bytes = (uint32_t)RAWW * 4u;
     const Steer steer = {p.steer_zero, p.steer_one, p.steer_k32, p.steer_k256, p.steer_k8192};
 
@@ -349,7 +306,7 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_fence_init();
-        for (int c = 0; c < WNB && c < NC; c++) {
+        for (int c = 0; c < 2 && c < NC; c++) {
             mbar_arrive_expect_tx(&bars[c], chunk_bytes);
             tma_load_1d(raw + (size_t)c * RAWW, src + (size_t)c * RAWW, chunk_bytes, &bars[c]);
         }
@@ -357,7 +314,7 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
     SDRD_SYNCWARP();
 
     for (int u = 0; u <= u_last; u++) {
-        /* ================= phase A: every shared-memory read of the step ================= */
+        /* ================= phase A: every read of the stage regions, and the arithmetic ================= */
         bool task_on = has_task;
         const int* sE = srcE;
         const int* sO = srcO;
@@ -376,9 +333,6 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
             }
             if (dst_halves_4 && (u & 1)) { dE += 16; dO += 16; } /* chunk u-4 odd */
         }
-        Fir32Regs fr;
-        if (task_on) fir32_load(sE, sO, fr);
-
         int4 tl_v[TSLOTS];
         bool tl_on[TSLOTS];
 #pragma unroll
@@ -407,13 +361,22 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
             }
         }
 
+        /* the FIR task itself: loads and arithmetic, results stay in registers until the barrier */
+        int y[32];
+        if (task_on) {
+            const long long a0 = DB ? ((abs0 + (long long)c_first * WC0) >> t_stage) + 32 * ti : 0;
+            fir32_stream<DB>(sE, sO, steer, a0, y);
+        }
+        SDRD_SYNCWARP();
+
+        /* ================= phase B: every shared-memory write of the step =========
+         * (the raw chunk is written by the TMA only, so its loads may follow the barrier) */
         const bool unpack_now = u < NC;
         uint4 rw[4];
         int2 x[16];
         if (unpack_now) {
-            const int rb = WNB == 2 ? (u & 1) : 0;
-            mbar_wait(&bars[rb], (uint32_t)((WNB == 2 ? (u >> 1) : u) & 1));
-            const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)rb * RAWW);
+            mbar_wait(&bars[u & 1], (uint32_t)((u >> 1) & 1));
+            const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)(u & 1) * RAWW);
             if (!PRO) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) rw[k] = r4[32 * k + lane];
@@ -422,38 +385,9 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
                 for (int k = 0; k < 16; k++) x[k] = rot4(r4[32 * k + lane], p.prologue);
             }
         }
-        SDRD_SYNCWARP();
-        if (WNB == 1 && lane == 0 && u + 1 < NC) { /* every lane holds its part of chunk u in registers */
-            mbar_arrive_expect_tx(&bars[0], chunk_bytes);
-            tma_load_1d(raw, src + (size_t)(u + 1) * RAWW, chunk_bytes, &bars[0]);
-        }
-
-        /* ================= phase B: arithmetic and every shared-memory write of the step ========= */
 #pragma unroll
         for (int k = 0; k < TSLOTS; k++)
             if (tl_on[k]) *reinterpret_cast<int4*>(const_cast<int*>(tl_src[k]) - tl_back[k]) = tl_v[k];
-
-        if (unpack_now) {
-            if (!PRO) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) { /* entries 64 k + 2 q, + 1: two 32-entry blocks further per k */
-                    int* o = up + 2 * BLK * k;
-                    *reinterpret_cast<int2*>(o + UP_EI) = make_int2(s16lo(rw[k].x), s16lo(rw[k].z));
-                    *reinterpret_cast<int2*>(o + UP_EQ) = make_int2(s16hi(rw[k].x), s16hi(rw[k].z));
-                    *reinterpret_cast<int2*>(o + UP_OI) = make_int2(s16lo(rw[k].y), s16lo(rw[k].w));
-                    *reinterpret_cast<int2*>(o + UP_OQ) = make_int2(s16hi(rw[k].y), s16hi(rw[k].w));
-                }
-            } else {
-                /* cascade input 32 k + q: parity q & 1, entry 16 k + (q >> 1): half a block further per k */
-                int* oi = up + ((lane & 1) ? UP_OI : UP_EI);
-                int* oq = up + ((lane & 1) ? UP_OQ : UP_EQ);
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    oi[(k >> 1) * BLK + (k & 1) * 16] = x[k].x;
-                    oq[(k >> 1) * BLK + (k & 1) * 16] = x[k].y;
-                }
-            }
-        }
 
         if (pack_now) {
             /* (y << norm_shift) >> trunk_shift truncated to 16 bits (Decimators.cpp:408-409, SDRDaemon.h:59) */
@@ -483,37 +417,37 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
         }
 
         if (task_on) {
-            /* DB: the reference's stages start from all-zero state, but a DB stage maps zero input to 1;
-             * outputs that lie before the stream origin must read as 0. */
-            const long long a0 = DB ? ((abs0 + (long long)c_first * WC0) >> t_stage) + 32 * ti : 0;
-#if SDRD_K1_PIPELINED
-            fir32_pipelined<DB>(fr, steer, a0, dE, dO);
-#else
-            int y[16];
-            fir32_half<0>(fr, acc0, steer, y);
-            if (DB && a0 < 0) {
 #pragma unroll
-                for (int r = 0; r < 16; r++)
-                    if (a0 + r < 0) y[r] = 0;
+            for (int g = 0; g < 4; g++) {
+                reinterpret_cast<int4*>(dE)[g] = make_int4(y[8 * g], y[8 * g + 2], y[8 * g + 4], y[8 * g + 6]);
+                reinterpret_cast<int4*>(dO)[g] = make_int4(y[8 * g + 1], y[8 * g + 3], y[8 * g + 5], y[8 * g + 7]);
             }
-            reinterpret_cast<int4*>(dE)[0] = make_int4(y[0], y[2], y[4], y[6]);
-            reinterpret_cast<int4*>(dE)[1] = make_int4(y[8], y[10], y[12], y[14]);
-            reinterpret_cast<int4*>(dO)[0] = make_int4(y[1], y[3], y[5], y[7]);
-            reinterpret_cast<int4*>(dO)[1] = make_int4(y[9], y[11], y[13], y[15]);
-            fir32_half<1>(fr, acc0, steer, y);
-            if (DB && a0 + 16 < 0) {
-#pragma unroll
-                for (int r = 0; r < 16; r++)
-                    if (a0 + 16 + r < 0) y[r] = 0;
-            }
-            reinterpret_cast<int4*>(dE)[2] = make_int4(y[0], y[2], y[4], y[6]);
-            reinterpret_cast<int4*>(dE)[3] = make_int4(y[8], y[10], y[12], y[14]);
-            reinterpret_cast<int4*>(dO)[2] = make_int4(y[1], y[3], y[5], y[7]);
-            reinterpret_cast<int4*>(dO)[3] = make_int4(y[9], y[11], y[13], y[15]);
-#endif
         }
+
+        if (unpack_now) {
+            if (!PRO) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) { /* entries 64 k + 2 q, + 1: two 32-entry blocks further per k */
+                    int* o = up + 2 * BLK * k;
+                    *reinterpret_cast<int2*>(o + UP_EI) = make_int2(s16lo(rw[k].x), s16lo(rw[k].z));
+                    *reinterpret_cast<int2*>(o + UP_EQ) = make_int2(s16hi(rw[k].x), s16hi(rw[k].z));
+                    *reinterpret_cast<int2*>(o + UP_OI) = make_int2(s16lo(rw[k].y), s16lo(rw[k].w));
+                    *reinterpret_cast<int2*>(o + UP_OQ) = make_int2(s16hi(rw[k].y), s16hi(rw[k].w));
+                }
+            } else {
+                /* cascade input 32 k + q: parity q & 1, entry 16 k + (q >> 1): half a block further per k */
+                int* oi = up + ((lane & 1) ? UP_OI : UP_EI);
+                int* oq = up + ((lane & 1) ? UP_OQ : UP_EQ);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    oi[(k >> 1) * BLK + (k & 1) * 16] = x[k].x;
+                    oq[(k >> 1) * BLK + (k & 1) * 16] = x[k].y;
+                }
+            }
+        }
+
         SDRD_SYNCWARP();
-        if (WNB == 2 && lane == 0 && u + 2 < NC) {
+        if (lane == 0 && u + 2 < NC) {
             mbar_arrive_expect_tx(&bars[u & 1], chunk_bytes);
             tma_load_1d(raw + (size_t)(u & 1) * RAWW, src + (size_t)(u + 2) * RAWW, chunk_bytes, &bars[u & 1]);
         }
