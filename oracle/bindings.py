@@ -53,6 +53,12 @@ def lib() -> C.CDLL:
         L.sdro_dec_create.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sdro_dec_destroy.argtypes = [C.c_void_p]
         L.sdro_dec_reset.argtypes = [C.c_void_p]
+        L.sdro_int_create.restype = C.c_void_p
+        L.sdro_int_create.argtypes = [C.c_int]
+        L.sdro_int_destroy.argtypes = [C.c_void_p]
+        L.sdro_int_reset.argtypes = [C.c_void_p]
+        L.sdro_int_process.restype = C.c_size_t
+        L.sdro_int_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.sdro_dec_process.restype = C.c_size_t
         L.sdro_dec_process.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.c_void_p, C.c_size_t, C.c_void_p]
         for f in ("sdro_gf_mul", "sdro_gf_div"):
@@ -121,6 +127,30 @@ class Decimator:
         ss = C.c_uint(sample_bits)
         n = lib().sdro_dec_process(self._h, C.byref(ss), iq.ctypes.data, len(iq), out.ctypes.data)
         return out[:n].copy(), ss.value
+
+
+class Interpolator:
+    """sdro_int_*: one Upsampler + Interpolators state."""
+
+    def __init__(self, log2_interp: int):
+        self._h = lib().sdro_int_create(log2_interp)
+        if not self._h:
+            raise ValueError("Invalid log2 interpolation factor")
+        self.log2_interp = log2_interp
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().sdro_int_destroy(self._h)
+            self._h = None
+
+    def reset(self) -> None:
+        lib().sdro_int_reset(self._h)
+
+    def process(self, iq: np.ndarray) -> np.ndarray:
+        iq = _iq(iq)
+        out = np.zeros(((len(iq) << self.log2_interp) + 1, 2), dtype=np.int16)
+        n = lib().sdro_int_process(self._h, iq.ctypes.data, len(iq), out.ctypes.data)
+        return out[:n].copy()
 
 
 def cm256_encode(originals: np.ndarray, n_fec: int) -> np.ndarray:
@@ -248,6 +278,11 @@ def ref(variant: int = HB_EO1) -> C.CDLL:
         L.ref_ds_process.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.c_void_p, C.c_size_t, C.c_void_p]
         L.ref_ds_process_streams.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
                                              C.c_size_t]
+        L.ref_us_create.restype = C.c_void_p
+        L.ref_us_create.argtypes = [C.c_int]
+        L.ref_us_destroy.argtypes = [C.c_void_p]
+        L.ref_us_process.restype = C.c_size_t
+        L.ref_us_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.ref_fecbuf_create.restype = C.c_void_p
         L.ref_fecbuf_destroy.argtypes = [C.c_void_p]
         L.ref_fecbuf_write_and_read.restype = C.c_int
@@ -285,6 +320,26 @@ class RefDownsampler:
         ss = C.c_uint(sample_bits)
         n = self._L.ref_ds_process(self._h, C.byref(ss), iq.ctypes.data, len(iq), out.ctypes.data)
         return out[:n].copy(), ss.value
+
+
+class RefUpsampler:
+    """The reference's Upsampler (+Interpolators), EO1 or DB build."""
+
+    def __init__(self, log2_interp: int, variant: int = HB_EO1):
+        self._L = ref(variant)
+        self._h = self._L.ref_us_create(log2_interp)
+        self.log2_interp = log2_interp
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ref_us_destroy(self._h)
+            self._h = None
+
+    def process(self, iq: np.ndarray) -> np.ndarray:
+        iq = _iq(iq)
+        out = np.zeros(((len(iq) << self.log2_interp) + 1, 2), dtype=np.int16)
+        n = self._L.ref_us_process(self._h, iq.ctypes.data, len(iq), out.ctypes.data)
+        return out[:n].copy()
 
 
 class RefFecBuffer:

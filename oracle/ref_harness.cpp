@@ -30,6 +30,7 @@
 #include <string>
 
 #include "Downsampler.h"
+#include "Upsampler.h"
 #include "SDRdaemonFECBuffer.h"
 #include "UDPSinkFEC.h"
 #include "DeviceSource.h"
@@ -65,6 +66,22 @@ size_t ref_ds_process(void* h, unsigned* sample_bits, const int16_t* iq_in, size
     IQSampleVector in(n_in), out;
     memcpy((void*)in.data(), iq_in, n_in * sizeof(IQSample));
     ds->process(*sample_bits, in, out);
+    memcpy(iq_out, (const void*)out.data(), out.size() * sizeof(IQSample));
+    return out.size();
+}
+
+/* ------------------------------------------------------------------ Upsampler ---- */
+
+void* ref_us_create(int log2_interp) { return new Upsampler((unsigned)log2_interp); }
+void ref_us_destroy(void* h) { delete (Upsampler*)h; }
+
+/* Upsampler::process, include/Upsampler.h:50.  Returns samples_out.size(). */
+size_t ref_us_process(void* h, const int16_t* iq_in, size_t n_in, int16_t* iq_out)
+{
+    Upsampler* us = (Upsampler*)h;
+    IQSampleVector in(n_in), out;
+    memcpy((void*)in.data(), iq_in, n_in * sizeof(IQSample));
+    us->process(in, out);
     memcpy(iq_out, (const void*)out.data(), out.size() * sizeof(IQSample));
     return out.size();
 }

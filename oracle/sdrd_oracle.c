@@ -684,4 +684,104 @@ long long sdro_rx_streams(int log2_decim, int fcpos, int variant, int nb_fec, in
     }
     if (digest) *digest = dg;
     return frames;
+}/* ---------------------------------------------------------------- interpolator ---- */
+
+/* HBFIRFilterTraits<32>/<16>::hbCoeffs as integers (sdmnbase/HBFilterTraits.cpp:62-72 and :25-31,
+ * (int32_t)(c * (1 << 14)) truncated toward zero; values printed by a probe against the reference). */
+static const int32_t HB32[8] = {-30, 63, -135, 261, -469, 830, -1605, 5176};
+static const int32_t HB16[4] = {-85, 380, -1246, 5041};
+
+/* One interpolating half-band stage: IntHalfbandFilterEO1<N>::myInterpolate + doInterpolateFIR
+ * (include/IntHalfbandFilterEO1.h:44-65,149-168; IntHalfbandFilterDB.h:51-72,109-127 is the same
+ * arithmetic).  Ring of N/2 samples, double-buffered so that a window never wraps. */
+typedef struct {
+    int order;                /* 64, 32 or 16 */
+    int ptr;
+    int32_t smp[64][2];
+} int_stage;
+
+static void int_stage_reset(int_stage* st, int order)
+{
+    memset(st, 0, sizeof *st);
+    st->order = order;
 }
+
+/* in: (x1, y1); out: first sample (x1, y1) = the middle of the window, second (x2, y2) = the FIR */
+static void int_stage_run(int_stage* st, int32_t* x1, int32_t* y1, int32_t* x2, int32_t* y2)
+{
+    const int half = st->order / 2, quarter = st->order / 4;
+    const int32_t* co = st->order == 64 ? HB64 : st->order == 32 ? HB32 : HB16;
+    st->smp[st->ptr][0] = *x1;
+    st->smp[st->ptr][1] = *y1;
+    st->smp[st->ptr + half][0] = *x1;
+    st->smp[st->ptr + half][1] = *y1;
+    st->ptr = st->ptr < half - 1 ? st->ptr + 1 : 0;
+    *x1 = st->smp[st->ptr + quarter - 1][0];
+    *y1 = st->smp[st->ptr + quarter - 1][1];
+    uint32_t ia = 0, qa = 0; /* wrapping int32 arithmetic */
+    int a = st->ptr, b = st->ptr + half - 1;
+    for (int i = 0; i < quarter; i++, a++, b--) {
+        ia += ((uint32_t)st->smp[a][0] + (uint32_t)st->smp[b][0]) * (uint32_t)co[i];
+        qa += ((uint32_t)st->smp[a][1] + (uint32_t)st->smp[b][1]) * (uint32_t)co[i];
+    }
+    *x2 = (int32_t)ia >> 13; /* hbShift - 1 */
+    *y2 = (int32_t)qa >> 13;
+}
+
+struct sdro_int {
+    int log2_interp;
+    int_stage st[6];
+};
+
+sdro_int* sdro_int_create(int log2_interp)
+{
+    if (log2_interp < 0 || log2_interp > 6) return NULL; /* Upsampler.cpp:38-42 */
+    sdro_int* u = (sdro_int*)calloc(1, sizeof *u);
+    if (!u) return NULL;
+    u->log2_interp = log2_interp;
+    sdro_int_reset(u);
+    return u;
+}
+void sdro_int_destroy(sdro_int* u) { free(u); }
+void sdro_int_reset(sdro_int* u)
+{
+    static const int orders[6] = {64, 32, 16, 16, 16, 16}; /* Interpolators.h:31-33 */
+    for (int i = 0; i < 6; i++) int_stage_reset(&u->st[i], orders[i]);
+}
+
+/* stage s (0-based) expands buf[0..n) (interleaved int32 I/Q pairs at stride `step` pairs) in place the
+ * way interpolateN_cen threads its intbuf through the stages (Interpolators.cpp:60-71 etc.): the sample
+ * at slot k gets its second output at slot k + step/2. */
+size_t sdro_int_process(sdro_int* u, const int16_t* iq_in, size_t n_in, int16_t* iq_out)
+{
+    const int M = u->log2_interp;
+    if (M == 0) { /* samples_out = samples_in */
+        memcpy(iq_out, iq_in, n_in * 4);
+        return n_in;
+    }
+    /* Reference quirk, reproduced: interpolate64_cen (Interpolators.cpp:363-605) runs only the five
+     * stages of interpolate32_cen into intbuf[0..63] and then emits intbuf[0..127], whose upper half
+     * is zeroed once before the loop (:370) and never written: per input sample 32 interpolated
+     * samples followed by 32 zero samples.  m_interpolator64 is never used. */
+    const int S = M == 6 ? 5 : M;   /* stages actually run */
+    const int W = 1 << S;           /* samples they produce per input sample */
+    const int WO = 1 << M;          /* samples emitted per input sample */
+    int32_t buf[64][2];
+    memset(buf, 0, sizeof buf);
+    for (size_t k = 0; k < n_in; k++) {
+        buf[0][0] = iq_in[2 * k];
+        buf[0][1] = iq_in[2 * k + 1];
+        for (int s = 0; s < S; s++) {
+            const int step = W >> s; /* distance between the samples stage s consumes */
+            for (int j = 0; j < W; j += step)
+                int_stage_run(&u->st[s], &buf[j][0], &buf[j][1], &buf[j + step / 2][0], &buf[j + step / 2][1]);
+        }
+        for (int j = 0; j < WO; j++) { /* IQSample::setReal/setImag take int16_t: truncation */
+            iq_out[2 * (k * WO + j)] = j < W ? (int16_t)buf[j][0] : (int16_t)0;
+            iq_out[2 * (k * WO + j) + 1] = j < W ? (int16_t)buf[j][1] : (int16_t)0;
+        }
+    }
+    return n_in << M;
+}
+
+

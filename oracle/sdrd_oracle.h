@@ -50,6 +50,19 @@ void      sdro_dec_reset(sdro_dec* d);
 size_t    sdro_dec_process(sdro_dec* d, unsigned* sample_bits, const int16_t* iq_in, size_t n_in,
                            int16_t* iq_out);
 
+/* ---------------------------------------------------------------- interpolator ---- */
+
+typedef struct sdro_int sdro_int;
+
+/* One Upsampler+Interpolators state: up to six persistent half-band stages of orders 64, 32, 16, 16,
+ * 16, 16 (Interpolators.h:31-33,52-58). */
+sdro_int* sdro_int_create(int log2_interp);
+void      sdro_int_destroy(sdro_int* u);
+void      sdro_int_reset(sdro_int* u);
+/* Upsampler::process (Upsampler.cpp:57-84) -> Interpolators::interpolate{2..64}_cen
+ * (Interpolators.cpp:23-606).  Writes n_in << log2_interp samples, returns that count. */
+size_t    sdro_int_process(sdro_int* u, const int16_t* iq_in, size_t n_in, int16_t* iq_out);
+
 /* ---------------------------------------------------------------- GF(256) / CM256 ---- */
 
 uint8_t sdro_gf_mul(uint8_t a, uint8_t b);

@@ -38,6 +38,23 @@ def check_decimator_golden(dec_factory):
     assert n_checked >= 90
 
 
+def check_interpolator_golden(int_factory):
+    """int_factory(M) -> object with .process(x) -> y (state carried across calls)."""
+    g = load("interpolator_ref.npz")
+    n_checked = 0
+    for key in g.files:
+        if not key.startswith("out_"):
+            continue
+        name, M = key[4:key.rindex("_M")], int(key[key.rindex("_M") + 2:])
+        x = g[f"in_{name}"]
+        m = len(x) if M <= 4 else 400
+        u = int_factory(M)
+        y = np.concatenate([u.process(x[:333]), u.process(x[333:m])])
+        assert y.shape == g[key].shape and np.array_equal(y, g[key]), key
+        n_checked += 1
+    assert n_checked == 28
+
+
 def check_sink_golden(sink_factory):
     """sink_factory(F, tv_sec, tv_usec) -> object with .write(x) -> (n_frames, 128+F, 512)."""
     g = load("sink_ref.npz")

@@ -14,6 +14,22 @@ def test_decimator_golden(oracle):
     golden_cases.check_decimator_golden(lambda M, fc, v: oracle.Decimator(M, fc, v))
 
 
+def test_interpolator_golden(oracle):
+    golden_cases.check_interpolator_golden(lambda M: oracle.Interpolator(M))
+
+
+def test_interpolator_vs_reference_build(oracle):
+    """fresh random inputs through the reference's own Upsampler, when its build is present"""
+    if not (oracle.ref_available(0) and oracle.ref_available(1)):
+        pytest.skip("reference build not present (GPU box)")
+    rng = np.random.default_rng(77)
+    x = rng.integers(-32768, 32768, size=(2500, 2), dtype=np.int16)
+    for M in range(7):
+        o, r = oracle.Interpolator(M), oracle.RefUpsampler(M, M & 1)
+        for a, b in ((0, 1), (1, 700), (700, 2500)):
+            assert np.array_equal(o.process(x[a:b]), r.process(x[a:b])), (M, a, b)
+
+
 def test_sink_golden(oracle):
     def factory(F, tv_sec, tv_usec):
         class S:
