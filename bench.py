@@ -270,6 +270,88 @@ def run_decode(args):
                                    "note": "K3 is ALU-pipe bound (PRMT/LOP3 table arithmetic), see DESIGN.md"}}), flush=True)
 
 
+def run_interp(args):
+    """SURVEY 8(f)-1, the Tx side: 592 superframes of 16129 samples interpolated by 16 (Upsampler)."""
+    import ctypes as C
+
+    M = args.log2_decim or 4
+    nfr = args.frames or 592
+    n_in = nfr * FRAME_SAMPLES
+    metric = "Msamples/s IQ out of the interpolation cascade"
+    if args.impl == "reference":
+        from oracle import bindings as ob
+
+        rng = np.random.default_rng(0x7A)
+        n = 16 * FRAME_SAMPLES
+        x = rng.integers(-32768, 32768, size=(n, 2), dtype=np.int16)
+        kind = "reference" if ob.ref_available(0) else "port"
+        u = ob.RefUpsampler(M, 0) if kind == "reference" else ob.Interpolator(M)
+        t0 = time.perf_counter()
+        y = u.process(x)
+        dt = time.perf_counter() - t0
+        v = len(y) / dt / 1e6
+        base = {"value": round(v, 3), "unit": UNIT, "cores": 1, "kind": kind,
+                "sample": f"{n} input samples, one Upsampler (reference Interpolators.cpp, one thread)"}
+        print(json.dumps({"impl": "reference", "metric": metric, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+                          "warmup": 0, "higher_is_better": True, "config": {"workload": f"tx: interpolate by {1 << M}, CPU, 1 thread"},
+                          "cpu_baseline": base, "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              flush=True)
+        return
+    import torch
+
+    from sdrdaemon_b200 import capi
+
+    lib = capi.load()
+    torch.cuda.set_device(0)
+    u = capi.Interpolator(M, 1, max_in=n_in)
+    in_ptr, _ = u.dev_input()
+    out_ptr, _ = u.dev_output()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0x7A)
+    dev_in = torch.as_tensor(DevView(in_ptr, n_in * 4), device="cuda").view(torch.int16)
+    dev_in.copy_(torch.randint(-32768, 32768, (n_in * 2,), dtype=torch.int16, device="cuda", generator=g))
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    # parity of the first 2048 inputs against the oracle (outside the timed region)
+    parity = "unchecked"
+    u.process_dev(n_in, stream.cuda_stream)
+    stream.synchronize()
+    try:
+        from oracle import bindings as ob
+
+        x0 = dev_in[: 2 * 2048].cpu().numpy().reshape(-1, 2)
+        y0 = torch.as_tensor(DevView(out_ptr, (2048 << M) * 4), device="cuda").cpu().numpy().view(np.int16).reshape(-1, 2)
+        parity = "first 2048 inputs bit-exact vs oracle" if np.array_equal(y0, ob.Interpolator(M).process(x0)) else "MISMATCH vs oracle"
+    except Exception as e:
+        parity = f"unchecked ({type(e).__name__})"
+    if parity.startswith("MISMATCH"):
+        raise SystemExit("bench: GPU result differs from the oracle; refusing to report a number")
+    for _ in range(max(args.warmup, 3)):
+        u.process_dev(n_in, stream.cuda_stream)
+    stream.synchronize()
+    steps = min(args.steps, 300)
+    l0 = u.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        u.process_dev(n_in, stream.cuda_stream)
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n_out = n_in << M
+    peak, peak_src = measured_peaks()
+    alg = 4 * n_in + 4 * n_out
+    print(json.dumps({"metric": metric, "value": round(n_out / ms / 1e3, 1), "unit": UNIT, "n_gpus": 1, "steps": steps,
+                      "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "dtype": "int32", "data": "synthetic",
+                      "config": {"workload": f"tx (SURVEY 8f-1): {nfr} superframes ({n_in} samples) interpolated by {1 << M}, "
+                                             f"{n_out * 4 / 1e6:.0f} MB out per step", "parity": parity,
+                                 "l2": "outputs larger than L2 (no flush needed)"},
+                      "gpu_launches": int(u.launches - l0),
+                      "roofline": {"bound": "hbm", "kernel": f"hbi::interpolate_kernel<{min(M, 5)}> (K4)", "achieved": round(alg / ms / 1e6, 1),
+                                   "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": None,
+                                   "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}}), flush=True)
+
+
 class DevView:
     """Zero-copy torch view of a raw device pointer (CUDA array interface)."""
 
@@ -283,7 +365,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json config (2 = headline)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5, 6],
+                    help="BASELINE.json config (2 = headline); 6 = the Tx interpolation cascade (SURVEY 8f-1)")
     ap.add_argument("--frames", type=int, default=0, help="superframes per stream per step (default: per config)")
     ap.add_argument("--log2-decim", type=int, default=0, help="experiments: override the workload's log2 decimation")
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -292,6 +375,8 @@ def main():
     args = ap.parse_args()
     if args.config == 4:
         return run_decode(args)
+    if args.config == 6:
+        return run_interp(args)
     if args.log2_decim:
         WORKLOADS[args.config] = dict(WORKLOADS[args.config], M=args.log2_decim,
                                       name=WORKLOADS[args.config]["name"] + f" [log2_decim overridden to {args.log2_decim}]")

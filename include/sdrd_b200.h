@@ -94,6 +94,34 @@ int sdrd_dec_process_dev(sdrd_dec* dec, size_t n_in, size_t* n_out, unsigned* sa
 long long sdrd_dec_launches(const sdrd_dec* dec);
 
 /* ------------------------------------------------------------------------------------------
+ * Interpolator (Tx side): Upsampler + Interpolators + IntHalfbandFilter{EO1,DB}<64/32/16>
+ *   replaces  Upsampler::Upsampler/configure/process (include/Upsampler.h:36-50,
+ *             sdmnbase/Upsampler.cpp:22-84) and Interpolators::interpolate{2..64}_cen
+ *             (sdmnbase/Interpolators.cpp:23-606), called from sdrdaemontx.cpp's main loop.
+ *   The EO1 and DB builds of the reference compute the same samples here.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdrd_int sdrd_int;
+
+/* log2_interp 0..6; max_in = largest n_in per stream per call. */
+int sdrd_int_create(sdrd_int** up, int log2_interp, int n_streams, size_t max_in);
+void sdrd_int_destroy(sdrd_int* up);
+/* Forget all filter state (a freshly constructed Interpolators, include/Interpolators.h:52-58). */
+int sdrd_int_reset(sdrd_int* up);
+/* Upsampler::configure (Upsampler.cpp:32-55): change interp between blocks; the filter state is kept
+ * as input history, the new cascade continues from it. */
+int sdrd_int_configure(sdrd_int* up, int log2_interp);
+int sdrd_int_log2_interp(const sdrd_int* up);
+/* Upsampler::process (include/Upsampler.h:50) for n_streams streams at once: iq_out receives
+ * n_in << log2_interp samples per stream (HOST pointers, pitches in samples). */
+int sdrd_int_process(sdrd_int* up, const int16_t* iq_in, size_t n_in, size_t in_stride, int16_t* iq_out,
+                     size_t out_stride, size_t* n_out);
+/* Device-resident form, as for the decimator. */
+void* sdrd_int_dev_input(sdrd_int* up, size_t* stride);
+void* sdrd_int_dev_output(sdrd_int* up, size_t* stride);
+int sdrd_int_process_dev(sdrd_int* up, size_t n_in, size_t* n_out, void* cuda_stream);
+long long sdrd_int_launches(const sdrd_int* up);
+
+/* ------------------------------------------------------------------------------------------
  * CM256 (Cauchy MDS GF(256) erasure code), batched over superframes
  *   replaces  CM256::cm256_encode as called at sdmnbase/UDPSinkFEC.cpp:228-246 and
  *             CM256::cm256_decode as called at sdmnbase/SDRdaemonFECBuffer.cpp:170-213

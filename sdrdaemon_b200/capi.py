@@ -41,6 +41,16 @@ SYMBOLS = [
     ("sdrd_dec_dev_output", _P, [_P, _SZP]),
     ("sdrd_dec_process_dev", C.c_int, [_P, _SZ, _SZP, _UP, _P]),
     ("sdrd_dec_launches", C.c_longlong, [_P]),
+    ("sdrd_int_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _SZ]),
+    ("sdrd_int_destroy", None, [_P]),
+    ("sdrd_int_reset", C.c_int, [_P]),
+    ("sdrd_int_configure", C.c_int, [_P, C.c_int]),
+    ("sdrd_int_log2_interp", C.c_int, [_P]),
+    ("sdrd_int_process", C.c_int, [_P, _P, _SZ, _SZ, _P, _SZ, _SZP]),
+    ("sdrd_int_dev_input", _P, [_P, _SZP]),
+    ("sdrd_int_dev_output", _P, [_P, _SZP]),
+    ("sdrd_int_process_dev", C.c_int, [_P, _SZ, _SZP, _P]),
+    ("sdrd_int_launches", C.c_longlong, [_P]),
     ("sdrd_cm256_encode", C.c_int, [_P, _SZ, C.c_int, C.c_int, _P]),
     ("sdrd_cm256_encode_dev", C.c_int, [_P, _SZ, C.c_int, C.c_int, _P, _P]),
     ("sdrd_sink_create", C.c_int, [C.POINTER(_P), C.c_int, _SZ]),
@@ -232,6 +242,66 @@ def fec_decode(superblocks: np.ndarray, n_blocks, lib: Optional[Library] = None)
                                   status.ctypes.data))
     return payload, block0, status
 
+
+
+class Interpolator:
+    """Upsampler + Interpolators for n_streams independent streams (sdrd_int_*)."""
+
+    def __init__(self, log2_interp: int, n_streams: int = 1, max_in: int = 1 << 16, lib: Optional[Library] = None):
+        self.lib = lib or load()
+        self._h = _P()
+        self.n_streams = n_streams
+        self.max_in = max_in
+        self.lib.check(self.lib.sdrd_int_create(C.byref(self._h), log2_interp, n_streams, max_in))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sdrd_int_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        self.lib.check(self.lib.sdrd_int_reset(self._h))
+
+    def configure(self, log2_interp: int):
+        self.lib.check(self.lib.sdrd_int_configure(self._h, log2_interp))
+
+    @property
+    def log2_interp(self) -> int:
+        return self.lib.sdrd_int_log2_interp(self._h)
+
+    @property
+    def launches(self) -> int:
+        return self.lib.sdrd_int_launches(self._h)
+
+    def process(self, iq: np.ndarray) -> np.ndarray:
+        """Upsampler::process.  iq (n,2) or (S,n,2) int16 -> (n << log2_interp) samples per stream."""
+        single = np.asarray(iq).ndim == 2
+        a = _iq3(iq)
+        s, n, _ = a.shape
+        if s != self.n_streams:
+            raise ValueError(f"expected {self.n_streams} streams, got {s}")
+        out = np.zeros((s, max(n << self.log2_interp, 1), 2), dtype=np.int16)
+        n_out = C.c_size_t(0)
+        self.lib.check(self.lib.sdrd_int_process(self._h, a.ctypes.data, n, n, out.ctypes.data, out.shape[1], C.byref(n_out)))
+        out = out[:, : n_out.value].copy()
+        return out[0] if single else out
+
+    def dev_input(self) -> Tuple[int, int]:
+        st = C.c_size_t(0)
+        p = self.lib.sdrd_int_dev_input(self._h, C.byref(st))
+        return p, st.value
+
+    def dev_output(self) -> Tuple[int, int]:
+        st = C.c_size_t(0)
+        p = self.lib.sdrd_int_dev_output(self._h, C.byref(st))
+        return p, st.value
+
+    def process_dev(self, n_in: int, stream: int = 0) -> int:
+        n_out = C.c_size_t(0)
+        self.lib.check(self.lib.sdrd_int_process_dev(self._h, n_in, C.byref(n_out), _P(stream)))
+        return n_out.value
 
 class Sink:
     """UDPSinkFEC framing + encode for n_streams streams (sdrd_sink_*)."""

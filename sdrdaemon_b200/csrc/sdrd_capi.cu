@@ -11,6 +11,7 @@
 #include "fec_kernels.cuh"
 #include "gf256_host.h"
 #include "hb_decimate.cuh"
+#include "hb_interpolate.cuh"
 #include "sdrd_rt.cuh"
 
 #include <sys/time.h>
@@ -399,6 +400,171 @@ extern "C" int sdrd_dec_process(sdrd_dec* d, const int16_t* iq_in, size_t n_in, 
     SDRD_TRY(rt::copy2d(iq_out, out_stride * 4, d->d_out, d->out_pitch * 4, n_out * 4, (size_t)d->S, rt::D2H, d->stream),
              "copy samples to host");
     SDRD_TRY(rt::sync(d->stream), "decimate");
+    if (n_out_p) *n_out_p = n_out;
+    return 0;
+}
+
+/* ========================================================================================== */
+/* interpolator                                                                                */
+/* ========================================================================================== */
+
+struct sdrd_int {
+    int log2_interp = 0, S = 1;
+    size_t max_in = 0;
+    uint32_t* d_in = nullptr;    /* [S][in_pitch]: hbi::HIST history words, then the new samples */
+    uint32_t* d_hist = nullptr;  /* [S][hbi::HIST] */
+    uint32_t* d_out = nullptr;   /* [S][out_pitch] */
+    size_t in_pitch = 0, out_pitch = 0;
+    long long launches = 0;
+    rt::stream_t stream = 0;
+};
+
+static int check_interp(int log2_interp)
+{
+    if (log2_interp < 0 || log2_interp > 6) return fail(SDRD_EINVAL, "Invalid log2 interpolation factor"); /* Upsampler.cpp:38-42 */
+    return 0;
+}
+
+extern "C" int sdrd_int_create(sdrd_int** out, int log2_interp, int n_streams, size_t max_in)
+{
+    if (!out) return fail(SDRD_EINVAL, "null handle pointer");
+    *out = nullptr;
+    if (int rc = check_interp(log2_interp)) return rc;
+    if (n_streams < 1 || max_in < 1) return fail(SDRD_EINVAL, "n_streams and max_in must be positive");
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    sdrd_int* u = new (std::nothrow) sdrd_int();
+    if (!u) return fail(SDRD_ENOMEM, "out of host memory");
+    u->log2_interp = log2_interp;
+    u->S = n_streams;
+    u->max_in = max_in;
+    u->in_pitch = hbi::HIST + round_up(max_in, 4) + 4;
+    u->out_pitch = round_up(max_in, 4) << 6; /* room for any interp up to 64 (configure may raise it) */
+    if (rt::alloc((void**)&u->d_in, u->in_pitch * 4 * (size_t)n_streams) != 0 ||
+        rt::alloc((void**)&u->d_hist, hbi::HIST * 4 * (size_t)n_streams) != 0 ||
+        rt::alloc((void**)&u->d_out, u->out_pitch * 4 * (size_t)n_streams) != 0 || rt::stream_create(&u->stream) != 0) {
+        int rc = fail_cuda("allocating interpolator buffers");
+        sdrd_int_destroy(u);
+        return rc;
+    }
+    rt::fill(u->d_in, 0, u->in_pitch * 4 * (size_t)n_streams, u->stream);
+    if (int rc = sdrd_int_reset(u)) {
+        sdrd_int_destroy(u);
+        return rc;
+    }
+    *out = u;
+    return 0;
+}
+
+extern "C" void sdrd_int_destroy(sdrd_int* u)
+{
+    if (!u) return;
+    rt::sync(u->stream);
+    rt::release(u->d_in);
+    rt::release(u->d_hist);
+    rt::release(u->d_out);
+    rt::stream_destroy(u->stream);
+    delete u;
+}
+
+extern "C" int sdrd_int_reset(sdrd_int* u)
+{
+    if (!u) return fail(SDRD_EINVAL, "null handle");
+    SDRD_TRY(rt::fill(u->d_hist, 0, hbi::HIST * 4 * (size_t)u->S, u->stream), "reset history");
+    SDRD_TRY(rt::sync(u->stream), "reset history");
+    return 0;
+}
+
+extern "C" int sdrd_int_configure(sdrd_int* u, int log2_interp)
+{
+    if (!u) return fail(SDRD_EINVAL, "null handle");
+    if (int rc = check_interp(log2_interp)) return rc;
+    u->log2_interp = log2_interp;
+    return 0;
+}
+extern "C" int sdrd_int_log2_interp(const sdrd_int* u) { return u ? u->log2_interp : -1; }
+extern "C" long long sdrd_int_launches(const sdrd_int* u) { return u ? u->launches : 0; }
+extern "C" void* sdrd_int_dev_input(sdrd_int* u, size_t* stride)
+{
+    if (!u) return nullptr;
+    if (stride) *stride = u->in_pitch;
+    return u->d_in + hbi::HIST;
+}
+extern "C" void* sdrd_int_dev_output(sdrd_int* u, size_t* stride)
+{
+    if (!u) return nullptr;
+    if (stride) *stride = u->out_pitch;
+    return u->d_out;
+}
+
+namespace {
+template <int NS>
+void launch_interpolate(const hbi::Params& p, int S, rt::stream_t st)
+{
+    const int tiles = (int)((p.n_in + hbi::tile_in(NS) - 1) / hbi::tile_in(NS));
+    SDRD_LAUNCH((hbi::interpolate_kernel<NS>), tiles, S, hbi::NT, hbi::smem_bytes(NS), st, p);
+}
+} /* namespace */
+
+static int int_run(sdrd_int* u, size_t n_in, size_t* n_out_p, rt::stream_t st)
+{
+    if (n_in > u->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    const int L = u->log2_interp;
+    /* history of the previous calls in front of the new samples */
+    SDRD_TRY(rt::copy2d(u->d_in, u->in_pitch * 4, u->d_hist, hbi::HIST * 4, hbi::HIST * 4, (size_t)u->S, rt::D2D, st),
+             "restore history");
+    if (n_in) {
+        if (L == 0) { /* samples_out = samples_in, Upsampler.cpp:59-62 */
+            SDRD_TRY(rt::copy2d(u->d_out, u->out_pitch * 4, u->d_in + hbi::HIST, u->in_pitch * 4, n_in * 4, (size_t)u->S,
+                                rt::D2D, st),
+                     "copy samples");
+        } else {
+            hbi::Params p{};
+            p.in = u->d_in + hbi::HIST;
+            p.in_stride = (long long)u->in_pitch;
+            p.out = u->d_out;
+            p.out_stride = (long long)u->out_pitch;
+            p.n_in = (long long)n_in;
+            p.log2_interp = L;
+            switch (L < 5 ? L : 5) {
+                case 1: launch_interpolate<1>(p, u->S, st); break;
+                case 2: launch_interpolate<2>(p, u->S, st); break;
+                case 3: launch_interpolate<3>(p, u->S, st); break;
+                case 4: launch_interpolate<4>(p, u->S, st); break;
+                default: launch_interpolate<5>(p, u->S, st); break;
+            }
+            u->launches++;
+            if (!SDRD_LAUNCH_OK()) return fail_cuda("kernel launch");
+        }
+    }
+    /* the last HIST input samples become the next call's history */
+    SDRD_TRY(rt::copy2d(u->d_hist, hbi::HIST * 4, u->d_in + n_in, u->in_pitch * 4, hbi::HIST * 4, (size_t)u->S, rt::D2D, st),
+             "save history");
+    if (n_out_p) *n_out_p = n_in << L;
+    return 0;
+}
+
+extern "C" int sdrd_int_process_dev(sdrd_int* u, size_t n_in, size_t* n_out, void* cuda_stream)
+{
+    if (!u) return fail(SDRD_EINVAL, "null handle");
+    return int_run(u, n_in, n_out, (rt::stream_t)cuda_stream);
+}
+
+extern "C" int sdrd_int_process(sdrd_int* u, const int16_t* iq_in, size_t n_in, size_t in_stride, int16_t* iq_out,
+                                size_t out_stride, size_t* n_out_p)
+{
+    if (!u) return fail(SDRD_EINVAL, "null handle");
+    if ((!iq_in && n_in) || !iq_out) return fail(SDRD_EINVAL, "null sample pointer");
+    if (n_in > u->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    if (u->S > 1 && in_stride < n_in) return fail(SDRD_EINVAL, "in_stride smaller than n_in");
+    SDRD_TRY(rt::copy2d(u->d_in + hbi::HIST, u->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)u->S, rt::H2D, u->stream),
+             "copy samples to device");
+    size_t n_out = 0;
+    if (int rc = int_run(u, n_in, &n_out, u->stream)) return rc;
+    if (u->S > 1 && out_stride < n_out) return fail(SDRD_EINVAL, "out_stride smaller than the output length");
+    SDRD_TRY(rt::copy2d(iq_out, out_stride * 4, u->d_out, u->out_pitch * 4, n_out * 4, (size_t)u->S, rt::D2H, u->stream),
+             "copy samples to host");
+    SDRD_TRY(rt::sync(u->stream), "interpolate");
     if (n_out_p) *n_out_p = n_out;
     return 0;
 }

@@ -234,6 +234,66 @@ private:
     std::string m_error;
 };
 
+/* ------------------------------------------------------------------------------------------
+ * Upsampler (reference include/Upsampler.h:28-76, sdmnbase/Upsampler.cpp): the Tx side's
+ * interpolation by 2^interp, behind sdrd_int_*.
+ * ------------------------------------------------------------------------------------------ */
+class Upsampler {
+public:
+    Upsampler(unsigned int interp = 0, std::size_t max_block = 1 << 16) : m_interp(interp), m_int(nullptr)
+    {
+        if (sdrd_int_create(&m_int, (int)interp, 1, max_block) != 0) m_error = sdrd_last_error();
+    }
+    ~Upsampler() { sdrd_int_destroy(m_int); }
+    Upsampler(const Upsampler&) = delete;
+    Upsampler& operator=(const Upsampler&) = delete;
+
+    /* Upsampler.cpp:32-55: key "interp" (0..6) */
+    bool configure(parsekv::pairs_type& m)
+    {
+        if (m.find("interp") != m.end()) {
+            int log2Interp = atoi(m["interp"].c_str());
+            if (log2Interp < 0 || log2Interp > 6) {
+                m_error = "Invalid log2 interpolation factor";
+                return false;
+            }
+            if (!m_int || sdrd_int_configure(m_int, log2Interp) != 0) {
+                m_error = sdrd_last_error();
+                return false;
+            }
+            m_interp = (unsigned)log2Interp;
+        }
+        return true;
+    }
+    unsigned int getLog2Interpolation() const { return m_interp; }
+
+    void process(const IQSampleVector& samples_in, IQSampleVector& samples_out)
+    {
+        if (!m_int) return;
+        samples_out.resize(samples_in.size() ? (samples_in.size() << m_interp) : 1);
+        std::size_t n_out = 0;
+        if (sdrd_int_process(m_int, reinterpret_cast<const int16_t*>(samples_in.data()), samples_in.size(), samples_in.size(),
+                             reinterpret_cast<int16_t*>(samples_out.data()), samples_out.size(), &n_out) != 0) {
+            m_error = sdrd_last_error();
+            samples_out.clear();
+            return;
+        }
+        samples_out.resize(n_out);
+    }
+    operator bool() const { return m_error.empty(); }
+    std::string error()
+    {
+        std::string ret(m_error);
+        m_error.clear();
+        return ret;
+    }
+
+private:
+    unsigned int m_interp;
+    sdrd_int* m_int;
+    std::string m_error;
+};
+
 /* ---------------------------------------------------------------- UDP helpers ---------------- */
 
 class UdpTx {

@@ -56,6 +56,22 @@ def check_decimator(lib, ob, M, fcpos, variant, x, splits, bits=16):
     d.close()
 
 
+def check_interpolator(lib, ob, M, x, splits):
+    """x (S, n, 2); the stream is fed in the pieces given by `splits` (state carried across calls)."""
+    S, n, _ = x.shape
+    u = capi.Interpolator(M, S, max_in=max(max(b - a for a, b in zip(splits[:-1], splits[1:])), 1), lib=lib)
+    refs = [ob.Interpolator(M) for _ in range(S)]
+    for a, b in zip(splits[:-1], splits[1:]):
+        y = u.process(x[:, a:b])
+        for s in range(S):
+            yo = refs[s].process(x[s, a:b])
+            assert y[s].shape == yo.shape, (y[s].shape, yo.shape)
+            if not np.array_equal(y[s], yo):
+                bad = np.nonzero((y[s] != yo).any(axis=1))[0]
+                raise AssertionError(f"interp M={M} stream {s} piece [{a},{b}): {len(bad)} samples differ, first at {bad[:5]}")
+    u.close()
+
+
 def check_sink(lib, ob, F, x, splits):
     S = x.shape[0]
     sk = capi.Sink(n_streams=S, max_samples=max(b - a for a, b in zip(splits[:-1], splits[1:])), n_fec=F, lib=lib)

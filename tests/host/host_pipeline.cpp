@@ -6,6 +6,9 @@
  *   UDPSourceFEC::read -> DataBuffer -> FileSink (.sdriq)
  *
  *   host_pipeline testsource <n_samples> <srate> <dfp> <power_db> <out.raw>
+ *   host_pipeline upsample <interp> <block> <in.raw> <out.raw>       Upsampler::process block by block, the
+ *       Tx side's step after UDPSourceFEC::read (sdrdaemontx.cpp); interp is re-configured through
+ *       Upsampler::configure("interp=..") after the first block like a control message would
  *   host_pipeline pipeline <port> <config> <n_blocks> <out.sdriq> <datagrams.bin> [puncture]
  *       config e.g. "srate=2400000,decim=4,fecblk=16,dfp=100000,power=6,blklen=65536"
  *
@@ -37,6 +40,37 @@ static int run_testsource(int argc, char** argv)
     FILE* f = fopen(argv[6], "wb");
     fwrite(buf.data(), 2, buf.size(), f);
     fclose(f);
+    return 0;
+}
+
+static int run_upsample(int argc, char** argv)
+{
+    if (argc < 6) return 2;
+    const int interp = atoi(argv[2]);
+    const size_t block = (size_t)atoi(argv[3]);
+    FILE* fi = fopen(argv[4], "rb");
+    FILE* fo = fopen(argv[5], "wb");
+    if (!fi || !fo) return 1;
+    Upsampler up(0, block);
+    if (!up) { fprintf(stderr, "Upsampler: %s\n", up.error().c_str()); return 1; }
+    parsekv::pairs_type bad;
+    bad["interp"] = "9";
+    if (up.configure(bad) || up.error() != "Invalid log2 interpolation factor") return 3; /* Upsampler.cpp:38-42 */
+    parsekv::pairs_type kv;
+    kv["interp"] = std::to_string(interp);
+    if (!up.configure(kv) || (int)up.getLog2Interpolation() != interp) return 4;
+    IQSampleVector in(block), out;
+    for (;;) {
+        size_t n = fread((void*)in.data(), sizeof(IQSample), block, fi);
+        if (n == 0) break;
+        in.resize(n);
+        up.process(in, out);
+        if (!up) { fprintf(stderr, "process: %s\n", up.error().c_str()); return 1; }
+        fwrite((const void*)out.data(), sizeof(IQSample), out.size(), fo);
+        in.resize(block);
+    }
+    fclose(fi);
+    fclose(fo);
     return 0;
 }
 
@@ -137,7 +171,8 @@ static int run_pipeline(int argc, char** argv)
 int main(int argc, char** argv)
 {
     if (argc >= 2 && std::string(argv[1]) == "testsource") return run_testsource(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "upsample") return run_upsample(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "pipeline") return run_pipeline(argc, argv);
-    fprintf(stderr, "usage: host_pipeline testsource|pipeline ...\n");
+    fprintf(stderr, "usage: host_pipeline testsource|upsample|pipeline ...\n");
     return 2;
 }

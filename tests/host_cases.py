@@ -83,3 +83,16 @@ def check_pipeline(exe, ob, tmp, port, decim=2, fecblk=8, n_blocks=5, blklen=655
     assert n_frames_rx >= n_full, (n_frames_rx, n_full, r.stdout)
     assert np.array_equal(samples[: n_full * FRAME], y[: n_full * FRAME]), "received stream differs from the decimated stream"
     return r.stdout
+
+
+def check_upsampler(exe, ob, tmp, interp=4, block=3000, n=10000):
+    """host Upsampler (configure + process, block by block) vs the oracle"""
+    rng = np.random.default_rng(55 + interp)
+    x = rng.integers(-32768, 32768, size=(n, 2), dtype=np.int16)
+    fin, fout = os.path.join(tmp, "up_in.raw"), os.path.join(tmp, "up_out.raw")
+    x.tofile(fin)
+    r = subprocess.run([exe, "upsample", str(interp), str(block), fin, fout], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout + r.stderr)
+    got = np.fromfile(fout, dtype=np.int16).reshape(-1, 2)
+    want = ob.Interpolator(interp).process(x)
+    assert got.shape == want.shape and np.array_equal(got, want)

@@ -64,3 +64,11 @@ def test_argument_errors(emu_lib):
     s = capi.Sink(lib=emu_lib)
     with pytest.raises(capi.SdrdError):
         s.set_nb_fec(129)
+    for bad in (-1, 7):
+        with pytest.raises(capi.SdrdError) as e:
+            capi.Interpolator(bad, lib=emu_lib)
+        assert e.value.code == -1 and "Invalid log2 interpolation factor" in e.value.msg  # Upsampler.cpp:40
+    u = capi.Interpolator(3, max_in=10, lib=emu_lib)
+    with pytest.raises(capi.SdrdError) as e:
+        u.process(np.zeros((11, 2), np.int16))
+    assert e.value.code == -5

@@ -37,6 +37,24 @@ def test_decimator_short_and_empty(emu_lib, oracle):
     cases.check_decimator(emu_lib, oracle, 6, 2, 0, x, [0, 10, 10, 70, 135, 1000])  # below one group, empty, ragged
 
 
+@pytest.mark.parametrize("M", [0, 1, 2, 3, 4, 5, 6])
+def test_interpolator(emu_lib, oracle, M):
+    rng = np.random.default_rng(800 + M)
+    n = 3000 if M <= 4 else 700
+    x = cases.rand_iq(rng, (2, n))
+    cases.check_interpolator(emu_lib, oracle, M, x, [0, 1, 1, 40, 1300, n])  # single sample, empty, shorter than the history
+
+
+def test_interpolator_golden_and_classes(emu_lib, oracle):
+    import golden_cases
+    from sdrdaemon_b200 import capi
+
+    golden_cases.check_interpolator_golden(lambda M: capi.Interpolator(M, max_in=2048, lib=emu_lib))
+    rng = np.random.default_rng(801)
+    for name, x in cases.input_classes(rng, 2048).items():
+        cases.check_interpolator(emu_lib, oracle, 4, x[None], [0, 777, 2048])
+
+
 @pytest.mark.parametrize("F", [0, 1, 16, 32, 40])
 def test_sink_framing_and_encode(emu_lib, oracle, F):
     rng = np.random.default_rng(400 + F)

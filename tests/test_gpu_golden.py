@@ -18,6 +18,10 @@ def test_decimator_golden(gpu_lib):
     golden_cases.check_decimator_golden(D)
 
 
+def test_interpolator_golden(gpu_lib):
+    golden_cases.check_interpolator_golden(lambda M: capi.Interpolator(M, max_in=2048, lib=gpu_lib))
+
+
 def test_sink_golden(gpu_lib):
     def factory(F, tv_sec, tv_usec):
         class S:

@@ -80,6 +80,34 @@ def test_decimator_large_single_stream(gpu_lib, oracle):
     assert np.array_equal(y, yo)
 
 
+@pytest.mark.parametrize("M", [0, 1, 2, 3, 4, 5, 6])
+def test_interpolator(gpu_lib, oracle, M):
+    rng = np.random.default_rng(900 + M)
+    n = 40000 if M <= 4 else 9000
+    x = cases.rand_iq(rng, (3, n))
+    cases.check_interpolator(gpu_lib, oracle, M, x, [0, 1, 1, 40, 4096 + 17, n])  # single sample, empty, ragged tiles
+
+
+def test_interpolator_input_classes_and_reconfigure(gpu_lib, oracle):
+    rng = np.random.default_rng(901)
+    for name, x in cases.input_classes(rng, 8192).items():
+        cases.check_interpolator(gpu_lib, oracle, 4, x[None], [0, 3333, 8192])
+    # decimate by 16 then interpolate by 16: the Rx and Tx cascades back to back keep a slow tone
+    from sdrdaemon_b200 import capi
+
+    n = 1 << 16
+    t = np.arange(n)
+    tone = np.stack([np.round(8000 * np.cos(2 * np.pi * t / 4096.0)), np.round(8000 * np.sin(2 * np.pi * t / 4096.0))],
+                    axis=1).astype(np.int16)
+    y, _ = capi.Decimator(4, max_in=n, lib=gpu_lib).process(tone)
+    z = capi.Interpolator(4, max_in=len(y), lib=gpu_lib).process(y)
+    zo = oracle.Interpolator(4).process(oracle.Decimator(4).process(tone)[0])
+    assert np.array_equal(z, zo)
+    d = 30 * 15 + 16 + 8 + 2 * 4  # group delays of the two cascades, in input samples (approx.)
+    err = np.abs(z[4096:n - 4096].astype(np.int32) - tone[4096 - d:n - 4096 - d].astype(np.int32)).max()
+    assert err < 1500, err
+
+
 @pytest.mark.parametrize("F", [0, 1, 16, 20, 32, 40, 128])
 def test_sink_framing_and_encode(gpu_lib, oracle, F):
     rng = np.random.default_rng(4000 + F)

@@ -17,6 +17,16 @@ def test_host_pipeline_emulated(tmp_path):
     assert "frames_received=" in out
 
 
+def test_host_upsampler_emulated(tmp_path):
+    host_cases.check_upsampler(host_cases.build("emu"), ob, str(tmp_path), interp=3, block=700, n=3000)
+
+
+@pytest.mark.gpu
+def test_host_upsampler_gpu(tmp_path):
+    for interp in (1, 4, 6):
+        host_cases.check_upsampler(host_cases.build("gpu"), ob, str(tmp_path), interp=interp)
+
+
 @pytest.mark.gpu
 def test_host_pipeline_gpu(tmp_path):
     out = host_cases.check_pipeline(host_cases.build("gpu"), ob, str(tmp_path), port=19312, decim=4, fecblk=16, n_blocks=20)
