@@ -53,16 +53,14 @@ SDRD_DEVICE void selectors(uint32_t x, uint32_t& s0, uint32_t& s1, uint32_t& s2)
     s1 = pack_digits((x >> 3) & 0x07070707u);
     s2 = pack_digits((x >> 6) & 0x03030303u);
 }
-SDRD_DEVICE uint32_t mul4(uint4 a, uint32_t b, uint32_t s0, uint32_t s1, uint32_t s2)
-{
-    return prmt(a.x, a.y, s0) ^ prmt(a.z, a.w, s1) ^ prmt(b, b, s2);
-}
-
 /* One pass: rows [row0, row0 + nrows) (nrows <= 16) of  out = C * img  accumulated into rec16
- * (16 x 128 words, zeroed by the caller).  coefT[j * cstride + r] = C[r][j]. */
-SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint8_t* SDRD_RESTRICT coefT, int cstride,
-                             int row0, int nrows, const uint4* SDRD_RESTRICT tabA,
-                             const uint32_t* SDRD_RESTRICT tabB, uint32_t* rec16, int tid)
+ * (16 x 128 words, zeroed by the caller).  coefT[j * cstride + r] = 32 * C[r][j]: the byte offset of
+ * the multiplier's entry in `tab` ({8-entry tables for digits 0 and 1: 16 bytes, digit 2: 4 bytes,
+ * padding}), fetched with a 16-bit shared load so that no ALU instruction is spent on it -- the ALU
+ * pipe (PRMT, LOP3) is what bounds this kernel.  Two columns are folded into an accumulator with three
+ * 3-input XORs. */
+SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride,
+                             int row0, int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
     uint32_t acc[RB][4];
@@ -71,22 +69,32 @@ SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint8_t* S
 #pragma unroll
         for (int w = 0; w < 4; w++) acc[r][w] = 0u;
 
-    for (int jj = 0; jj < 16; jj++) {
+    for (int jj = 0; jj < 16; jj += 2) {
         const int j = warp * 16 + jj;
-        uint32_t s0[4], s1[4], s2[4];
+        uint32_t s0[2][4], s1[2][4], s2[2][4];
 #pragma unroll
-        for (int w = 0; w < 4; w++) selectors(img[j * ROW_WORDS + lane + 32 * w], s0[w], s1[w], s2[w]);
-        /* the 16 coefficients of this column for the rows of the pass: one 128-bit load */
-        const uint4 cv = *reinterpret_cast<const uint4*>(coefT + j * cstride + row0);
-        const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int w = 0; w < 4; w++) selectors(img[(j + c) * ROW_WORDS + lane + 32 * w], s0[c][w], s1[c][w], s2[c][w]);
+        const uint16_t* co0 = coefT + j * cstride + row0;
+        const uint16_t* co1 = co0 + cstride;
 #pragma unroll
         for (int r = 0; r < RB; r++) {
             if (r < nrows) {
-                const unsigned c = (cw[r >> 2] >> (8 * (r & 3))) & 0xFFu;
-                const uint4 a = tabA[c];
-                const uint32_t b = tabB[c];
+                const unsigned char* e0 = tab + co0[r];
+                const unsigned char* e1 = tab + co1[r];
+                const uint4 a0 = *reinterpret_cast<const uint4*>(e0);
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(e0 + 16);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(e1);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(e1 + 16);
 #pragma unroll
-                for (int w = 0; w < 4; w++) acc[r][w] ^= mul4(a, b, s0[w], s1[w], s2[w]);
+                for (int w = 0; w < 4; w++) {
+                    uint32_t v = acc[r][w];
+                    v = v ^ prmt(a0.x, a0.y, s0[0][w]) ^ prmt(a0.z, a0.w, s1[0][w]);
+                    v = v ^ prmt(b0, b0, s2[0][w]) ^ prmt(a1.x, a1.y, s0[1][w]);
+                    v = v ^ prmt(a1.z, a1.w, s1[1][w]) ^ prmt(b1, b1, s2[1][w]);
+                    acc[r][w] = v;
+                }
             }
         }
     }
@@ -103,28 +111,27 @@ SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint8_t* S
 struct Smem {
     uint32_t* img;    /* [128][128] */
     uint32_t* rec16;  /* [16][128] */
-    uint4* tabA;      /* [256] */
-    uint32_t* tabB;   /* [256] */
-    uint8_t* coefT;   /* [128][cstride] */
+    unsigned char* tab; /* [256] entries of 32 bytes: tabA[c] (16), tabB[c] (4), padding */
+    uint16_t* coefT;    /* [128][cstride], 32 * coefficient */
     uint8_t* extra;
 };
-constexpr size_t SMEM_FIXED = (size_t)IMG_WORDS * 4 + (size_t)RB * ROW_WORDS * 4 + 4096 + 1024;
+constexpr int TAB_ENTRY = 32;
+constexpr size_t SMEM_FIXED = (size_t)IMG_WORDS * 4 + (size_t)RB * ROW_WORDS * 4 + 256 * TAB_ENTRY;
 SDRD_DEVICE Smem carve(unsigned char* base, int cstride)
 {
     Smem s;
     s.img = reinterpret_cast<uint32_t*>(base);
     s.rec16 = s.img + IMG_WORDS;
-    s.tabA = reinterpret_cast<uint4*>(s.rec16 + RB * ROW_WORDS);
-    s.tabB = reinterpret_cast<uint32_t*>(s.tabA + 256);
-    s.coefT = reinterpret_cast<uint8_t*>(s.tabB + 256);
-    s.extra = s.coefT + 128 * cstride;
+    s.tab = reinterpret_cast<unsigned char*>(s.rec16 + RB * ROW_WORDS);
+    s.coefT = reinterpret_cast<uint16_t*>(s.tab + 256 * TAB_ENTRY);
+    s.extra = reinterpret_cast<uint8_t*>(s.coefT + 128 * cstride);
     return s;
 }
 SDRD_DEVICE void load_tables(const Smem& s, const Tables& t, int tid)
 {
     for (int i = tid; i < 256; i += NT) {
-        s.tabA[i] = t.tabA[i];
-        s.tabB[i] = t.tabB[i];
+        *reinterpret_cast<uint4*>(s.tab + i * TAB_ENTRY) = t.tabA[i];
+        *reinterpret_cast<uint32_t*>(s.tab + i * TAB_ENTRY + 16) = t.tabB[i];
     }
 }
 
@@ -151,7 +158,7 @@ struct EncParams {
     Tables tab;
 };
 
-inline size_t enc_smem_bytes(int cstride) { return SMEM_FIXED + (size_t)128 * cstride; }
+inline size_t enc_smem_bytes(int cstride) { return SMEM_FIXED + (size_t)128 * cstride * 2; }
 
 SDRD_KERNEL(NT, 2) encode_kernel(EncParams p)
 {
@@ -163,7 +170,7 @@ SDRD_KERNEL(NT, 2) encode_kernel(EncParams p)
     /* coefficient rows of the Cauchy matrix, transposed so that the 16 rows of a pass are adjacent */
     for (int k = tid; k < 128 * p.cstride; k += NT) {
         const int j = k / p.cstride, r = k - j * p.cstride;
-        sm.coefT[k] = r < p.F ? p.tab.cauchy[r * 128 + j] : (uint8_t)0;
+        sm.coefT[k] = (uint16_t)(TAB_ENTRY * (r < p.F ? p.tab.cauchy[r * 128 + j] : (uint8_t)0));
     }
 
     const unsigned frame_index = (p.frame_index0 + (unsigned)f) & 0xFFFFu;
@@ -180,10 +187,17 @@ SDRD_KERNEL(NT, 2) encode_kernel(EncParams p)
         const uint32_t* src = p.samples + (long long)s * p.sample_stride;
         const uint32_t* pend = p.pending + (long long)s * FRAME_SAMPLES;
         const long long g0 = (long long)f * FRAME_SAMPLES - p.n_pending; /* index into this call's samples */
-        for (int k = tid; k < FRAME_SAMPLES; k += NT) {
-            const int b = k / 127, i = k - b * 127;
-            const long long g = g0 + k;
-            sm.img[(b + 1) * ROW_WORDS + 1 + i] = g < 0 ? pend[g + p.n_pending] : src[g];
+        /* one warp per block of 127 samples: four coalesced loads, no index division */
+        for (int b = tid >> 5; b < 127; b += NT / 32) {
+            const long long gb = g0 + (long long)b * 127;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = (tid & 31) + 32 * q;
+                if (i < 127) {
+                    const long long g = gb + i;
+                    sm.img[(b + 1) * ROW_WORDS + 1 + i] = g < 0 ? pend[g + p.n_pending] : src[g];
+                }
+            }
         }
     } else {
         for (int k = tid; k < 128 * 127; k += NT) {
@@ -208,7 +222,7 @@ SDRD_KERNEL(NT, 2) encode_kernel(EncParams p)
         const int nrows = p.F - row0 < RB ? p.F - row0 : RB;
         for (int k = tid; k < RB * ROW_WORDS; k += NT) sm.rec16[k] = 0u;
         __syncthreads();
-        matvec_pass(sm.img, sm.coefT, p.cstride, row0, nrows, sm.tabA, sm.tabB, sm.rec16, tid);
+        matvec_pass(sm.img, sm.coefT, p.cstride, row0, nrows, sm.tab, sm.rec16, tid);
         __syncthreads();
         if (p.mode == 0) {
             /* recovery datagram = header {frameIndex, blockIndex = 128 + r, filler 0} + payload */
@@ -248,7 +262,7 @@ template <int DCAP>
 inline size_t dec_smem_bytes()
 {
     /* coefT [128][DCAP] + aug [DCAP][2*DCAP] + exp/log + small lists */
-    return SMEM_FIXED + (size_t)128 * DCAP + (size_t)DCAP * 2 * DCAP + 512 + 256 + 2048;
+    return SMEM_FIXED + (size_t)128 * DCAP * 2 + (size_t)DCAP * 2 * DCAP + 512 + 256 + 2048;
 }
 
 SDRD_DEVICE uint8_t gmul(const uint8_t* ex, const uint8_t* lg, uint8_t a, uint8_t b)
@@ -354,7 +368,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
         /* coefficient matrix D [N][128 columns = image rows] */
         if (N == 1) {
             /* cm256's single-recovery shortcut: XOR of everything received, whatever the row */
-            for (int k = tid; k < 128 * DCAP; k += NT) sm.coefT[k] = (uint8_t)((k % DCAP) == 0 ? 1 : 0);
+            for (int k = tid; k < 128 * DCAP; k += NT) sm.coefT[k] = (uint16_t)((k % DCAP) == 0 ? TAB_ENTRY : 0);
         } else {
             /* A[k][c] = M[x_k][e_c]; invert by Gauss-Jordan on [A | I] (no pivoting needed: every
              * leading minor of a Cauchy matrix is non-zero) */
@@ -414,7 +428,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
                             v ^= gmul(gfexp, gflog, aug[c * W2 + N + kk], m);
                         }
                     }
-                    sm.coefT[i * DCAP + c] = v;
+                    sm.coefT[i * DCAP + c] = (uint16_t)(TAB_ENTRY * v);
                 }
             }
         }
@@ -441,7 +455,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
             const int nrows = N - row0 < RB ? N - row0 : RB;
             for (int k = tid; k < RB * ROW_WORDS; k += NT) sm.rec16[k] = 0u;
             __syncthreads();
-            matvec_pass(sm.img, sm.coefT, DCAP, row0, nrows, sm.tabA, sm.tabB, sm.rec16, tid);
+            matvec_pass(sm.img, sm.coefT, DCAP, row0, nrows, sm.tab, sm.rec16, tid);
             __syncthreads();
             for (int k = tid; k < nrows * 127; k += NT) {
                 const int r = k / 127, i = k - r * 127;
