@@ -73,15 +73,27 @@ inline bool device_ok(std::string& why)
         why = std::string("no CUDA device: ") + last_error();
         return false;
     }
-    cudaDeviceProp pr;
-    if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess) {
-        why = std::string("cudaGetDeviceProperties: ") + last_error();
-        return false;
+    /* cudaGetDeviceProperties costs milliseconds: ask the two attributes needed, once per device */
+    static int cached_major[64];
+    static bool cached[64];
+    int major = 0;
+    if (dev >= 0 && dev < 64 && cached[dev]) {
+        major = cached_major[dev];
+    } else {
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+            why = std::string("cudaDeviceGetAttribute: ") + last_error();
+            return false;
+        }
+        if (dev >= 0 && dev < 64) {
+            cached_major[dev] = major;
+            cached[dev] = true;
+        }
     }
-    if (pr.major != 10) {
+    if (major != 10) {
+        int minor = 0;
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
         char b[400];
-        snprintf(b, sizeof b, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", dev, pr.name,
-                 pr.major, pr.minor);
+        snprintf(b, sizeof b, "device %d is sm_%d%d; this library carries sm_100a code only", dev, major, minor);
         why = b;
         return false;
     }
