@@ -17,8 +17,9 @@
  *
  * Design: the cascade's receptive field is short (42 input samples of history for five stages), so a
  * CTA takes a tile of K = 4096 >> S input samples plus that halo, runs stage after stage through
- * shared memory as int32 {I, Q} pairs (one thread per output pair, coalesced 8-byte shared loads),
- * and the last stage packs and writes its 4096 output samples straight to global memory with 8-byte
+ * shared memory as int32 {I, Q} pairs (two output pairs per thread from one register window,
+ * conflict-free 16-byte shared loads),
+ * and the last stage packs and writes its 4096 output samples straight to global memory with 16-byte
  * stores.  Arithmetic per OUTPUT sample is small (16 S / 2^S multiply-adds per component), the kernel
  * is bound by the 4 + 4 / 2^S bytes it moves per output sample and by shared-memory reads.
  *
@@ -40,11 +41,11 @@ constexpr int HIST = 64; /* input samples of history kept in front of a call's s
 /* ring length L (= filter order / 2) of stage s = 1..5 */
 SDRD_HD constexpr int ring_len(int s) { return s == 1 ? 32 : s == 2 ? 16 : 8; }
 /* samples of stage s needed in front of a tile's first sample so that stages s+1..S can be computed,
- * rounded up to whole output pairs */
+ * rounded up to a multiple of 4 (two output pairs per thread, 16-byte aligned window loads) */
 SDRD_HD constexpr int halo(int s, int S)
 {
     int h = 0;
-    for (int t = S; t > s; t--) h = (((h + 1) >> 1) + ring_len(t) - 1 + 1) & ~1;
+    for (int t = S; t > s; t--) h = (((h + 1) >> 1) + ring_len(t) - 1 + 3) & ~3;
     return h;
 }
 SDRD_HD constexpr int tile_in(int S) { return 4096 >> S; }
@@ -67,34 +68,49 @@ struct Params {
     int log2_interp;      /* 1..6; stages run S = min(log2_interp, 5) */
 };
 
+/* Two consecutive steps k, k + 1 (k even) of one stage from a register window win[j] = x[k - L + j],
+ * j = 0 .. L + 1, fetched with (L + 2) / 2 conflict-free 16-byte shared loads (a thread's window starts
+ * 16 bytes after its neighbour's):  ev[i] = x[k + i - L/2],  od[i] = FIR at step k + i. */
 template <int L>
-SDRD_DEVICE int2 fir_pair(const int2* SDRD_RESTRICT x /* points at x[k] */)
+SDRD_DEVICE void fir_two(const int2* SDRD_RESTRICT x /* points at x[k - L], 16-byte aligned */, int2 (&ev)[2], int2 (&od)[2])
 {
     constexpr int T = L / 2;
     constexpr int C64[16] = SDRD_HB64_ITAPS;
     constexpr int C32[8] = SDRD_HB32_ITAPS;
     constexpr int C16[4] = SDRD_HB16_ITAPS;
-    uint32_t ia = 0, qa = 0;
+    int2 win[L + 2];
 #pragma unroll
-    for (int i = 0; i < T; i++) {
-        const int c = L == 32 ? C64[i & 15] : L == 16 ? C32[i & 7] : C16[i & 3];
-        const int2 a = x[-(L - 1) + i], b = x[-i];
-        ia += ((uint32_t)a.x + (uint32_t)b.x) * (uint32_t)c;
-        qa += ((uint32_t)a.y + (uint32_t)b.y) * (uint32_t)c;
+    for (int j = 0; j < (L + 2) / 2; j++) {
+        const int4 v = reinterpret_cast<const int4*>(x)[j];
+        win[2 * j] = make_int2(v.x, v.y);
+        win[2 * j + 1] = make_int2(v.z, v.w);
     }
-    return make_int2(asr32(ia, 13), asr32(qa, 13));
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        uint32_t ia = 0, qa = 0;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const int c = L == 32 ? C64[t & 15] : L == 16 ? C32[t & 7] : C16[t & 3];
+            const int2 a = win[i + 1 + t], b = win[i + L - t]; /* x[k+i-L+1+t], x[k+i-t] */
+            ia += ((uint32_t)a.x + (uint32_t)b.x) * (uint32_t)c;
+            qa += ((uint32_t)a.y + (uint32_t)b.y) * (uint32_t)c;
+        }
+        od[i] = make_int2(asr32(ia, 13), asr32(qa, 13));
+        ev[i] = win[i + L - L / 2];
+    }
 }
 
-/* stage s: src holds x_{s-1}[src0 ...], dst receives x_s[dst0 ... dst0 + 2 * npairs) (dst0 even) */
+/* stage s: src holds x_{s-1}[src0 ...], dst receives x_s[dst0 ... dst0 + 4 * nquads) (dst0 a multiple of 4,
+ * src0 even) */
 template <int L>
-SDRD_DEVICE void run_stage(const int2* SDRD_RESTRICT src, long long src0, int2* SDRD_RESTRICT dst, long long dst0, int npairs, int tid)
+SDRD_DEVICE void run_stage(const int2* SDRD_RESTRICT src, long long src0, int2* SDRD_RESTRICT dst, long long dst0, int nquads, int tid)
 {
-    for (int q = tid; q < npairs; q += NT) {
-        const long long k = (dst0 >> 1) + q;
-        const int2* x = src + (k - src0);
-        const int2 ev = x[-(L / 2)];
-        const int2 od = fir_pair<L>(x);
-        *reinterpret_cast<int4*>(dst + 2 * q) = make_int4(ev.x, ev.y, od.x, od.y);
+    for (int q = tid; q < nquads; q += NT) {
+        const long long k = (dst0 >> 1) + 2 * q;
+        int2 ev[2], od[2];
+        fir_two<L>(src + (k - L - src0), ev, od);
+        *reinterpret_cast<int4*>(dst + 4 * q) = make_int4(ev[0].x, ev[0].y, od[0].x, od[0].y);
+        *reinterpret_cast<int4*>(dst + 4 * q + 2) = make_int4(ev[1].x, ev[1].y, od[1].x, od[1].y);
     }
 }
 
@@ -130,7 +146,7 @@ SDRD_KERNEL(NT, 2) interpolate_kernel(Params p)
     if (S > (t)) {                                                                                                   \
         constexpr int hs = halo((t), S), hp = halo((t) - 1, S);                                                      \
         run_stage<ring_len(t)>(buf + buf_off((t) - 1, S), (k0 << ((t) - 1)) - hp, buf + buf_off((t), S),           \
-                               (k0 << (t)) - hs, (buf_len((t), S)) >> 1, tid);                                      \
+                               (k0 << (t)) - hs, (buf_len((t), S)) >> 2, tid);                                      \
         __syncthreads();                                                                                             \
     }
     SDRD_HBI_STAGE(1)
@@ -146,15 +162,26 @@ SDRD_KERNEL(NT, 2) interpolate_kernel(Params p)
         const int2* src = buf + buf_off(S - 1, S);
         const long long src0 = (k0 << (S - 1)) - hp;
         const long long n_valid = p.n_in << S; /* stage-S samples that exist */
-        for (int q = tid; q < (K << S) / 2; q += NT) {
-            const long long k = (k0 << (S - 1)) + q;
-            const long long n = 2 * k; /* stage-S index of the pair */
+        for (int q = tid; q < (K << S) / 4; q += NT) {
+            const long long k = (k0 << (S - 1)) + 2 * q;
+            const long long n = 2 * k; /* stage-S index of the first of the four samples */
             if (n >= n_valid) break;
-            const int2* x = src + (k - src0);
-            const uint32_t ev = pack16(x[-(L / 2)]), od = pack16(fir_pair<L>(x));
-            /* sample n of the cascade is emitted at (n >> S << wo) + (n & (2^S - 1)) */
-            const long long pos = ((n >> S) << wo) + (n & ((1 << S) - 1));
-            *reinterpret_cast<uint2*>(out + pos) = make_uint2(ev, od);
+            int2 ev[2], od[2];
+            fir_two<L>(src + (k - L - src0), ev, od);
+            /* sample n of the cascade is emitted at (n >> S << wo) + (n & (2^S - 1)); S >= 2: the four stay together */
+            if (S >= 2) {
+                const long long pos = ((n >> S) << wo) + (n & ((1 << S) - 1));
+                *reinterpret_cast<uint4*>(out + pos) = make_uint4(pack16(ev[0]), pack16(od[0]), pack16(ev[1]), pack16(od[1]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const long long ni = n + 2 * i;
+                    if (ni < n_valid) {
+                        const long long pos = ((ni >> S) << wo) + (ni & ((1 << S) - 1));
+                        *reinterpret_cast<uint2*>(out + pos) = make_uint2(pack16(ev[i]), pack16(od[i]));
+                    }
+                }
+            }
         }
         if (wo > S) { /* interpolate64_cen: 32 zero samples after every 32 (Interpolators.cpp:370,413-603) */
             const int zw = (1 << wo) - (1 << S); /* zero words per input sample */
