@@ -155,92 +155,170 @@ struct EncParams {
     const uint8_t* originals;  /* frame f block j: originals + (f * 128 + j) * block_pitch */
     long long block_pitch;
     uint8_t* recovery;         /* frame f row r: recovery + (f * F + r) * 508 */
+    int n_frames, n_streams;   /* work items = n_streams * n_frames, spread over a persistent grid */
     Tables tab;
 };
 
-inline size_t enc_smem_bytes(int cstride) { return SMEM_FIXED + (size_t)128 * cstride * 2; }
+/* persistent form: two datagram images (the next superframe is gathered while this one is encoded) */
+constexpr int ENC_NT = 512;
+inline size_t enc_smem_bytes(int cstride) { return SMEM_FIXED + (size_t)IMG_WORDS * 4 + (size_t)128 * cstride * 2; }
 
-SDRD_KERNEL(NT, 2) encode_kernel(EncParams p)
+/* 16 warps: warp w takes columns 8w .. 8w+7 of a pass */
+SDRD_DEVICE void enc_matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride, int row0,
+                                 int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
 {
-    SDRD_DYN_SMEM(smem_raw);
-    const int tid = (int)threadIdx.x;
-    const int f = (int)blockIdx.x, s = (int)blockIdx.y;
-    Smem sm = carve(smem_raw, p.cstride);
-    load_tables(sm, p.tab, tid);
-    /* coefficient rows of the Cauchy matrix, transposed so that the 16 rows of a pass are adjacent */
-    for (int k = tid; k < 128 * p.cstride; k += NT) {
-        const int j = k / p.cstride, r = k - j * p.cstride;
-        sm.coefT[k] = (uint16_t)(TAB_ENTRY * (r < p.F ? p.tab.cauchy[r * 128 + j] : (uint8_t)0));
-    }
-
-    const unsigned frame_index = (p.frame_index0 + (unsigned)f) & 0xFFFFu;
-    if (p.mode == 0) {
-        /* UDPSinkFEC::write: block 0 = meta data, blocks 1..127 = 127 samples each */
-        const uint32_t* meta = (f == 0 && p.n_pending > 0) ? p.meta_first : p.meta_next;
-        for (int k = tid; k < ROW_WORDS; k += NT) {
-            uint32_t v = 0;
-            if (k == 0) v = frame_index;
-            else if (k <= 6) v = meta[k - 1];
-            sm.img[k] = v;
-        }
-        for (int k = tid; k < 127; k += NT) sm.img[(k + 1) * ROW_WORDS] = frame_index | ((uint32_t)(k + 1) << 16);
-        const uint32_t* src = p.samples + (long long)s * p.sample_stride;
-        const uint32_t* pend = p.pending + (long long)s * FRAME_SAMPLES;
-        const long long g0 = (long long)f * FRAME_SAMPLES - p.n_pending; /* index into this call's samples */
-        /* one warp per block of 127 samples: four coalesced loads, no index division */
-        for (int b = tid >> 5; b < 127; b += NT / 32) {
-            const long long gb = g0 + (long long)b * 127;
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t acc[RB][4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int i = (tid & 31) + 32 * q;
-                if (i < 127) {
-                    const long long g = gb + i;
-                    sm.img[(b + 1) * ROW_WORDS + 1 + i] = g < 0 ? pend[g + p.n_pending] : src[g];
+    for (int r = 0; r < RB; r++)
+#pragma unroll
+        for (int w = 0; w < 4; w++) acc[r][w] = 0u;
+    for (int jj = 0; jj < 8; jj += 2) {
+        const int j = warp * 8 + jj;
+        uint32_t s0[2][4], s1[2][4], s2[2][4];
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int w = 0; w < 4; w++) selectors(img[(j + c) * ROW_WORDS + lane + 32 * w], s0[c][w], s1[c][w], s2[c][w]);
+        const uint16_t* co0 = coefT + j * cstride + row0;
+        const uint16_t* co1 = co0 + cstride;
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            if (r < nrows) {
+                const unsigned char* e0 = tab + co0[r];
+                const unsigned char* e1 = tab + co1[r];
+                const uint4 a0 = *reinterpret_cast<const uint4*>(e0);
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(e0 + 16);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(e1);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(e1 + 16);
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    uint32_t v = acc[r][w];
+                    v = v ^ prmt(a0.x, a0.y, s0[0][w]) ^ prmt(a0.z, a0.w, s1[0][w]);
+                    v = v ^ prmt(b0, b0, s2[0][w]) ^ prmt(a1.x, a1.y, s0[1][w]);
+                    v = v ^ prmt(a1.z, a1.w, s1[1][w]) ^ prmt(b1, b1, s2[1][w]);
+                    acc[r][w] = v;
                 }
             }
         }
-    } else {
-        for (int k = tid; k < 128 * 127; k += NT) {
-            const int j = k / 127, i = k - j * 127;
-            const uint32_t* row = reinterpret_cast<const uint32_t*>(p.originals + ((long long)f * 128 + j) * p.block_pitch);
-            sm.img[j * ROW_WORDS + 1 + i] = row[i];
+    }
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (r < nrows) {
+#pragma unroll
+            for (int w = 0; w < 4; w++) atomicXor(&rec16[r * ROW_WORDS + lane + 32 * w], acc[r][w]);
         }
-        for (int k = tid; k < 128; k += NT) sm.img[k * ROW_WORDS] = 0u;
     }
-    __syncthreads();
+}
 
-    uint32_t* out = nullptr;
-    if (p.mode == 0) {
-        out = p.dgrams + (long long)s * p.dgram_stride + (long long)f * (128 + p.F) * ROW_WORDS;
-        /* the 128 original datagrams leave as they are */
-        const uint4* src4 = reinterpret_cast<const uint4*>(sm.img);
-        uint4* dst4 = reinterpret_cast<uint4*>(out);
-        for (int k = tid; k < IMG_WORDS / 4; k += NT) dst4[k] = src4[k];
+/* Persistent: CTA c encodes work items c, c + gridDim.x, ... (item = stream * n_frames + frame).  While
+ * item i is being encoded out of one image buffer, the samples of item i + gridDim.x arrive in the other
+ * through cp.async (4-byte LDGSTS: the 127-sample blocks are neither 16-byte aligned nor a multiple of 16
+ * bytes long, which rules the bulk copy out). */
+SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
+{
+    SDRD_DYN_SMEM(smem_raw);
+    const int tid = (int)threadIdx.x;
+    Smem sm = carve(smem_raw, p.cstride);
+    uint32_t* const img2[2] = {sm.img, reinterpret_cast<uint32_t*>(sm.extra)};
+    load_tables(sm, p.tab, tid);
+    /* coefficient rows of the Cauchy matrix, transposed so that the 16 rows of a pass are adjacent */
+    for (int k = tid; k < 128 * p.cstride; k += ENC_NT) {
+        const int j = k / p.cstride, r = k - j * p.cstride;
+        sm.coefT[k] = (uint16_t)(TAB_ENTRY * (r < p.F ? p.tab.cauchy[r * 128 + j] : (uint8_t)0));
     }
+    const long long n_items = (long long)p.n_frames * p.n_streams;
 
-    for (int row0 = 0; row0 < p.F; row0 += RB) {
-        const int nrows = p.F - row0 < RB ? p.F - row0 : RB;
-        for (int k = tid; k < RB * ROW_WORDS; k += NT) sm.rec16[k] = 0u;
-        __syncthreads();
-        matvec_pass(sm.img, sm.coefT, p.cstride, row0, nrows, sm.tab, sm.rec16, tid);
-        __syncthreads();
+    /* request the payload words of work item `it` into image `im`, write its header words */
+    auto gather = [&](long long it, uint32_t* im) {
+        const int s = (int)(it / p.n_frames), f = (int)(it - (long long)s * p.n_frames);
+        const unsigned frame_index = (p.frame_index0 + (unsigned)f) & 0xFFFFu;
         if (p.mode == 0) {
-            /* recovery datagram = header {frameIndex, blockIndex = 128 + r, filler 0} + payload */
-            for (int k = tid; k < nrows; k += NT)
-                sm.rec16[k * ROW_WORDS] = frame_index | ((uint32_t)(128 + row0 + k) << 16);
-            __syncthreads();
-            const uint4* src4 = reinterpret_cast<const uint4*>(sm.rec16);
-            uint4* dst4 = reinterpret_cast<uint4*>(out + (128 + row0) * ROW_WORDS);
-            for (int k = tid; k < nrows * ROW_WORDS / 4; k += NT) dst4[k] = src4[k];
-        } else {
-            for (int k = tid; k < nrows * 127; k += NT) {
-                const int r = k / 127, i = k - r * 127;
-                uint32_t* row = reinterpret_cast<uint32_t*>(p.recovery + ((long long)f * p.F + row0 + r) * 508);
-                row[i] = sm.rec16[r * ROW_WORDS + 1 + i];
+            /* UDPSinkFEC::write: block 0 = meta data, blocks 1..127 = 127 samples each */
+            const uint32_t* meta = (f == 0 && p.n_pending > 0) ? p.meta_first : p.meta_next;
+            for (int k = tid; k < ROW_WORDS; k += ENC_NT) {
+                uint32_t v = 0;
+                if (k == 0) v = frame_index;
+                else if (k <= 6) v = meta[k - 1];
+                im[k] = v;
             }
+            for (int k = tid; k < 127; k += ENC_NT) im[(k + 1) * ROW_WORDS] = frame_index | ((uint32_t)(k + 1) << 16);
+            const uint32_t* src = p.samples + (long long)s * p.sample_stride;
+            const uint32_t* pend = p.pending + (long long)s * FRAME_SAMPLES;
+            const long long g0 = (long long)f * FRAME_SAMPLES - p.n_pending; /* index into this call's samples */
+            /* one warp per block of 127 samples: four coalesced requests, no index division */
+            for (int b = tid >> 5; b < 127; b += ENC_NT / 32) {
+                const long long gb = g0 + (long long)b * 127;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = (tid & 31) + 32 * q;
+                    if (i < 127) {
+                        const long long g = gb + i;
+                        cp_async4(&im[(b + 1) * ROW_WORDS + 1 + i], g < 0 ? &pend[g + p.n_pending] : &src[g]);
+                    }
+                }
+            }
+        } else {
+            for (int j = tid >> 5; j < 128; j += ENC_NT / 32) {
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(p.originals + ((long long)f * 128 + j) * p.block_pitch);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = (tid & 31) + 32 * q;
+                    if (i < 127) cp_async4(&im[j * ROW_WORDS + 1 + i], &row[i]);
+                }
+            }
+            for (int k = tid; k < 128; k += ENC_NT) im[k * ROW_WORDS] = 0u;
         }
-        __syncthreads();
+        cp_async_commit();
+    };
+
+    long long it = blockIdx.x;
+    int cur = 0;
+    if (it < n_items) gather(it, img2[0]);
+    for (; it < n_items; it += gridDim.x, cur ^= 1) {
+        cp_async_wait_all();
+        __syncthreads(); /* image `cur` complete; everybody is done with image `cur ^ 1` */
+        if (it + gridDim.x < n_items) gather(it + gridDim.x, img2[cur ^ 1]);
+        const uint32_t* img = img2[cur];
+        const int s = (int)(it / p.n_frames), f = (int)(it - (long long)s * p.n_frames);
+        const unsigned frame_index = (p.frame_index0 + (unsigned)f) & 0xFFFFu;
+
+        uint32_t* out = nullptr;
+        if (p.mode == 0) {
+            out = p.dgrams + (long long)s * p.dgram_stride + (long long)f * (128 + p.F) * ROW_WORDS;
+            /* the 128 original datagrams leave as they are */
+            const uint4* src4 = reinterpret_cast<const uint4*>(img);
+            uint4* dst4 = reinterpret_cast<uint4*>(out);
+            for (int k = tid; k < IMG_WORDS / 4; k += ENC_NT) dst4[k] = src4[k];
+        }
+        for (int row0 = 0; row0 < p.F; row0 += RB) {
+            const int nrows = p.F - row0 < RB ? p.F - row0 : RB;
+            for (int k = tid; k < RB * ROW_WORDS; k += ENC_NT) sm.rec16[k] = 0u;
+            __syncthreads();
+            enc_matvec_pass(img, sm.coefT, p.cstride, row0, nrows, sm.tab, sm.rec16, tid);
+            __syncthreads();
+            if (p.mode == 0) {
+                /* recovery datagram = header {frameIndex, blockIndex = 128 + r, filler 0} + payload */
+                for (int k = tid; k < nrows; k += ENC_NT)
+                    sm.rec16[k * ROW_WORDS] = frame_index | ((uint32_t)(128 + row0 + k) << 16);
+                __syncthreads();
+                const uint4* src4 = reinterpret_cast<const uint4*>(sm.rec16);
+                uint4* dst4 = reinterpret_cast<uint4*>(out + (128 + row0) * ROW_WORDS);
+                for (int k = tid; k < nrows * ROW_WORDS / 4; k += ENC_NT) dst4[k] = src4[k];
+            } else {
+                for (int r = tid >> 5; r < nrows; r += ENC_NT / 32) {
+                    uint32_t* row = reinterpret_cast<uint32_t*>(p.recovery + ((long long)f * p.F + row0 + r) * 508);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int i = (tid & 31) + 32 * q;
+                        if (i < 127) row[i] = sm.rec16[r * ROW_WORDS + 1 + i];
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
+    cp_async_wait_all();
 }
 
 /* ============================================================================ decode ==== */

@@ -132,6 +132,15 @@ void shift_rule(unsigned ss, int log2_decim, int* norm_shift, int* trunk_shift, 
     *ss_out = ss + (unsigned)log2_decim - trunk;
 }
 
+/* persistent encode grid: one CTA per SM (two image buffers fill the shared memory), equal shares */
+int enc_grid(long long items)
+{
+    const long long sms = rt::sm_count();
+    if (items <= sms) return (int)items;
+    const long long per = (items + sms - 1) / sms;
+    return (int)((items + per - 1) / per);
+}
+
 template <int M, int PRO>
 void launch_decimate_warp2(const hb::Params& p, int n_seg, int S, rt::stream_t st)
 {
@@ -734,7 +743,9 @@ static int sink_run(sdrd_sink* k, const uint32_t* samples, size_t stride, size_t
         p.dgrams = k->d_dgrams;
         p.dgram_stride = (long long)dgram_stride;
         p.tab = k->tab;
-        SDRD_LAUNCH(fec::encode_kernel, n_frames, k->S, fec::NT, fec::enc_smem_bytes(p.cstride), st, p);
+        p.n_frames = (int)n_frames;
+        p.n_streams = k->S;
+        SDRD_LAUNCH(fec::encode_kernel, enc_grid((long long)n_frames * k->S), 1, fec::ENC_NT, fec::enc_smem_bytes(p.cstride), st, p);
         k->launches++;
         if (!SDRD_LAUNCH_OK()) return fail_cuda("encode kernel launch");
     }
@@ -922,7 +933,9 @@ extern "C" int sdrd_cm256_encode_dev(const uint8_t* originals, size_t block_pitc
     p.block_pitch = (long long)block_pitch;
     p.recovery = recovery;
     rt::stream_t st = (rt::stream_t)cuda_stream;
-    SDRD_LAUNCH(fec::encode_kernel, n_frames, 1, fec::NT, fec::enc_smem_bytes(p.cstride), st, p);
+    p.n_frames = n_frames;
+    p.n_streams = 1;
+    SDRD_LAUNCH(fec::encode_kernel, enc_grid(n_frames), 1, fec::ENC_NT, fec::enc_smem_bytes(p.cstride), st, p);
     if (!SDRD_LAUNCH_OK()) return fail_cuda("encode kernel launch");
     return 0;
 }

@@ -109,6 +109,10 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
 }
 
 namespace sdrd {
+/* cp.async (LDGSTS): in the emulation a plain copy, complete at once */
+static inline void cp_async4(void* dst_smem, const void* src_gmem) { memcpy(dst_smem, src_gmem, 4); }
+static inline void cp_async_commit() {}
+static inline void cp_async_wait_all() {}
 typedef std::atomic<uint64_t> mbar_t; /* completed-phase counter */
 static inline void mbar_init(mbar_t* b, int) { b->store(0, std::memory_order_relaxed); }
 static inline void mbar_fence_init() {}
@@ -141,6 +145,14 @@ namespace sdrd {
 typedef uint64_t mbar_t;
 
 SDRD_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+/* cp.async, 4 bytes per thread: global -> shared without passing through registers (SASS: LDGSTS) */
+SDRD_DEVICE void cp_async4(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+SDRD_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+SDRD_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 SDRD_DEVICE void mbar_init(mbar_t* b, int count)
 {
