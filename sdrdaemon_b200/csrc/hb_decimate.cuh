@@ -16,7 +16,7 @@
  * Design (B200; an instruction-issue / shared-memory bound streaming kernel, no tensor cores):
  * one WARP (a 32-thread CTA) walks one segment of one stream through all M stages.
  *
- *   - a step consumes WC0 = 512 cascade-input samples (2 KB, one TMA bulk copy, double buffered) and
+ *   - a step consumes WC0 = 512 cascade-input samples (2 KB, one TMA bulk copy requested a step ahead) and
  *     every lane owns one FIR task of 32 outputs x one component for the life of the warp:
  *         lanes  0-15  stage 1 (8 tasks per component)      lanes 24-27  stage 3
  *         lanes 16-23  stage 2                              lanes 28-29  stage 4
@@ -133,10 +133,10 @@ SDRD_HD constexpr int wmacro(int M) { return M <= 4 ? 1 : 1 << (M - 4); }       
 /* steps between unpacking the first chunk of a pack event and packing its outputs */
 SDRD_HD constexpr int wdelay(int M) { return M <= 4 ? M + 1 : (M == 5 ? 7 : 10); }
 SDRD_HD constexpr int wraw_words(int PRO) { return PRO ? 4 * WC0 : WC0; }
-/* raw double buffer | 2 mbarriers | regions of stages 0..M-1 | 8 words | last stage's results */
+/* raw chunk | mbarrier | regions of stages 0..M-1 | 8 words | last stage's results */
 SDRD_HD constexpr size_t wsmem_bytes(int M, int PRO)
 {
-    return (size_t)2 * wraw_words(PRO) * 4 + 128 + (size_t)(wplane_off(M, 0, 0) + 40) * 4 + (size_t)2 * wfin_stride(M) * 4;
+    return (size_t)wraw_words(PRO) * 4 + 128 + (size_t)(wplane_off(M, 0, 0) + 40) * 4 + (size_t)2 * wfin_stride(M) * 4;
 }
 /* warm-up chunks in front of a segment: >= 61 * (2^M - 1) samples, whole pack events */
 SDRD_HD constexpr int wwarm_chunks(int M)
@@ -225,8 +225,8 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
     const int seg = (int)blockIdx.x;
     const int s = (int)blockIdx.y;
     uint32_t* raw = reinterpret_cast<uint32_t*>(smem);
-    mbar_t* bars = reinterpret_cast<mbar_t*>(smem + (size_t)2 * RAWW * 4);
-    int* planes = reinterpret_cast<int*>(smem + (size_t)2 * RAWW * 4 + 128);
+    mbar_t* bars = reinterpret_cast<mbar_t*>(smem + (size_t)RAWW * 4);
+    int* planes = reinterpret_cast<int*>(smem + (size_t)RAWW * 4 + 128);
     int* fin = planes + wplane_off(M, 0, 0) + 8; /* residue 8 words: the last stage's stores miss the others' banks */
 
     const long long seg_first_out = (long long)seg * p.seg_out;
@@ -304,11 +304,10 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
 
     if (lane == 0) {
         mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
         mbar_fence_init();
-        for (int c = 0; c < 2 && c < NC; c++) {
-            mbar_arrive_expect_tx(&bars[c], chunk_bytes);
-            tma_load_1d(raw + (size_t)c * RAWW, src + (size_t)c * RAWW, chunk_bytes, &bars[c]);
+        if (NC > 0) {
+            mbar_arrive_expect_tx(&bars[0], chunk_bytes);
+            tma_load_1d(raw, src, chunk_bytes, &bars[0]);
         }
     }
     SDRD_SYNCWARP();
@@ -375,8 +374,8 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
         uint4 rw[4];
         int2 x[16];
         if (unpack_now) {
-            mbar_wait(&bars[u & 1], (uint32_t)((u >> 1) & 1));
-            const uint4* r4 = reinterpret_cast<const uint4*>(raw + (size_t)(u & 1) * RAWW);
+            mbar_wait(&bars[0], (uint32_t)(u & 1));
+            const uint4* r4 = reinterpret_cast<const uint4*>(raw);
             if (!PRO) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) rw[k] = r4[32 * k + lane];
@@ -447,9 +446,11 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
         }
 
         SDRD_SYNCWARP();
-        if (lane == 0 && u + 2 < NC) {
-            mbar_arrive_expect_tx(&bars[u & 1], chunk_bytes);
-            tma_load_1d(raw + (size_t)(u & 1) * RAWW, src + (size_t)(u + 2) * RAWW, chunk_bytes, &bars[u & 1]);
+        /* every lane has read chunk u out of the raw buffer: request chunk u + 1 into it; it has the whole
+         * arithmetic phase of the next step to arrive */
+        if (lane == 0 && u + 1 < NC) {
+            mbar_arrive_expect_tx(&bars[0], chunk_bytes);
+            tma_load_1d(raw, src + (size_t)(u + 1) * RAWW, chunk_bytes, &bars[0]);
         }
     }
 }
