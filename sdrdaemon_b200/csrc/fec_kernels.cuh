@@ -11,7 +11,8 @@
  * Both are the same computation: R output blocks, each a GF(2^8)-linear combination of the 128
  * blocks of the frame,  out[r] = XOR_j C[r][j] (x) blk[j]  over 508 payload bytes.  For the encoder C
  * is the fixed Cauchy matrix; for the decoder C = [A^-1 | A^-1 M] is built per frame from the
- * erasure pattern (A = Cauchy sub-matrix of the received recovery rows x erased columns).
+ * erasure pattern (A = Cauchy sub-matrix of the received recovery rows x erased columns, inverted in
+ * closed form).
  *
  * One CTA owns one superframe, kept in shared memory as 128 datagram images of 128 words (header
  * word + 127 payload words).  A constant-times-block product works on 4 packed bytes at a time:
@@ -339,17 +340,8 @@ struct DecParams {
 template <int DCAP>
 inline size_t dec_smem_bytes()
 {
-    /* coefT [128][DCAP] + aug [DCAP][2*DCAP] + exp/log + small lists */
+    /* coefT [128][DCAP] + scratch [DCAP][2*DCAP] (log of the inverse) + exp/log + small lists */
     return SMEM_FIXED + (size_t)128 * DCAP * 2 + (size_t)DCAP * 2 * DCAP + 512 + 256 + 2048;
-}
-
-SDRD_DEVICE uint8_t gmul(const uint8_t* ex, const uint8_t* lg, uint8_t a, uint8_t b)
-{
-    return (a && b) ? ex[lg[a] + lg[b]] : (uint8_t)0;
-}
-SDRD_DEVICE uint8_t gdiv(const uint8_t* ex, const uint8_t* lg, uint8_t a, uint8_t b)
-{
-    return a ? ex[lg[a] + 255 - lg[b]] : (uint8_t)0;
 }
 
 template <int DCAP>
@@ -448,65 +440,70 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
             /* cm256's single-recovery shortcut: XOR of everything received, whatever the row */
             for (int k = tid; k < 128 * DCAP; k += NT) sm.coefT[k] = (uint16_t)((k % DCAP) == 0 ? TAB_ENTRY : 0);
         } else {
-            /* A[k][c] = M[x_k][e_c]; invert by Gauss-Jordan on [A | I] (no pivoting needed: every
-             * leading minor of a Cauchy matrix is non-zero) */
-            const int W2 = 2 * N;
-            for (int k = tid; k < N * W2; k += NT) {
-                const int r = k / W2, c = k - r * W2;
-                uint8_t v;
-                if (c < N) {
-                    const uint8_t x = recIdxOf[r], y = erased[c];
-                    v = gdiv(gfexp, gflog, (uint8_t)(y ^ 128), (uint8_t)(x ^ y));
-                } else {
-                    v = (uint8_t)((c - N) == r ? 1 : 0);
+            /* A[k][c] = M[x_k][e_c] = d_c / (x_k ^ y_c) with x_k = index of recovery block k (128..255),
+             * y_c = erased original c (0..127), d_c = y_c ^ 128: a Cauchy matrix with scaled columns, whose
+             * inverse is explicit (no elimination, no pivots, two barriers):
+             *   Ainv[c][k] = P_c * Q_k / (d_c * (x_k ^ y_c)),
+             *   P_c = prod_j (y_c ^ x_j) / prod_{j != c} (y_c ^ y_j),  Q_k = prod_j (x_k ^ y_j) / prod_{j != k} (x_k ^ x_j).
+             * Everything is kept as discrete logarithms (entries of the inverse are never zero). */
+            uint8_t* lA = aug;                  /* [N][N] log Ainv[c][k] */
+            uint8_t* lq = erased + 128;         /* [N] log Q_k */
+            uint8_t* lp = lq + 128;             /* [N] log (P_c / d_c) */
+            if (tid < 2 * N) {
+                const bool isx = tid < N;
+                const int me = isx ? tid : tid - N;
+                const int v = isx ? recIdxOf[me] : erased[me];
+                int acc = 0;
+                for (int j = 0; j < N; j++) {
+                    const int xo = recIdxOf[j], yo = erased[j];
+                    acc += gflog[v ^ (isx ? yo : xo)];                      /* the other family: all of it */
+                    if (j != me) acc += 255 - gflog[v ^ (isx ? xo : yo)];   /* the own family: all but itself */
                 }
-                aug[r * W2 + c] = v;
+                if (!isx) acc += 255 - gflog[v ^ 128];
+                (isx ? lq : lp)[me] = (uint8_t)(acc % 255);
             }
             __syncthreads();
-            for (int col = 0; col < N; col++) {
-                const uint8_t piv = aug[col * W2 + col];
-                __syncthreads();
-                if (piv == 0) {
-                    if (tid == 0) flags[1] = 1;
-                    break;
-                }
-                for (int c = tid; c < W2; c += NT) aug[col * W2 + c] = gdiv(gfexp, gflog, aug[col * W2 + c], piv);
-                __syncthreads();
-                for (int k = tid; k < N * W2; k += NT) {
-                    const int r = k / W2, c = k - r * W2;
-                    if (r == col || c == col) continue;
-                    const uint8_t fac = aug[r * W2 + col];
-                    aug[k] ^= gmul(gfexp, gflog, fac, aug[col * W2 + c]);
-                }
-                __syncthreads();
-                for (int r = tid; r < N; r += NT)
-                    if (r != col) aug[r * W2 + col] = 0;
-                __syncthreads();
+            for (int k = tid; k < N * N; k += NT) {
+                const int c = k / N, kk = k - c * N;
+                lA[k] = (uint8_t)((lp[c] + lq[kk] + 255 - gflog[recIdxOf[kk] ^ erased[c]]) % 255);
             }
             __syncthreads();
-            if (flags[1]) {
-                st = ST_FAILED;
-                do_decode = false;
-            } else {
-                /* X_c = sum_k Ainv[c][k] * (rec_k ^ sum_o M[x_k][o] * orig_o) */
-                for (int k = tid; k < 128 * N; k += NT) {
-                    const int i = k / N, c = k - i * N; /* image row i, output row c */
-                    const int idx = (int)((sm.img[i * ROW_WORDS] >> 16) & 0xFFu);
-                    uint8_t v = 0;
-                    if (idx >= 128) {
-                        /* which recovery slot is image row i */
-                        const int wq = i >> 5;
-                        int kk = __popc(recMask[wq] & ((1u << (i & 31)) - 1u));
-                        for (int q = 0; q < wq; q++) kk += __popc(recMask[q]);
-                        v = aug[c * W2 + N + kk];
-                    } else if (origRow[idx] == i) {
+            /* D[c][i], the weight of image row i in erased original c:  X_c = sum_k Ainv[c][k] * (rec_k ^
+             * sum_o M[x_k][o] * orig_o).  Thread (i, h) does image row i for the rows c in every other
+             * block of 16, h = 0 / 1. */
+            {
+                const int i = tid & 127, h = tid >> 7;
+                const int idx = (int)((sm.img[i * ROW_WORDS] >> 16) & 0xFFu);
+                int kind = 0, kk0 = 0; /* 0: row not used, 1: recovery slot kk0, 2: an original */
+                if (idx >= 128) {
+                    kind = 1;
+                    const int wq = i >> 5;
+                    kk0 = __popc(recMask[wq] & ((1u << (i & 31)) - 1u));
+                    for (int q = 0; q < wq; q++) kk0 += __popc(recMask[q]);
+                } else if (origRow[idx] == i) {
+                    kind = 2;
+                }
+                const int lnum = gflog[(idx ^ 128) & 0xFF]; /* log of M's numerator (only used when kind == 2) */
+                for (int c0 = 16 * h; c0 < N; c0 += 32) {
+                    uint32_t acc[16];
+#pragma unroll
+                    for (int cc = 0; cc < 16; cc++) acc[cc] = 0u;
+                    if (kind == 1) {
+#pragma unroll
+                        for (int cc = 0; cc < 16; cc++)
+                            if (c0 + cc < N) acc[cc] = gfexp[lA[(c0 + cc) * N + kk0]];
+                    } else if (kind == 2) {
                         for (int kk = 0; kk < N; kk++) {
-                            const uint8_t x = recIdxOf[kk];
-                            const uint8_t m = gdiv(gfexp, gflog, (uint8_t)(idx ^ 128), (uint8_t)(x ^ idx));
-                            v ^= gmul(gfexp, gflog, aug[c * W2 + N + kk], m);
+                            int lm = lnum + 255 - gflog[recIdxOf[kk] ^ idx]; /* log M[x_kk][idx] */
+                            if (lm >= 255) lm -= 255;
+#pragma unroll
+                            for (int cc = 0; cc < 16; cc++)
+                                if (c0 + cc < N) acc[cc] ^= gfexp[lA[(c0 + cc) * N + kk] + lm];
                         }
                     }
-                    sm.coefT[i * DCAP + c] = (uint16_t)(TAB_ENTRY * v);
+#pragma unroll
+                    for (int cc = 0; cc < 16; cc++)
+                        if (c0 + cc < N) sm.coefT[i * DCAP + c0 + cc] = (uint16_t)(TAB_ENTRY * acc[cc]);
                 }
             }
         }
