@@ -218,6 +218,36 @@ int sdrd_fec_decode_dev(const uint8_t* superblocks, size_t blocks_pitch, const i
 int sdrd_cm256_encode_dev(const uint8_t* originals, size_t block_pitch, int n_frames, int recovery_count,
                           uint8_t* recovery, void* cuda_stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Receiver framing, batched: SDRdaemonFECBuffer::writeAndRead (sdmnbase/SDRdaemonFECBuffer.cpp:112-250)
+ * applied to a whole burst of datagrams in arrival order -- what UDPSourceFEC::read does one
+ * datagram at a time (sdmnbase/UDPSourceFEC.cpp:52-78).  Every change of header.frameIndex closes the
+ * current slot (a frame is the run of datagrams between two changes; only its first 128 count, :143);
+ * all slots closed by a call are decoded in ONE kernel launch; the open slot is carried to the next call.
+ * As in the reference, the very first datagram closes the initial empty slot, which comes out as a frame
+ * of zeros with 0 blocks.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdrd_src sdrd_src;
+
+/* max_datagrams = most datagrams a single feed call may carry */
+int sdrd_src_create(sdrd_src** src, size_t max_datagrams);
+void sdrd_src_destroy(sdrd_src* src);
+int sdrd_src_reset(sdrd_src* src);
+/* datagrams: n x 512 bytes (HOST).  Outputs for the frames closed by this call, in order:
+ *   payload      n_frames x 127 x 508 bytes (blocks 1..127; missing blocks zero, :109)
+ *   block0       n_frames x 508 bytes or NULL
+ *   status       SDRD_FRAME_* per frame
+ *   nb_blocks    datagrams received for the frame (m_curNbBlocks, uncapped), nb_recovery (m_curNbRecovery)
+ * frame_capacity bounds n_frames (SDRD_ERANGE otherwise; at most n + 1 frames can close). */
+int sdrd_src_feed(sdrd_src* src, const uint8_t* datagrams, size_t n, uint8_t* payload, uint8_t* block0,
+                  size_t frame_capacity, size_t* n_frames, int* status, int* nb_blocks, int* nb_recovery);
+/* the reference's getters: the min / max getters reset their value (include/SDRdaemonFECBuffer.h:95-110) */
+int sdrd_src_cur_nb_blocks(const sdrd_src* src);
+int sdrd_src_cur_nb_recovery(const sdrd_src* src);
+int sdrd_src_min_nb_blocks(sdrd_src* src);
+int sdrd_src_max_nb_recovery(sdrd_src* src);
+long long sdrd_src_launches(const sdrd_src* src);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,15 @@ SYMBOLS = [
     ("sdrd_dec_dev_output", _P, [_P, _SZP]),
     ("sdrd_dec_process_dev", C.c_int, [_P, _SZ, _SZP, _UP, _P]),
     ("sdrd_dec_launches", C.c_longlong, [_P]),
+    ("sdrd_src_create", C.c_int, [C.POINTER(_P), _SZ]),
+    ("sdrd_src_destroy", None, [_P]),
+    ("sdrd_src_reset", C.c_int, [_P]),
+    ("sdrd_src_feed", C.c_int, [_P, _P, _SZ, _P, _P, _SZ, _SZP, _P, _P, _P]),
+    ("sdrd_src_cur_nb_blocks", C.c_int, [_P]),
+    ("sdrd_src_cur_nb_recovery", C.c_int, [_P]),
+    ("sdrd_src_min_nb_blocks", C.c_int, [_P]),
+    ("sdrd_src_max_nb_recovery", C.c_int, [_P]),
+    ("sdrd_src_launches", C.c_longlong, [_P]),
     ("sdrd_int_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _SZ]),
     ("sdrd_int_destroy", None, [_P]),
     ("sdrd_int_reset", C.c_int, [_P]),
@@ -440,3 +449,53 @@ class Rx:
         nfr = C.c_size_t(0)
         self.lib.check(self.lib.sdrd_rx_process_dev(self._h, n_in, C.byref(nfr), _P(stream)))
         return nfr.value
+
+
+class Source:
+    """Batched receiver framing (sdrd_src_*): SDRdaemonFECBuffer::writeAndRead over bursts of datagrams."""
+
+    def __init__(self, max_datagrams: int = 4096, lib: Optional[Library] = None):
+        self.lib = lib or load()
+        self._h = _P()
+        self.max_datagrams = max_datagrams
+        self.lib.check(self.lib.sdrd_src_create(C.byref(self._h), max_datagrams))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sdrd_src_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        self.lib.check(self.lib.sdrd_src_reset(self._h))
+
+    def feed(self, datagrams: np.ndarray):
+        """datagrams (n, 512) uint8 in arrival order -> (payload (f,127,508), block0 (f,508), status, nb_blocks, nb_recovery)
+        for the f frames closed by this burst."""
+        dg = np.ascontiguousarray(datagrams, dtype=np.uint8).reshape(-1, 512)
+        n = len(dg)
+        cap = n + 1
+        pay = np.zeros((cap, 127, 508), np.uint8)
+        b0 = np.zeros((cap, 508), np.uint8)
+        st = np.zeros(cap, np.int32)
+        nbl = np.zeros(cap, np.int32)
+        nrec = np.zeros(cap, np.int32)
+        nf = C.c_size_t(0)
+        self.lib.check(self.lib.sdrd_src_feed(self._h, dg.ctypes.data, n, pay.ctypes.data, b0.ctypes.data, cap, C.byref(nf),
+                                              st.ctypes.data, nbl.ctypes.data, nrec.ctypes.data))
+        f = nf.value
+        return pay[:f].copy(), b0[:f].copy(), st[:f].copy(), nbl[:f].copy(), nrec[:f].copy()
+
+    def stats(self) -> Tuple[int, int]:
+        return self.lib.sdrd_src_cur_nb_blocks(self._h), self.lib.sdrd_src_cur_nb_recovery(self._h)
+
+    def min_nb_blocks(self) -> int:
+        return self.lib.sdrd_src_min_nb_blocks(self._h)
+
+    def max_nb_recovery(self) -> int:
+        return self.lib.sdrd_src_max_nb_recovery(self._h)
+
+    @property
+    def launches(self) -> int:
+        return self.lib.sdrd_src_launches(self._h)

@@ -329,6 +329,7 @@ constexpr int ST_INCOMPLETE = 0, ST_COMPLETE = 1, ST_RECOVERED = 2, ST_FAILED = 
 struct DecParams {
     const uint32_t* sb;        /* frame f datagram i: sb + (f * blocks_pitch + i) * 128 */
     long long blocks_pitch;    /* datagrams */
+    const long long* frame_start; /* optional: frame f begins at datagram frame_start[f] instead of f * blocks_pitch */
     const int* n_blocks;       /* [n_frames] */
     uint32_t* payload;         /* frame f: payload + f * 127 * 127 words (blocks 1..127) */
     uint32_t* block0;          /* frame f: block0 + f * 127 words, may be null */
@@ -374,7 +375,8 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
     if (nb > 128) nb = 128; /* blocks beyond the first 128 received are dropped (.cpp:143) */
     if (nb < 0) nb = 0;
     {
-        const uint4* src4 = reinterpret_cast<const uint4*>(p.sb + (long long)f * p.blocks_pitch * ROW_WORDS);
+        const long long first = p.frame_start ? p.frame_start[f] : (long long)f * p.blocks_pitch;
+        const uint4* src4 = reinterpret_cast<const uint4*>(p.sb + first * ROW_WORDS);
         uint4* dst4 = reinterpret_cast<uint4*>(sm.img);
         for (int k = tid; k < nb * (ROW_WORDS / 4); k += NT) dst4[k] = src4[k];
         for (int k = nb * (ROW_WORDS / 4) + tid; k < IMG_WORDS / 4; k += NT) dst4[k] = make_uint4(0u, 0u, 0u, 0u);

@@ -1019,3 +1019,185 @@ extern "C" int sdrd_fec_decode(const uint8_t* superblocks, size_t blocks_pitch, 
     SDRD_TRY(rt::sync(0), "fec decode");
     return 0;
 }
+
+/* ========================================================================================== */
+/* batched receiver framing                                                                    */
+/* ========================================================================================== */
+
+struct sdrd_src {
+    size_t max_dg = 0;
+    /* the open slot: its first <= 128 datagrams (host copy), counters as SDRdaemonFECBuffer keeps them */
+    std::vector<uint8_t> carry;      /* 128 x 512 */
+    int frame_head = -1, block_count = 0, recovery_count = 0;
+    int cur_nb_blocks = 0, cur_nb_recovery = 0, min_nb_blocks = 256, max_nb_recovery = 0;
+    /* device side */
+    uint8_t* d_dg = nullptr;         /* (128 + max_dg) datagrams: carried ones, then the call's */
+    long long* d_start = nullptr;    /* [max_dg + 1] */
+    int* d_nb = nullptr;             /* [max_dg + 1] */
+    int* d_status = nullptr;
+    uint8_t* d_payload = nullptr;    /* grow-only */
+    uint8_t* d_block0 = nullptr;
+    size_t frames_cap = 0;
+    long long launches = 0;
+    rt::stream_t stream = 0;
+};
+
+extern "C" int sdrd_src_create(sdrd_src** out, size_t max_datagrams)
+{
+    if (!out) return fail(SDRD_EINVAL, "null handle pointer");
+    *out = nullptr;
+    if (max_datagrams < 1) return fail(SDRD_EINVAL, "max_datagrams must be positive");
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    sdrd_src* k = new (std::nothrow) sdrd_src();
+    if (!k) return fail(SDRD_ENOMEM, "out of host memory");
+    k->max_dg = max_datagrams;
+    k->carry.assign((size_t)128 * SDRD_UDPSIZE, 0);
+    if (rt::alloc((void**)&k->d_dg, (128 + max_datagrams) * (size_t)SDRD_UDPSIZE) != 0 ||
+        rt::alloc((void**)&k->d_start, (max_datagrams + 1) * sizeof(long long)) != 0 ||
+        rt::alloc((void**)&k->d_nb, (max_datagrams + 1) * sizeof(int)) != 0 ||
+        rt::alloc((void**)&k->d_status, (max_datagrams + 1) * sizeof(int)) != 0 || rt::stream_create(&k->stream) != 0) {
+        int rc = fail_cuda("allocating receiver buffers");
+        sdrd_src_destroy(k);
+        return rc;
+    }
+    *out = k;
+    return 0;
+}
+
+extern "C" void sdrd_src_destroy(sdrd_src* k)
+{
+    if (!k) return;
+    rt::sync(k->stream);
+    rt::release(k->d_dg);
+    rt::release(k->d_start);
+    rt::release(k->d_nb);
+    rt::release(k->d_status);
+    rt::release(k->d_payload);
+    rt::release(k->d_block0);
+    rt::stream_destroy(k->stream);
+    delete k;
+}
+
+extern "C" int sdrd_src_reset(sdrd_src* k)
+{
+    if (!k) return fail(SDRD_EINVAL, "null handle");
+    k->frame_head = -1;
+    k->block_count = k->recovery_count = 0;
+    k->cur_nb_blocks = k->cur_nb_recovery = 0;
+    k->min_nb_blocks = 256;
+    k->max_nb_recovery = 0;
+    return 0;
+}
+extern "C" int sdrd_src_cur_nb_blocks(const sdrd_src* k) { return k ? k->cur_nb_blocks : -1; }
+extern "C" int sdrd_src_cur_nb_recovery(const sdrd_src* k) { return k ? k->cur_nb_recovery : -1; }
+extern "C" int sdrd_src_min_nb_blocks(sdrd_src* k)
+{
+    if (!k) return -1;
+    int v = k->min_nb_blocks;
+    k->min_nb_blocks = 256;
+    return v;
+}
+extern "C" int sdrd_src_max_nb_recovery(sdrd_src* k)
+{
+    if (!k) return -1;
+    int v = k->max_nb_recovery;
+    k->max_nb_recovery = 0;
+    return v;
+}
+extern "C" long long sdrd_src_launches(const sdrd_src* k) { return k ? k->launches : 0; }
+
+extern "C" int sdrd_src_feed(sdrd_src* k, const uint8_t* dg, size_t n, uint8_t* payload, uint8_t* block0, size_t frame_capacity,
+                             size_t* n_frames_p, int* status, int* nb_blocks, int* nb_recovery)
+{
+    if (!k) return fail(SDRD_EINVAL, "null handle");
+    if (n_frames_p) *n_frames_p = 0;
+    if (n == 0) return 0;
+    if (!dg) return fail(SDRD_EINVAL, "null datagram pointer");
+    if (n > k->max_dg) return fail(SDRD_ERANGE, "more datagrams than the max_datagrams given at create time");
+    /* ---- host: SDRdaemonFECBuffer::writeAndRead's bookkeeping, datagram by datagram (.cpp:118-168).
+     * Device array = [stored datagrams of the open slot | this call's datagrams]; a frame's first <= 128
+     * datagrams are contiguous in it. */
+    const int carried = k->block_count < 128 ? k->block_count : 128; /* datagrams of the open slot held in `carry` */
+    std::vector<long long> start;
+    std::vector<int> nb, fr_blocks, fr_recovery;
+    long long slot_start = 0; /* position of the open slot's first datagram in the device array */
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* sb = dg + i * SDRD_UDPSIZE;
+        const int frame_index = sb[0] | (sb[1] << 8);
+        if (k->frame_head != frame_index) {
+            start.push_back(slot_start);
+            nb.push_back(k->block_count < 128 ? k->block_count : 128);
+            fr_blocks.push_back(k->block_count);
+            fr_recovery.push_back(k->recovery_count);
+            k->cur_nb_blocks = k->block_count;
+            k->cur_nb_recovery = k->recovery_count;
+            if (k->cur_nb_blocks < k->min_nb_blocks) k->min_nb_blocks = k->cur_nb_blocks;
+            if (k->cur_nb_recovery > k->max_nb_recovery) k->max_nb_recovery = k->cur_nb_recovery;
+            k->block_count = 0;
+            k->recovery_count = 0;
+            k->frame_head = frame_index;
+            slot_start = (long long)carried + (long long)i;
+        }
+        if (k->block_count < 128 && sb[2] >= 128) k->recovery_count++;
+        k->block_count++;
+    }
+    const size_t nf = start.size();
+    if (nf > frame_capacity) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of frames closed by this call");
+    if (nf && (!payload || !status)) return fail(SDRD_EINVAL, "null output pointer");
+    rt::stream_t st = k->stream;
+    if (nf) {
+        if (nf > k->frames_cap) {
+            rt::sync(st);
+            rt::release(k->d_payload);
+            rt::release(k->d_block0);
+            k->d_payload = k->d_block0 = nullptr;
+            k->frames_cap = 0;
+            if (rt::alloc((void**)&k->d_payload, nf * (size_t)127 * SDRD_BLOCK_BYTES) != 0 ||
+                rt::alloc((void**)&k->d_block0, nf * (size_t)SDRD_BLOCK_BYTES) != 0)
+                return fail_cuda("allocating receiver output buffers");
+            k->frames_cap = nf;
+        }
+        if (carried) SDRD_TRY(rt::copy(k->d_dg, k->carry.data(), (size_t)carried * SDRD_UDPSIZE, rt::H2D, st), "copy carried datagrams");
+        SDRD_TRY(rt::copy(k->d_dg + (size_t)carried * SDRD_UDPSIZE, dg, n * SDRD_UDPSIZE, rt::H2D, st), "copy datagrams to device");
+        SDRD_TRY(rt::copy(k->d_start, start.data(), nf * sizeof(long long), rt::H2D, st), "copy frame table");
+        SDRD_TRY(rt::copy(k->d_nb, nb.data(), nf * sizeof(int), rt::H2D, st), "copy frame table");
+        fec::DecParams p{};
+        if (int rc = get_tables(&p.tab)) return rc;
+        p.sb = reinterpret_cast<const uint32_t*>(k->d_dg);
+        p.blocks_pitch = 128;
+        p.frame_start = k->d_start;
+        p.n_blocks = k->d_nb;
+        p.payload = reinterpret_cast<uint32_t*>(k->d_payload);
+        p.block0 = reinterpret_cast<uint32_t*>(k->d_block0);
+        p.status = k->d_status;
+        p.pass = 0;
+        SDRD_LAUNCH(fec::decode_kernel<32>, (int)nf, 1, fec::NT, fec::dec_smem_bytes<32>(), st, p);
+        p.pass = 1;
+        SDRD_LAUNCH(fec::decode_kernel<128>, (int)nf, 1, fec::NT, fec::dec_smem_bytes<128>(), st, p);
+        k->launches += 2;
+        if (!SDRD_LAUNCH_OK()) return fail_cuda("decode kernel launch");
+        SDRD_TRY(rt::copy(payload, k->d_payload, nf * (size_t)127 * SDRD_BLOCK_BYTES, rt::D2H, st), "copy payload to host");
+        if (block0) SDRD_TRY(rt::copy(block0, k->d_block0, nf * (size_t)SDRD_BLOCK_BYTES, rt::D2H, st), "copy block 0 to host");
+        SDRD_TRY(rt::copy(status, k->d_status, nf * sizeof(int), rt::D2H, st), "copy status to host");
+        SDRD_TRY(rt::sync(st), "receiver decode");
+        for (size_t f = 0; f < nf; f++) {
+            if (nb_blocks) nb_blocks[f] = fr_blocks[f];
+            if (nb_recovery) nb_recovery[f] = fr_recovery[f];
+        }
+    }
+    /* ---- keep the open slot's first <= 128 datagrams for the next call ---- */
+    {
+        const int have = k->block_count < 128 ? k->block_count : 128;
+        if (nf == 0) {
+            /* the slot was open before this call: append what arrived */
+            for (int j = carried; j < have; j++)
+                memcpy(&k->carry[(size_t)j * SDRD_UDPSIZE], dg + (size_t)(j - carried) * SDRD_UDPSIZE, SDRD_UDPSIZE);
+        } else {
+            const size_t first = (size_t)(slot_start - carried); /* index in dg of the open slot's first datagram */
+            memcpy(k->carry.data(), dg + first * SDRD_UDPSIZE, (size_t)have * SDRD_UDPSIZE);
+        }
+    }
+    if (n_frames_p) *n_frames_p = nf;
+    return 0;
+}

@@ -161,3 +161,57 @@ def check_decode(lib, ob, sb, nb):
         assert np.array_equal(pay[f], po), f"frame {f}: payload differs"
         assert np.array_equal(b0[f], bo), f"frame {f}: block 0 differs"
     return pay, b0, st
+
+
+def receiver_traffic(ob, rng, n_frames, F):
+    """A datagram stream as a lossy network would deliver it: per frame some blocks dropped, some
+    duplicated, recovery blocks sometimes ahead of originals, one frame interrupted by a stray datagram
+    of another frame index, one frame with more than 128 datagrams.  Returns (x, datagrams (n, 512))."""
+    x, frames = make_frames(ob, rng, n_frames, F)
+    out = []
+    for f in range(n_frames):
+        fr = frames[f]
+        order = list(range(128 + F))
+        kind = f % 6
+        if kind == 1:    # lose up to F originals
+            lost = set(rng.choice(128, size=int(rng.integers(1, F + 1)), replace=False).tolist())
+            order = [i for i in order if i not in lost]
+        elif kind == 2:  # lose more than can be recovered
+            lost = set(rng.choice(128, size=F + 3, replace=False).tolist())
+            order = [i for i in order if i not in lost]
+        elif kind == 3:  # a recovery block overtakes the originals, one original lost
+            order = [128] + [i for i in range(128) if i != 77] + list(range(129, 128 + F))
+        elif kind == 4:  # duplicates: more than 128 datagrams, the tail is dropped
+            order = list(range(128)) + [5, 6, 7] + list(range(128, 128 + F))
+        elif kind == 5:  # short frame
+            order = list(range(0, 60))
+        out.append(fr[order])
+        if f == 2:       # a stray datagram of an old frame closes the slot early
+            out.append(frames[0][10:11])
+    return x, np.concatenate(out)
+
+
+def check_receiver(lib, ob, dg, cuts):
+    """feed `dg` in bursts cut at `cuts`; every closed frame and the counters equal SDRdaemonFECBuffer (oracle)"""
+    src = capi.Source(max_datagrams=max(b - a for a, b in zip(cuts[:-1], cuts[1:])), lib=lib)
+    fb = ob.FecBuffer()
+    n_checked = 0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        want, want_stats = [], []
+        for i in range(a, b):
+            fr = fb.write_and_read(dg[i])
+            if fr is not None:
+                want.append(fr)
+                want_stats.append(fb.stats())
+        pay, b0, st, nbl, nrec = src.feed(dg[a:b])
+        assert len(pay) == len(want), (a, b, len(pay), len(want))
+        for f in range(len(want)):
+            assert np.array_equal(pay[f].reshape(-1), want[f]), (a, b, f)
+            assert (int(nbl[f]), int(nrec[f])) == want_stats[f], (a, b, f, nbl[f], nrec[f], want_stats[f])
+            n_checked += 1
+        if b > a:
+            assert src.stats() == fb.stats()
+    assert src.min_nb_blocks() == fb.min_nb_blocks() and src.max_nb_recovery() == fb.max_nb_recovery()
+    assert src.min_nb_blocks() == 256 and fb.min_nb_blocks() == 256  # the getters reset
+    src.close()
+    return n_checked

@@ -91,6 +91,14 @@ def test_decode_all_branches(emu_lib, oracle):
         assert np.array_equal(pay[f].reshape(-1), x[f * cases.FRAME:(f + 1) * cases.FRAME].view(np.uint8).reshape(-1))
 
 
+def test_receiver_batched(emu_lib, oracle):
+    rng = np.random.default_rng(650)
+    x, dg = cases.receiver_traffic(oracle, rng, 9, 8)
+    n = len(dg)
+    assert cases.check_receiver(emu_lib, oracle, dg, [0, n]) >= 10           # one burst
+    assert cases.check_receiver(emu_lib, oracle, dg, [0, 1, 1, 50, 137, 300, 301, 700, n]) >= 10  # ragged bursts, empty burst
+
+
 def test_golden_through_emulation(emu_lib):
     """the golden vectors through the emulated library as well (host logic + kernel indexing)"""
     import golden_cases

@@ -213,6 +213,15 @@ def test_config4_decode_4096_frames(gpu_lib, oracle):
         assert so == 2 and np.array_equal(po, pay[f])
 
 
+def test_receiver_batched(gpu_lib, oracle):
+    rng = np.random.default_rng(651)
+    for F in (8, 40):
+        x, dg = cases.receiver_traffic(oracle, rng, 13, F)
+        n = len(dg)
+        assert cases.check_receiver(gpu_lib, oracle, dg, [0, n]) >= 13
+        assert cases.check_receiver(gpu_lib, oracle, dg, [0, 3, 3, 129, 500, 501, 1200, n]) >= 13
+
+
 def test_rx_pipeline_config2(gpu_lib, oracle):
     """config 2 end to end through sdrd_rx_process: decimate-by-16 + 128+16 FEC, ragged call sizes."""
     from sdrdaemon_b200 import capi
