@@ -272,19 +272,26 @@ extern "C" void* sdrd_dec_dev_output(sdrd_dec* d, size_t* stride)
     return d->d_out;
 }
 
-static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_bits, rt::stream_t st)
+/* in_off / first / last: a call may be processed in consecutive slices of the input buffer (sdrd_rx_process
+ * overlaps the host copies with the kernels that way): slice i > 0 finds its history in place, right in
+ * front of it; only the first restores it and only the last saves it.  Every slice but the last must be a
+ * multiple of 2^log2_decim samples. */
+static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_bits, rt::stream_t st, size_t in_off = 0,
+                   bool first = true, bool last = true)
 {
-    if (n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    if (in_off + n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
     const int L = d->log2_decim;
     unsigned ss = sample_bits ? *sample_bits : 16u;
     if (ss < 1 || ss > 16) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
     size_t n_out = 0;
     size_t consumed_now = 0;
-    const uint32_t* in0 = d->d_in + HISTW;
+    const uint32_t* in0 = d->d_in + HISTW + in_off;
+    uint32_t* out0 = d->d_out + (in_off >> L);
 
     /* history of the previous calls in front of the new samples */
-    SDRD_TRY(rt::copy2d(d->d_in, d->in_pitch * 4, d->d_hist, HISTW * 4, HISTW * 4, (size_t)d->S, rt::D2D, st),
-             "restore history");
+    if (first)
+        SDRD_TRY(rt::copy2d(d->d_in, d->in_pitch * 4, d->d_hist, HISTW * 4, HISTW * 4, (size_t)d->S, rt::D2D, st),
+                 "restore history");
 
     if (L == 0) {
         /* Downsampler.cpp:76-80: copy, then decimate1's left-justification for < 16-bit sources */
@@ -293,7 +300,7 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
         if (n_in) {
             hb::PlainParams p{};
             p.in = in0; p.in_stride = (long long)d->in_pitch;
-            p.out = d->d_out; p.out_stride = (long long)d->out_pitch;
+            p.out = out0; p.out_stride = (long long)d->out_pitch;
             p.n_units = (long long)n_in; p.mode = 0;
             p.norm_shift = ss < 16 ? (int)(16 - ss) : 0;
             const int gx = (int)std::min<size_t>((n_in + 255) / 256, (size_t)d->sms * 8);
@@ -307,7 +314,7 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
         shift_rule(ss, L, &norm, &trunk, &ss_out);
         hb::PlainParams p{};
         p.in = in0; p.in_stride = (long long)d->in_pitch;
-        p.out = d->d_out; p.out_stride = (long long)d->out_pitch;
+        p.out = out0; p.out_stride = (long long)d->out_pitch;
         p.supra = d->fcpos == SDRD_FC_SUPRA;
         p.norm_shift = norm; p.trunk_shift = trunk;
         const size_t quads = n_in / 4;
@@ -338,7 +345,7 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
         if (n_out) {
             hb::Params p{};
             p.in = in0; p.in_stride = (long long)d->in_pitch;
-            p.out = d->d_out; p.out_stride = (long long)d->out_pitch;
+            p.out = out0; p.out_stride = (long long)d->out_pitch;
             p.n_out = (long long)n_out;
             p.round_add = d->variant == SDRD_HB_DB ? 1 : 0;
             p.norm_shift = norm; p.trunk_shift = trunk;
@@ -378,9 +385,10 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
     if (!SDRD_LAUNCH_OK()) return fail_cuda("kernel launch");
 
     /* the last HISTW consumed samples become the next call's history */
-    SDRD_TRY(rt::copy2d(d->d_hist, HISTW * 4, d->d_in + consumed_now, d->in_pitch * 4, HISTW * 4, (size_t)d->S, rt::D2D,
-                        st),
-             "save history");
+    if (last)
+        SDRD_TRY(rt::copy2d(d->d_hist, HISTW * 4, d->d_in + in_off + consumed_now, d->in_pitch * 4, HISTW * 4, (size_t)d->S,
+                            rt::D2D, st),
+                 "save history");
     d->consumed += (long long)consumed_now;
     if (d->consumed > (1LL << 50)) d->consumed = 1LL << 50;
     if (n_out_p) *n_out_p = n_out;
@@ -820,6 +828,8 @@ extern "C" long long sdrd_sink_launches(const sdrd_sink* k) { return k ? k->laun
 struct sdrd_rx {
     sdrd_dec* dec = nullptr;
     sdrd_sink* sink = nullptr;
+    rt::stream_t copy_stream = 0;   /* host -> device copies of sdrd_rx_process, ahead of the kernels */
+    rt::event_t copied[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int variant, int n_streams, size_t max_in)
@@ -830,6 +840,9 @@ extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int vari
     if (!r) return fail(SDRD_ENOMEM, "out of host memory");
     int rc = sdrd_dec_create(&r->dec, log2_decim, fcpos, variant, n_streams, max_in);
     if (!rc) rc = sdrd_sink_create(&r->sink, n_streams, max_in);
+    if (!rc && rt::stream_create(&r->copy_stream) != 0) rc = fail_cuda("creating the copy stream");
+    for (int i = 0; i < 8 && !rc; i++)
+        if (rt::event_create(&r->copied[i]) != 0) rc = fail_cuda("creating events");
     if (rc) {
         sdrd_rx_destroy(r);
         return rc;
@@ -840,8 +853,11 @@ extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int vari
 extern "C" void sdrd_rx_destroy(sdrd_rx* r)
 {
     if (!r) return;
+    if (r->copy_stream) rt::sync(r->copy_stream);
     sdrd_dec_destroy(r->dec);
     sdrd_sink_destroy(r->sink);
+    for (int i = 0; i < 8; i++) rt::event_destroy(r->copied[i]);
+    rt::stream_destroy(r->copy_stream);
     delete r;
 }
 extern "C" int sdrd_rx_reset(sdrd_rx* r)
@@ -878,13 +894,49 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
     sdrd_dec* d = r->dec;
     if (n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
     rt::stream_t st = d->stream;
-    SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, rt::H2D, st),
-             "copy samples to device");
-    size_t n_out = 0, n_frames = 0;
-    unsigned ss = 16;
-    if (int rc = dec_run(d, n_in, &n_out, &ss, st)) return rc;
-    if (int rc = sink_run(r->sink, d->d_out, d->out_pitch, n_out, &n_frames, st)) return rc;
-    if (int rc = sink_fetch(r->sink, datagrams, frame_capacity, n_frames, st)) return rc;
+    /* Large calls go through in slices: the copy of slice i + 1 (copy stream) runs while slice i is being
+     * decimated, framed, encoded and its datagrams copied back (compute stream), so the call costs little
+     * more than its host -> device copy. */
+    const int L = d->log2_decim;
+    int n_slices = 1;
+    /* SDRD_RX_SLICE_BYTES: tests lower the threshold to exercise the sliced path on small inputs */
+    const char* thr_env = getenv("SDRD_RX_SLICE_BYTES");
+    const size_t slice_threshold = thr_env ? (size_t)strtoull(thr_env, nullptr, 10) : ((size_t)32 << 20);
+    if ((size_t)d->S * n_in * 4 >= slice_threshold) n_slices = 8;
+    size_t slice = n_in / (size_t)n_slices;
+    slice -= slice % (((size_t)1 << L) * 4); /* whole decimation groups, 16-byte aligned */
+    if (slice == 0) n_slices = 1;
+    size_t n_frames = 0;
+    const size_t frame_bytes = (size_t)(128 + r->sink->nb_fec) * SDRD_UDPSIZE;
+    for (int i = 0; i < n_slices; i++) {
+        const size_t off = (size_t)i * slice;
+        const size_t len = i == n_slices - 1 ? n_in - off : slice;
+        if (n_slices > 1) {
+            SDRD_TRY(rt::copy2d(d->d_in + HISTW + off, d->in_pitch * 4, iq_in + 2 * off, in_stride * 4, len * 4, (size_t)d->S,
+                                rt::H2D, r->copy_stream),
+                     "copy samples to device");
+            SDRD_TRY(rt::event_record(r->copied[i], r->copy_stream), "record copy event");
+        } else {
+            SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, rt::H2D, st),
+                     "copy samples to device");
+        }
+    }
+    for (int i = 0; i < n_slices; i++) {
+        const size_t off = (size_t)i * slice;
+        const size_t len = i == n_slices - 1 ? n_in - off : slice;
+        if (n_slices > 1) SDRD_TRY(rt::stream_wait(st, r->copied[i]), "wait for copy");
+        size_t n_out = 0, nf = 0;
+        unsigned ss = 16;
+        if (int rc = dec_run(d, len, &n_out, &ss, st, off, i == 0, i == n_slices - 1)) return rc;
+        if (int rc = sink_run(r->sink, d->d_out + (off >> L), d->out_pitch, n_out, &nf, st)) return rc;
+        if (nf) {
+            if (n_frames + nf > frame_capacity) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of completed frames");
+            SDRD_TRY(rt::copy2d(datagrams + n_frames * frame_bytes, frame_capacity * frame_bytes, r->sink->d_dgrams,
+                                r->sink->last_dgram_stride * 4, nf * frame_bytes, (size_t)d->S, rt::D2H, st),
+                     "copy datagrams to host");
+        }
+        n_frames += nf;
+    }
     SDRD_TRY(rt::sync(st), "rx process");
     if (n_frames_p) *n_frames_p = n_frames;
     return 0;

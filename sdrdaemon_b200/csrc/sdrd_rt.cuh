@@ -41,6 +41,11 @@ inline int copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t
 inline int sync(stream_t) { return 0; }
 inline int stream_create(stream_t* s) { *s = nullptr; return 0; }
 inline void stream_destroy(stream_t) {}
+typedef void* event_t;
+inline int event_create(event_t* e) { *e = nullptr; return 0; }
+inline void event_destroy(event_t) {}
+inline int event_record(event_t, stream_t) { return 0; }
+inline int stream_wait(stream_t, event_t) { return 0; }
 inline const char* last_error() { return "emu"; }
 
 #define SDRD_LAUNCH(kernel, gx, gy, nthreads, smem, stream, params)                                            \
@@ -127,6 +132,11 @@ inline int copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t
 inline int sync(stream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
 inline int stream_create(stream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : -1; }
 inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
+typedef cudaEvent_t event_t;
+inline int event_create(event_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess ? 0 : -1; }
+inline void event_destroy(event_t e) { if (e) cudaEventDestroy(e); }
+inline int event_record(event_t e, stream_t s) { return cudaEventRecord(e, s) == cudaSuccess ? 0 : -1; }
+inline int stream_wait(stream_t s, event_t e) { return cudaStreamWaitEvent(s, e, 0) == cudaSuccess ? 0 : -1; }
 
 #define SDRD_LAUNCH(kernel, gx, gy, nthreads, smem, stream, params)                                       \
     do {                                                                                                  \

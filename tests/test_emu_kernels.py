@@ -114,6 +114,12 @@ def test_golden_through_emulation(emu_lib):
     golden_cases.check_fecbuffer_golden(lambda sb: capi.fec_decode(sb[None], [len(sb)], lib=emu_lib)[0][0])
 
 
+def test_rx_pipeline_sliced(emu_lib, oracle, monkeypatch):
+    """sdrd_rx_process in 8 overlapped slices (what large calls do) gives the same datagrams"""
+    monkeypatch.setenv("SDRD_RX_SLICE_BYTES", "1")
+    test_rx_pipeline(emu_lib, oracle)
+
+
 def test_rx_pipeline(emu_lib, oracle):
     from sdrdaemon_b200 import capi
 

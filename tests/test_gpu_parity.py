@@ -222,6 +222,24 @@ def test_receiver_batched(gpu_lib, oracle):
         assert cases.check_receiver(gpu_lib, oracle, dg, [0, 3, 3, 129, 500, 501, 1200, n]) >= 13
 
 
+def test_rx_pipeline_sliced(gpu_lib, oracle, monkeypatch):
+    """the overlapped (sliced) form of sdrd_rx_process, forced on a small input, DB variant, 3 streams"""
+    from sdrdaemon_b200 import capi
+
+    monkeypatch.setenv("SDRD_RX_SLICE_BYTES", "1")
+    rng = np.random.default_rng(710)
+    M, F, S = 3, 8, 3
+    n = (2 * cases.FRAME + 1234) << M
+    x = cases.rand_iq(rng, (S, 2 * n))
+    rx = capi.Rx(M, n_streams=S, max_in=n, n_fec=F, variant=1, lib=gpu_lib)
+    got = np.concatenate([rx.process(x[:, :n]), rx.process(x[:, n:])], axis=1)
+    for s in range(S):
+        y, _ = oracle.Decimator(M, 2, 1).process(x[s])
+        sk = oracle.Sink(n_fec=F)
+        sk.write(y)
+        assert np.array_equal(got[s], np.stack(sk.frames))
+
+
 def test_rx_pipeline_config2(gpu_lib, oracle):
     """config 2 end to end through sdrd_rx_process: decimate-by-16 + 128+16 FEC, ragged call sizes."""
     from sdrdaemon_b200 import capi
