@@ -34,8 +34,9 @@
  *     a 16-output task needs 4): shared-memory bandwidth (128 B/clk/SM) is the second limit of this
  *     kernel right behind instruction issue, see DESIGN.md.  The window streams through registers in
  *     four groups of 8 outputs (fir32_stream);
- *   - regions are padded 32 -> 36 words and placed at chosen residues mod 32 words so that the eight
- *     lanes of every quarter-warp hit eight different 16-byte bank groups on every LDS.128 / STS.128;
+ *   - regions are padded 32 -> 36 words and laid out in an order that puts their start residues mod 32
+ *     words where the eight lanes of every quarter-warp hit eight different 16-byte bank groups on every
+ *     LDS.128 / STS.128, with no padding between regions (wregion_unit_off);
  *   - the last stage leaves int32 results in a small staging area that the next step packs to int16
  *     pairs, one output per lane, coalesced.
  *
@@ -106,27 +107,22 @@ SDRD_HD constexpr int wphys(int k) { return k + 4 * (k >> 5); }
  * component: 32 history + what one consumer step reads as new (m >= 4: two producer steps' worth) */
 SDRD_HD constexpr int wregion_entries(int m) { return m <= 3 ? 32 + (256 >> m) : 64; }
 SDRD_HD constexpr int wregion_words(int m) { return wregion_entries(m) / 32 * BLK; }
-/* start of a region modulo 32 words (a multiple of 4 words = one 16-byte bank group), chosen so that
- * the mixed quarter-warps 16-23 (stage 2: 4 I + 4 Q tasks) and 24-31 (stages 3..6) are conflict free
- * both when they load their windows and when they store their results */
-SDRD_HD constexpr int wresidue(int m, int comp)
+/* Placement of the regions.  All E regions, then all O regions, each set in the order
+ *   m1.I  m2.Q  m0.I  m0.Q  m3.I  m1.Q  m3.Q  m2.I  (m4.I  m4.Q  m5.I  m5.Q)
+ * which makes the start residues modulo 32 words (8 bank groups of 16 bytes) come out right WITHOUT any
+ * padding between the first eight: the mixed quarter-warps 16-23 (stage 2: tasks I0-3, Q0-3) and 24-31
+ * (stages 3..6) then hit eight different bank groups both when they load their windows and when they
+ * store their results (m1: Q - I = 4 groups; m2: Q - I = 2; lanes 24-31 read groups {3,4},{5,6},2,1,0,7).
+ * Found by exhaustive search over the 8! orders; offsets in units of 16 bytes. */
+SDRD_HD constexpr int wregion_unit_off(int m, int comp)
 {
-    return 4 * (m == 0 ? 0 : m == 1 ? (comp ? 4 : 0) : m == 2 ? (comp ? 2 : 0) : m == 3 ? (comp ? 5 : 4) : (comp ? 7 : 6));
+    return m == 0 ? (comp ? 153 : 72) : m == 1 ? (comp ? 252 : 0) : m == 2 ? (comp ? 45 : 315) : m == 3 ? (comp ? 297 : 234)
+         : m == 4 ? (comp ? 367 : 344) : (comp ? 415 : 392);
 }
-/* word offset of region (m, parity, comp) from the start of the plane area; m = 6 gives the total */
-SDRD_HD constexpr int wplane_off(int m, int parity, int comp)
-{
-    int off = 0;
-    for (int mm = 0; mm < 6; mm++)
-        for (int pp = 0; pp < 2; pp++)
-            for (int cc = 0; cc < 2; cc++) {
-                const int r = wresidue(mm, cc);
-                off += ((r - off) % 32 + 32) % 32;
-                if (mm == m && pp == parity && cc == comp) return off;
-                off += wregion_words(mm);
-            }
-    return off;
-}
+SDRD_HD constexpr int wset_units(int M) { return M <= 4 ? 342 : M == 5 ? 385 : 433; } /* one parity's regions */
+/* word offset of region (m, parity, comp) from the start of the plane area, for an M-stage cascade */
+SDRD_HD constexpr int wplane_off(int M, int m, int parity, int comp) { return 4 * (parity * wset_units(M) + wregion_unit_off(m, comp)); }
+SDRD_HD constexpr int wplanes_words(int M) { return 8 * wset_units(M); }
 SDRD_HD constexpr int wfin_n(int M) { return (WC0 >> M) > 32 ? (WC0 >> M) : 32; } /* outputs per pack event */
 SDRD_HD constexpr int wfin_stride(int M) { return wfin_n(M) + 4; }                  /* words between the I and Q results */
 SDRD_HD constexpr int wmacro(int M) { return M <= 4 ? 1 : 1 << (M - 4); }           /* steps per pack event */
@@ -136,7 +132,7 @@ SDRD_HD constexpr int wraw_words(int PRO) { return PRO ? 4 * WC0 : WC0; }
 /* raw chunk | mbarrier | regions of stages 0..M-1 | 8 words | last stage's results */
 SDRD_HD constexpr size_t wsmem_bytes(int M, int PRO)
 {
-    return (size_t)wraw_words(PRO) * 4 + 128 + (size_t)(wplane_off(M, 0, 0) + 40) * 4 + (size_t)2 * wfin_stride(M) * 4;
+    return (size_t)wraw_words(PRO) * 4 + 128 + (size_t)(wplanes_words(M) + 8) * 4 + (size_t)2 * wfin_stride(M) * 4;
 }
 /* warm-up chunks in front of a segment: >= 61 * (2^M - 1) samples, whole pack events */
 SDRD_HD constexpr int wwarm_chunks(int M)
@@ -227,7 +223,7 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
     uint32_t* raw = reinterpret_cast<uint32_t*>(smem);
     mbar_t* bars = reinterpret_cast<mbar_t*>(smem + (size_t)RAWW * 4);
     int* planes = reinterpret_cast<int*>(smem + (size_t)RAWW * 4 + 128);
-    int* fin = planes + wplane_off(M, 0, 0) + 8; /* residue 8 words: the last stage's stores miss the others' banks */
+    int* fin = planes + wplanes_words(M) + 8;
 
     const long long seg_first_out = (long long)seg * p.seg_out;
     long long seg_n_out = p.n_out - seg_first_out;
@@ -254,20 +250,20 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
     const bool has_task = tm < M;
     const bool sub_rate = lane >= 30; /* only meaningful when M >= 5 */
     if (!has_task) tm = 0;
-    const int* srcE = planes + wplane_off(tm, 0, tcomp) + BLK * ti;
-    const int* srcO = planes + wplane_off(tm, 1, tcomp) + BLK * ti;
+    const int* srcE = planes + wplane_off(M, tm, 0, tcomp) + BLK * ti;
+    const int* srcO = planes + wplane_off(M, tm, 1, tcomp) + BLK * ti;
     int* dstE;
     int* dstO;
     if (tm + 1 < M) {
-        dstE = planes + wplane_off(tm + 1, 0, tcomp) + wphys(32 + 16 * ti);
-        dstO = planes + wplane_off(tm + 1, 1, tcomp) + wphys(32 + 16 * ti);
+        dstE = planes + wplane_off(M, tm + 1, 0, tcomp) + wphys(32 + 16 * ti);
+        dstO = planes + wplane_off(M, tm + 1, 1, tcomp) + wphys(32 + 16 * ti);
     } else {
         dstE = fin + tcomp * FS + 16 * ti;
         dstO = dstE + FN / 2;
     }
     /* M = 6: lanes 30/31 alternate between stage 5 (regions 4 -> 5) and stage 6 (regions 5 -> fin) */
-    const int* srcE_b = planes + wplane_off(M == 6 ? 5 : 0, 0, tcomp);
-    const int* srcO_b = planes + wplane_off(M == 6 ? 5 : 0, 1, tcomp);
+    const int* srcE_b = planes + wplane_off(M, M == 6 ? 5 : 0, 0, tcomp);
+    const int* srcO_b = planes + wplane_off(M, M == 6 ? 5 : 0, 1, tcomp);
     int* dstE_b = fin + tcomp * FS;
     int* dstO_b = dstE_b + FN / 2;
     /* producers of regions 4 and 5 fill them in two halves of 16 entries */
@@ -288,7 +284,7 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
         const int parity = rr < 8 ? 1 : 0;
         const int unit = parity ? rr : 4 + (rr - 8);
         tl_back[k] = (wregion_entries(m) - 32) / 32 * BLK;
-        tl_src[k] = planes + wplane_off(m, parity, comp) + 4 * unit + tl_back[k];
+        tl_src[k] = planes + wplane_off(M, m, parity, comp) + 4 * unit + tl_back[k];
         tl_m[k] = on ? m : -1;
     }
 
@@ -296,7 +292,7 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
      *      4 (32 k + q) .. + 3 -> entries 64 k + 2 q, + 1 of the four stage-0 regions.
      *      (/4 prologue: lane q turns raw unit 32 k + q, k = 0..15, into cascade input 32 k + q) ---- */
     int* const up = planes + (PRO ? wphys(32 + (lane >> 1)) : wphys(32 + 2 * lane));
-    constexpr int UP_EI = wplane_off(0, 0, 0), UP_EQ = wplane_off(0, 0, 1), UP_OI = wplane_off(0, 1, 0), UP_OQ = wplane_off(0, 1, 1);
+    constexpr int UP_EI = wplane_off(M, 0, 0, 0), UP_EQ = wplane_off(M, 0, 0, 1), UP_OI = wplane_off(M, 0, 1, 0), UP_OQ = wplane_off(M, 0, 1, 1);
 
     /* ---- pack: lane l packs outputs OPL*l .. OPL*l+OPL-1 of an event; output r of a component sits at
      *      fin[r even ? r/2 : FN/2 + r/2] ---- */
