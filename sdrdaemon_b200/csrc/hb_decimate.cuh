@@ -70,13 +70,15 @@ struct Params {
 };
 
 /* Pipe steering.  The FIR body is issue-bound: per output and component 16 pre-adds + 16
- * multiply-accumulates.  Left alone, ptxas turns about half of the pre-adds into IMAD.IADD, which
- * piles them onto the FMA pipe next to the IMADs (measured: fmaheavy 66 % busy, ALU 39 %, long
- * same-pipe runs).  `Steer` carries run-time constants the compiler cannot fold:
+ * multiply-accumulates, on two pipes that each take one warp instruction every 2 clocks.  Left alone,
+ * ptxas turns about half of the pre-adds into IMAD.IADD, which piles them onto the FMA pipe next to the
+ * IMADs.  `Steer` carries run-time constants the compiler cannot fold:
  *   zero   added as the THIRD operand of a pre-add  -> IADD3 with three sources, ALU pipe only;
- *   one    multiplier of an add written as IMAD      -> FMA pipe;
- *   k32, k256, k8192  multipliers of the power-of-two taps / centre tap -> IMAD instead of LEA.
- * Which taps use which form is fixed below so that ALU and FMA work per output are equal. */
+ *   one    multiplier of an add written as IMAD      -> FMA pipe (SDRD_HB_FMA_ADD_TAPS taps per output);
+ *   k32, k256, k8192  multipliers of the power-of-two taps / centre tap -> IMAD instead of a shift-add
+ *          (SDRD_HB_POW2_IMAD; off: measured on the warp-private kernel, FMA is the busier pipe there).
+ * Measured (config 2, K1 ms): FMA_ADD_TAPS 0/1/2/3 = 0.422/0.416/0.425/0.430 with POW2_IMAD = 0;
+ * POW2_IMAD 7 -> 0.422. */
 struct Steer {
     uint32_t zero, one, k32, k256, k8192;
 };
@@ -140,6 +142,9 @@ SDRD_HD constexpr int wwarm_chunks(int M)
     return ((61 * ((1 << M) - 1) + WC0 - 1) / WC0 + wmacro(M) - 1) / wmacro(M) * wmacro(M);
 }
 
+#ifndef SDRD_HB_POW2_IMAD
+#define SDRD_HB_POW2_IMAD 0 /* bit 0/1/2: tap 32 / tap 256 / centre tap multiply as IMAD with a run-time factor (FMA pipe) instead of a shift-add (ALU pipe) */
+#endif
 #ifndef SDRD_K1_WARPS_PER_SM
 #define SDRD_K1_WARPS_PER_SM 12 /* resident warps per SM the register budget is set for */
 #endif
@@ -182,7 +187,7 @@ SDRD_DEVICE void fir32_stream(const int* SDRD_RESTRICT srcE, const int* SDRD_RES
         }
 #pragma unroll
         for (int t = 0; t < 16; t++) {
-            const uint32_t h = H[t] == 32 ? st.k32 : (H[t] == 256 ? st.k256 : (uint32_t)H[t]);
+            const uint32_t h = (H[t] == 32 && (SDRD_HB_POW2_IMAD & 1)) ? st.k32 : ((H[t] == 256 && (SDRD_HB_POW2_IMAD & 2)) ? st.k256 : (uint32_t)H[t]);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 acc[j] = mad_lo(tmp[j], h, t == 0 ? acc0 : acc[j]);
@@ -195,7 +200,8 @@ SDRD_DEVICE void fir32_stream(const int* SDRD_RESTRICT srcE, const int* SDRD_RES
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) y[8 * g + j] = asr32(mad_lo(e[8 * g + 1 + j], st.k8192, acc[j]), HB_SHIFT);
+        for (int j = 0; j < 8; j++)
+            y[8 * g + j] = asr32((SDRD_HB_POW2_IMAD & 4) ? mad_lo(e[8 * g + 1 + j], st.k8192, acc[j]) : (e[8 * g + 1 + j] << HB_SHIFT) + acc[j], HB_SHIFT);
         if (DB && a0 + 8 * g < 0) {
             /* DB: the reference's stages start from all-zero state, but a DB stage maps zero input to 1;
              * outputs that lie before the stream origin must read as 0. */
