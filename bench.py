@@ -565,6 +565,8 @@ def main():
         if world == 1 and not args.no_cpu:
             cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             line["cpu_baseline"], _ = cpu_leg(10.0, cores)
+            one, _ = cpu_leg(3.0, 1)  # the single-thread figure next to the all-core one
+            line["cpu_baseline"]["one_core"] = one["value"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
