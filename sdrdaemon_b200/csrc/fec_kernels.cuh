@@ -516,14 +516,14 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
     uint32_t* b0 = p.block0 ? p.block0 + (long long)f * 127 : nullptr;
 
     /* originals that arrived go out as they are; blocks that did not arrive read as zero (.cpp:109) */
-    for (int k = tid; k < 128 * 127; k += NT) {
-        const int b = k / 127, i = k - b * 127;
+    for (int b = tid >> 5; b < 128; b += NT / 32) { /* one warp per block: four coalesced stores, no index division */
         const int row = origRow[b];
-        const uint32_t v = row >= 0 ? sm.img[row * ROW_WORDS + 1 + i] : 0u;
-        if (b == 0) {
-            if (b0) b0[i] = v;
-        } else if (row >= 0 || !do_decode) {
-            pay[(b - 1) * 127 + i] = v;
+        uint32_t* dstb = b == 0 ? b0 : pay + (b - 1) * 127;
+        if (!dstb || !(b == 0 || row >= 0 || !do_decode)) continue;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = (tid & 31) + 32 * q;
+            if (i < 127) dstb[i] = row >= 0 ? sm.img[row * ROW_WORDS + 1 + i] : 0u;
         }
     }
 
@@ -534,18 +534,18 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
             __syncthreads();
             matvec_pass(sm.img, sm.coefT, DCAP, row0, nrows, sm.tab, sm.rec16, tid);
             __syncthreads();
-            for (int k = tid; k < nrows * 127; k += NT) {
-                const int r = k / 127, i = k - r * 127;
+            for (int r = tid >> 5; r < nrows; r += NT / 32) {
                 const int b = erased[row0 + r];
                 /* The reference copies back only the LAST N descriptors (.cpp:208-213), i.e. it
                  * assumes the recovery blocks arrived after the originals; a recovery block that
                  * arrived earlier keeps its result to itself and the erased block stays zero. */
                 const bool copied = (int)recRowOf[row0 + r] >= 128 - N;
-                const uint32_t v = copied ? sm.rec16[r * ROW_WORDS + 1 + i] : 0u;
-                if (b == 0) {
-                    if (b0) b0[i] = v;
-                } else {
-                    pay[(b - 1) * 127 + i] = v;
+                uint32_t* dstb = b == 0 ? b0 : pay + (b - 1) * 127;
+                if (!dstb) continue;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = (tid & 31) + 32 * q;
+                    if (i < 127) dstb[i] = copied ? sm.rec16[r * ROW_WORDS + 1 + i] : 0u;
                 }
             }
             __syncthreads();
