@@ -61,7 +61,7 @@ struct Params {
     long long out_stride;  /* words */
     long long n_out;       /* outputs per stream */
     int seg_out;           /* outputs per segment, multiple of C0 >> M */
-    int warm_chunks;       /* chunks processed ahead of every segment: warm_chunks * C0 >= 61 * (2^M - 1) */
+    int warm_chunks;       /* informational: wwarm_chunks(M), the chunks processed ahead of every segment */
     int round_add;         /* 0: EO1, 1: DB */
     int norm_shift, trunk_shift;
     int prologue;          /* 0: centred; 1: infradyne /4; 2: supradyne /4 in front of the cascade */
