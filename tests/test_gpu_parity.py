@@ -80,6 +80,35 @@ def test_decimator_large_single_stream(gpu_lib, oracle):
     assert np.array_equal(y, yo)
 
 
+def test_full_bench_sizes_against_the_oracle(gpu_lib, oracle):
+    """BASELINE config 2 at bench.py's full size (592 superframes, 152.8 M input samples), every sample against
+    the oracle: decimate by 16 on the GPU, then the Tx cascade back up by 16 (152.8 M output samples)."""
+    from sdrdaemon_b200 import capi
+
+    rng = np.random.default_rng(3004)
+    n = 592 * cases.FRAME * 16
+    x = rng.integers(-32768, 32768, size=(n, 2), dtype=np.int16)
+    d = capi.Decimator(4, max_in=n, lib=gpu_lib)
+    y, _ = d.process(x)
+    d.close()
+    yo, _ = oracle.Decimator(4).process(x)
+    assert y.shape == yo.shape == (592 * cases.FRAME, 2) and np.array_equal(y, yo)
+    del x
+    # all 592 superframes, 128 + 16 datagrams each, against UDPSinkFEC::write + cm256_encode (oracle)
+    sk = capi.Sink(max_samples=len(y), n_fec=16, lib=gpu_lib)
+    dg = sk.write(y)
+    sk.close()
+    osk = oracle.Sink(n_fec=16)
+    osk.write(yo)
+    assert dg.shape == (592, 144, 512) and np.array_equal(dg, np.stack(osk.frames))
+    del dg, osk
+    u = capi.Interpolator(4, max_in=len(y), lib=gpu_lib)
+    z = u.process(y)
+    u.close()
+    zo = oracle.Interpolator(4).process(yo)
+    assert z.shape == (n, 2) and np.array_equal(z, zo)
+
+
 @pytest.mark.parametrize("M", [0, 1, 2, 3, 4, 5, 6])
 def test_interpolator(gpu_lib, oracle, M):
     rng = np.random.default_rng(900 + M)
