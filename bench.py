@@ -129,21 +129,28 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_leg(seconds: float, cores: int):
-    """The reference CPU path on a bounded sample of the workload: `cores` concurrent streams of whole
-    superframes (the reference runs one stream per thread; Decimators state is sequential)."""
+def cpu_sample(seconds: float, cores: int, rng):
+    """A bounded sample of the workload for the CPU arm: `cores` streams of whole superframes sized so that one
+    pass takes about `seconds`.  Returns (x, frames)."""
     from oracle import bindings as ob
 
-    rng = np.random.default_rng(1234)
     frames_cal = 2
     x = rng.integers(-32768, 32768, size=(cores, frames_cal * FRAME_IN, 2), dtype=np.int16)
     t0 = time.perf_counter()
-    fr, _, kind = ob.cpu_rx_streams(x, M_LOG2, N_FEC, cores)
+    ob.cpu_rx_streams(x, M_LOG2, N_FEC, cores)
     dt = time.perf_counter() - t0
     rate = x.shape[0] * x.shape[1] / dt
     frames = max(frames_cal, min(64, int(rate * seconds / (cores * FRAME_IN))))
     if frames != frames_cal:
         x = rng.integers(-32768, 32768, size=(cores, frames * FRAME_IN, 2), dtype=np.int16)
+    return x, frames
+
+
+def cpu_pass(x, frames: int, cores: int):
+    """One timed pass of the reference CPU path over the sample: `cores` concurrent streams (the reference runs
+    one stream per thread; Decimators state is sequential)."""
+    from oracle import bindings as ob
+
     t0 = time.perf_counter()
     fr, dig, kind = ob.cpu_rx_streams(x, M_LOG2, N_FEC, cores)
     dt = time.perf_counter() - t0
@@ -156,6 +163,11 @@ def cpu_leg(seconds: float, cores: int):
     return {"value": round(msps, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, dt
 
 
+def cpu_leg(seconds: float, cores: int):
+    x, frames = cpu_sample(seconds, cores, np.random.default_rng(1234))
+    return cpu_pass(x, frames, cores)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,19 +178,24 @@ def run_reference(args):
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    # each step: a bounded sample (~2 s of CPU work)
-    vals = []
+    # every step is one pass over the same bounded sample; the sample is sized so that the whole run
+    # (warm-up + steps) stays near one minute whatever --steps says
+    n_pass = max(args.warmup + args.steps, 1)
+    per_step = min(2.0, 60.0 / n_pass)
+    x, frames = cpu_sample(per_step, cores, np.random.default_rng(1234))
+    vals, times = [], []
     base = None
-    for i in range(args.warmup + args.steps):
-        base, dt = cpu_leg(2.0, cores)
+    for i in range(n_pass):
+        base, dt = cpu_pass(x, frames, cores)
         if i >= args.warmup:
             vals.append(base["value"])
+            times.append(dt)
     v = statistics.mean(vals)
     base["value"] = round(v, 3)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": round(1e3 * statistics.mean(times), 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config]["name"] + " (reference CPU path, bounded sample per step)",
                    "log2_decim": M_LOG2, "n_fec": N_FEC},
         "cpu_baseline": base,
