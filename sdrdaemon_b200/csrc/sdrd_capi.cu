@@ -363,7 +363,10 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
             const size_t smem = hb::wsmem_bytes(M, pro ? 1 : 0);
             long long resident = (long long)((227 * 1024) / (smem + 1024));
             if (resident > SDRD_K1_WARPS_PER_SM) resident = SDRD_K1_WARPS_PER_SM;
-            long long want = resident * d->sms / d->S;
+            /* SDRD_K1_WAVES_X4 (experiments): segments for this many quarter-waves of resident warps (default 4 = one wave) */
+            long long waves_x4 = 4;
+            if (const char* e = getenv("SDRD_K1_WAVES_X4")) waves_x4 = atoi(e) > 0 ? atoi(e) : 4;
+            long long want = resident * d->sms * waves_x4 / 4 / d->S;
             if (want < 1) want = 1;
             long long n_seg = want < n_seg_max ? want : n_seg_max;
             const long long seg_ev = (total_ev + n_seg - 1) / n_seg;
