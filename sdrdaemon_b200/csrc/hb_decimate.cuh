@@ -60,7 +60,9 @@ struct Params {
     uint32_t* out;         /* out[s * out_stride + n] */
     long long out_stride;  /* words */
     long long n_out;       /* outputs per stream */
-    int seg_out;           /* outputs per segment, multiple of C0 >> M */
+    long long ev_stream;   /* pack events (wfin_n(M) outputs each) per stream: ceil(n_out / wfin_n(M)) */
+    long long ev_total;    /* n_streams * ev_stream: the global event axis, stream after stream */
+    long long ev_warp;     /* events per warp: warp w takes global events [w * ev_warp, (w + 1) * ev_warp) */
     int warm_chunks;       /* informational: wwarm_chunks(M), the chunks processed ahead of every segment */
     int round_add;         /* 0: EO1, 1: DB */
     int norm_shift, trunk_shift;
@@ -224,25 +226,11 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
     constexpr int RAWW = wraw_words(PRO);
     SDRD_DYN_SMEM(smem);
     const int lane = (int)threadIdx.x;
-    const int seg = (int)blockIdx.x;
-    const int s = (int)blockIdx.y;
     uint32_t* raw = reinterpret_cast<uint32_t*>(smem);
     mbar_t* bars = reinterpret_cast<mbar_t*>(smem + (size_t)RAWW * 4);
     int* planes = reinterpret_cast<int*>(smem + (size_t)RAWW * 4 + 128);
     int* fin = planes + wplanes_words(M) + 8;
-
-    const long long seg_first_out = (long long)seg * p.seg_out;
-    long long seg_n_out = p.n_out - seg_first_out;
-    if (seg_n_out > p.seg_out) seg_n_out = p.seg_out;
     constexpr int warm_macro = wwarm_chunks(M) / MACRO;
-    const int n_macro = warm_macro + (int)((seg_n_out + FN - 1) / FN);
-    const int NC = n_macro * MACRO; /* chunks to unpack */
-    const int u_last = (n_macro - 1) * MACRO + DELAY;
-    const long long first_in = (seg_first_out << M) - (long long)wwarm_chunks(M) * WC0;
-    const uint32_t* src = p.in + (long long)s * p.in_stride + first_in * (PRO ? 4 : 1);
-    uint32_t* dst = p.out + (long long)s * p.out_stride + seg_first_out - (long long)warm_macro * FN;
-    const long long seg_room = p.n_out - seg_first_out + (long long)warm_macro * FN; /* valid: index < seg_room */
-    const long long abs0 = p.origin + first_in;
     constexpr uint32_t chunk_bytes = (uint32_t)RAWW * 4u;
     const Steer steer = {p.steer_zero, p.steer_one, p.steer_k32, p.steer_k256, p.steer_k8192};
 
@@ -307,154 +295,179 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
     if (lane == 0) {
         mbar_init(&bars[0], 1);
         mbar_fence_init();
-        if (NC > 0) {
-            mbar_arrive_expect_tx(&bars[0], chunk_bytes);
-            tma_load_1d(raw, src, chunk_bytes, &bars[0]);
-        }
     }
     SDRD_SYNCWARP();
 
-    for (int u = 0; u <= u_last; u++) {
-        /* ================= phase A: every read of the stage regions, and the arithmetic ================= */
-        bool task_on = has_task;
-        const int* sE = srcE;
-        const int* sO = srcO;
-        int* dE = dstE;
-        int* dO = dstO;
-        int c_first = u - 1 - tm; /* first chunk this task's outputs come from (DB origin test) */
-        int t_stage = tm + 1;
-        if (M >= 5) {
-            if (sub_rate) {
-                const bool run_a = (u & 1) == 0;           /* stage 5 */
-                const bool run_b = M == 6 && (u & 3) == 1; /* stage 6 */
-                task_on = run_a || run_b;
-                if (run_b) { sE = srcE_b; sO = srcO_b; dE = dstE_b; dO = dstO_b; c_first = u - 9; t_stage = 6; }
-                else { c_first = u - 6; }
-                if (dst_halves_5 && run_a && (((u >> 1) & 1) == 0)) { dE += 16; dO += 16; } /* pair (u-6)/2 odd */
-            }
-            if (dst_halves_4 && (u & 1)) { dE += 16; dO += 16; } /* chunk u-4 odd */
-        }
-        int4 tl_v[TSLOTS];
-        bool tl_on[TSLOTS];
-#pragma unroll
-        for (int k = 0; k < TSLOTS; k++) {
-            tl_on[k] = tl_m[k] >= 0 && (M <= 4 || tl_m[k] <= 3 || (tl_m[k] == 4 ? (u & 1) == 0 : (u & 3) == 1));
-            tl_v[k] = make_int4(0, 0, 0, 0);
-            if (tl_on[k]) tl_v[k] = *reinterpret_cast<const int4*>(tl_src[k]);
+    /* The warp's share of the global event axis (all streams laid end to end, so that the resident warps of
+     * the device get equally long shares whatever the number of streams).  A share that runs over the end of
+     * a stream continues at the start of the next one as a new piece with its own filter warm-up. */
+    long long g = (long long)blockIdx.x * p.ev_warp;
+    long long g_end = g + p.ev_warp;
+    if (g_end > p.ev_total) g_end = p.ev_total;
+    uint32_t tma_n = 0; /* chunks requested before this piece (mbarrier phase) */
+    while (g < g_end) {
+        const int s = (int)(g / p.ev_stream);
+        const long long e0 = g - (long long)s * p.ev_stream;
+        long long e1 = e0 + (g_end - g);
+        if (e1 > p.ev_stream) e1 = p.ev_stream;
+        g += e1 - e0;
+        const long long seg_first_out = e0 * FN;
+        const int n_macro = warm_macro + (int)(e1 - e0);
+        const int NC = n_macro * MACRO; /* chunks to unpack */
+        const int u_last = (n_macro - 1) * MACRO + DELAY;
+        const long long first_in = (seg_first_out << M) - (long long)wwarm_chunks(M) * WC0;
+        const uint32_t* src = p.in + (long long)s * p.in_stride + first_in * (PRO ? 4 : 1);
+        uint32_t* dst = p.out + (long long)s * p.out_stride + seg_first_out - (long long)warm_macro * FN;
+        const long long seg_room = p.n_out - seg_first_out + (long long)warm_macro * FN; /* valid: index < seg_room */
+        const long long abs0 = p.origin + first_in;
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars[0], chunk_bytes);
+            tma_load_1d(raw, src, chunk_bytes, &bars[0]);
         }
 
-        const int ev = u - DELAY; /* pack event e = ev / MACRO when ev is a non-negative multiple of MACRO */
-        const bool pack_now = ev >= warm_macro * MACRO && (MACRO == 1 || (ev & (MACRO - 1)) == 0);
-        int pki[OPL], pkq[OPL];
-#pragma unroll
-        for (int j = 0; j < OPL; j++) pki[j] = pkq[j] = 0;
-        if (pack_now) {
-            if (OPL == 1) {
-                pki[0] = pk[0];
-                pkq[0] = pk[FS];
-            } else {
-#pragma unroll
-                for (int j = 0; j < OPL; j++) { /* output OPL*l + j: even -> entry (OPL*l + j)/2, odd -> FN/2 + .. */
-                    const int idx = (j & 1) ? FN / 2 + (j >> 1) : (j >> 1);
-                    pki[j] = pk[idx];
-                    pkq[j] = pk[FS + idx];
+        for (int u = 0; u <= u_last; u++) {
+            /* ================= phase A: every read of the stage regions, and the arithmetic ================= */
+            bool task_on = has_task;
+            const int* sE = srcE;
+            const int* sO = srcO;
+            int* dE = dstE;
+            int* dO = dstO;
+            int c_first = u - 1 - tm; /* first chunk this task's outputs come from (DB origin test) */
+            int t_stage = tm + 1;
+            if (M >= 5) {
+                if (sub_rate) {
+                    const bool run_a = (u & 1) == 0;           /* stage 5 */
+                    const bool run_b = M == 6 && (u & 3) == 1; /* stage 6 */
+                    task_on = run_a || run_b;
+                    if (run_b) { sE = srcE_b; sO = srcO_b; dE = dstE_b; dO = dstO_b; c_first = u - 9; t_stage = 6; }
+                    else { c_first = u - 6; }
+                    if (dst_halves_5 && run_a && (((u >> 1) & 1) == 0)) { dE += 16; dO += 16; } /* pair (u-6)/2 odd */
                 }
+                if (dst_halves_4 && (u & 1)) { dE += 16; dO += 16; } /* chunk u-4 odd */
             }
-        }
-
-        /* the FIR task itself: loads and arithmetic, results stay in registers until the barrier */
-        int y[32];
-        if (task_on) {
-            const long long a0 = DB ? ((abs0 + (long long)c_first * WC0) >> t_stage) + 32 * ti : 0;
-            fir32_stream<DB>(sE, sO, steer, a0, y);
-        }
-        SDRD_SYNCWARP();
-
-        /* ================= phase B: every shared-memory write of the step =========
-         * (the raw chunk is written by the TMA only, so its loads may follow the barrier) */
-        const bool unpack_now = u < NC;
-        uint4 rw[4];
-        int2 x[16];
-        if (unpack_now) {
-            mbar_wait(&bars[0], (uint32_t)(u & 1));
-            const uint4* r4 = reinterpret_cast<const uint4*>(raw);
-            if (!PRO) {
+            int4 tl_v[TSLOTS];
+            bool tl_on[TSLOTS];
 #pragma unroll
-                for (int k = 0; k < 4; k++) rw[k] = r4[32 * k + lane];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 16; k++) x[k] = rot4(r4[32 * k + lane], p.prologue);
+            for (int k = 0; k < TSLOTS; k++) {
+                tl_on[k] = tl_m[k] >= 0 && (M <= 4 || tl_m[k] <= 3 || (tl_m[k] == 4 ? (u & 1) == 0 : (u & 3) == 1));
+                tl_v[k] = make_int4(0, 0, 0, 0);
+                if (tl_on[k]) tl_v[k] = *reinterpret_cast<const int4*>(tl_src[k]);
             }
-        }
-#pragma unroll
-        for (int k = 0; k < TSLOTS; k++)
-            if (tl_on[k]) *reinterpret_cast<int4*>(const_cast<int*>(tl_src[k]) - tl_back[k]) = tl_v[k];
 
-        if (pack_now) {
-            /* (y << norm_shift) >> trunk_shift truncated to 16 bits (Decimators.cpp:408-409, SDRDaemon.h:59) */
-            uint32_t o[OPL];
+            const int ev = u - DELAY; /* pack event e = ev / MACRO when ev is a non-negative multiple of MACRO */
+            const bool pack_now = ev >= warm_macro * MACRO && (MACRO == 1 || (ev & (MACRO - 1)) == 0);
+            int pki[OPL], pkq[OPL];
 #pragma unroll
-            for (int j = 0; j < OPL; j++) {
-                const uint32_t a = (uint32_t)asr32((uint32_t)pki[j] << p.norm_shift, p.trunk_shift);
-                const uint32_t b = (uint32_t)asr32((uint32_t)pkq[j] << p.norm_shift, p.trunk_shift);
-                o[j] = (a & 0xFFFFu) | (b << 16);
-            }
-            const long long n = (long long)(ev / MACRO) * FN + lane * OPL; /* relative to dst */
-            if (n + OPL <= seg_room) {
+            for (int j = 0; j < OPL; j++) pki[j] = pkq[j] = 0;
+            if (pack_now) {
                 if (OPL == 1) {
-                    dst[n] = o[0];
-                } else if (OPL == 2) {
-                    *reinterpret_cast<uint2*>(dst + n) = make_uint2(o[0], o[OPL - 1]);
+                    pki[0] = pk[0];
+                    pkq[0] = pk[FS];
                 } else {
 #pragma unroll
-                    for (int j = 0; j + 3 < OPL; j += 4)
-                        *reinterpret_cast<uint4*>(dst + n + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < OPL; j++)
-                    if (n + j < seg_room) dst[n + j] = o[j];
-            }
-        }
-
-        if (task_on) {
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                reinterpret_cast<int4*>(dE)[g] = make_int4(y[8 * g], y[8 * g + 2], y[8 * g + 4], y[8 * g + 6]);
-                reinterpret_cast<int4*>(dO)[g] = make_int4(y[8 * g + 1], y[8 * g + 3], y[8 * g + 5], y[8 * g + 7]);
-            }
-        }
-
-        if (unpack_now) {
-            if (!PRO) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) { /* entries 64 k + 2 q, + 1: two 32-entry blocks further per k */
-                    int* o = up + 2 * BLK * k;
-                    *reinterpret_cast<int2*>(o + UP_EI) = make_int2(s16lo(rw[k].x), s16lo(rw[k].z));
-                    *reinterpret_cast<int2*>(o + UP_EQ) = make_int2(s16hi(rw[k].x), s16hi(rw[k].z));
-                    *reinterpret_cast<int2*>(o + UP_OI) = make_int2(s16lo(rw[k].y), s16lo(rw[k].w));
-                    *reinterpret_cast<int2*>(o + UP_OQ) = make_int2(s16hi(rw[k].y), s16hi(rw[k].w));
-                }
-            } else {
-                /* cascade input 32 k + q: parity q & 1, entry 16 k + (q >> 1): half a block further per k */
-                int* oi = up + ((lane & 1) ? UP_OI : UP_EI);
-                int* oq = up + ((lane & 1) ? UP_OQ : UP_EQ);
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    oi[(k >> 1) * BLK + (k & 1) * 16] = x[k].x;
-                    oq[(k >> 1) * BLK + (k & 1) * 16] = x[k].y;
+                    for (int j = 0; j < OPL; j++) { /* output OPL*l + j: even -> entry (OPL*l + j)/2, odd -> FN/2 + .. */
+                        const int idx = (j & 1) ? FN / 2 + (j >> 1) : (j >> 1);
+                        pki[j] = pk[idx];
+                        pkq[j] = pk[FS + idx];
+                    }
                 }
             }
-        }
 
-        SDRD_SYNCWARP();
-        /* every lane has read chunk u out of the raw buffer: request chunk u + 1 into it; it has the whole
-         * arithmetic phase of the next step to arrive */
-        if (lane == 0 && u + 1 < NC) {
-            mbar_arrive_expect_tx(&bars[0], chunk_bytes);
-            tma_load_1d(raw, src + (size_t)(u + 1) * RAWW, chunk_bytes, &bars[0]);
+            /* the FIR task itself: loads and arithmetic, results stay in registers until the barrier */
+            int y[32];
+            if (task_on) {
+                const long long a0 = DB ? ((abs0 + (long long)c_first * WC0) >> t_stage) + 32 * ti : 0;
+                fir32_stream<DB>(sE, sO, steer, a0, y);
+            }
+            SDRD_SYNCWARP();
+
+            /* ================= phase B: every shared-memory write of the step =========
+             * (the raw chunk is written by the TMA only, so its loads may follow the barrier) */
+            const bool unpack_now = u < NC;
+            uint4 rw[4];
+            int2 x[16];
+            if (unpack_now) {
+                mbar_wait(&bars[0], (tma_n + (uint32_t)u) & 1u);
+                const uint4* r4 = reinterpret_cast<const uint4*>(raw);
+                if (!PRO) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) rw[k] = r4[32 * k + lane];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) x[k] = rot4(r4[32 * k + lane], p.prologue);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < TSLOTS; k++)
+                if (tl_on[k]) *reinterpret_cast<int4*>(const_cast<int*>(tl_src[k]) - tl_back[k]) = tl_v[k];
+
+            if (pack_now) {
+                /* (y << norm_shift) >> trunk_shift truncated to 16 bits (Decimators.cpp:408-409, SDRDaemon.h:59) */
+                uint32_t o[OPL];
+#pragma unroll
+                for (int j = 0; j < OPL; j++) {
+                    const uint32_t a = (uint32_t)asr32((uint32_t)pki[j] << p.norm_shift, p.trunk_shift);
+                    const uint32_t b = (uint32_t)asr32((uint32_t)pkq[j] << p.norm_shift, p.trunk_shift);
+                    o[j] = (a & 0xFFFFu) | (b << 16);
+                }
+                const long long n = (long long)(ev / MACRO) * FN + lane * OPL; /* relative to dst */
+                if (n + OPL <= seg_room) {
+                    if (OPL == 1) {
+                        dst[n] = o[0];
+                    } else if (OPL == 2) {
+                        *reinterpret_cast<uint2*>(dst + n) = make_uint2(o[0], o[OPL - 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j + 3 < OPL; j += 4)
+                            *reinterpret_cast<uint4*>(dst + n + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < OPL; j++)
+                        if (n + j < seg_room) dst[n + j] = o[j];
+                }
+            }
+
+            if (task_on) {
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    reinterpret_cast<int4*>(dE)[g] = make_int4(y[8 * g], y[8 * g + 2], y[8 * g + 4], y[8 * g + 6]);
+                    reinterpret_cast<int4*>(dO)[g] = make_int4(y[8 * g + 1], y[8 * g + 3], y[8 * g + 5], y[8 * g + 7]);
+                }
+            }
+
+            if (unpack_now) {
+                if (!PRO) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { /* entries 64 k + 2 q, + 1: two 32-entry blocks further per k */
+                        int* o = up + 2 * BLK * k;
+                        *reinterpret_cast<int2*>(o + UP_EI) = make_int2(s16lo(rw[k].x), s16lo(rw[k].z));
+                        *reinterpret_cast<int2*>(o + UP_EQ) = make_int2(s16hi(rw[k].x), s16hi(rw[k].z));
+                        *reinterpret_cast<int2*>(o + UP_OI) = make_int2(s16lo(rw[k].y), s16lo(rw[k].w));
+                        *reinterpret_cast<int2*>(o + UP_OQ) = make_int2(s16hi(rw[k].y), s16hi(rw[k].w));
+                    }
+                } else {
+                    /* cascade input 32 k + q: parity q & 1, entry 16 k + (q >> 1): half a block further per k */
+                    int* oi = up + ((lane & 1) ? UP_OI : UP_EI);
+                    int* oq = up + ((lane & 1) ? UP_OQ : UP_EQ);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        oi[(k >> 1) * BLK + (k & 1) * 16] = x[k].x;
+                        oq[(k >> 1) * BLK + (k & 1) * 16] = x[k].y;
+                    }
+                }
+            }
+
+            SDRD_SYNCWARP();
+            /* every lane has read chunk u out of the raw buffer: request chunk u + 1 into it; it has the whole
+             * arithmetic phase of the next step to arrive */
+            if (lane == 0 && u + 1 < NC) {
+                mbar_arrive_expect_tx(&bars[0], chunk_bytes);
+                tma_load_1d(raw, src + (size_t)(u + 1) * RAWW, chunk_bytes, &bars[0]);
+            }
         }
-    }
+        tma_n += (uint32_t)NC;
+    } /* pieces */
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -142,20 +142,20 @@ int enc_grid(long long items)
 }
 
 template <int M, int PRO>
-void launch_decimate_warp2(const hb::Params& p, int n_seg, int S, rt::stream_t st)
+void launch_decimate_warp2(const hb::Params& p, int n_seg, rt::stream_t st)
 {
     if (p.round_add)
-        SDRD_LAUNCH((hb::decimate_warp_kernel<M, 1, PRO>), n_seg, S, 32, hb::wsmem_bytes(M, PRO), st, p);
+        SDRD_LAUNCH((hb::decimate_warp_kernel<M, 1, PRO>), n_seg, 1, 32, hb::wsmem_bytes(M, PRO), st, p);
     else
-        SDRD_LAUNCH((hb::decimate_warp_kernel<M, 0, PRO>), n_seg, S, 32, hb::wsmem_bytes(M, PRO), st, p);
+        SDRD_LAUNCH((hb::decimate_warp_kernel<M, 0, PRO>), n_seg, 1, 32, hb::wsmem_bytes(M, PRO), st, p);
 }
 template <int M>
-void launch_decimate_warp(const hb::Params& p, int n_seg, int S, rt::stream_t st)
+void launch_decimate_warp(const hb::Params& p, int n_seg, rt::stream_t st)
 {
     if constexpr (M <= 4) { /* the /4 prologue leaves at most 4 half-band stages */
-        if (p.prologue) return launch_decimate_warp2<M, 1>(p, n_seg, S, st);
+        if (p.prologue) return launch_decimate_warp2<M, 1>(p, n_seg, st);
     }
-    launch_decimate_warp2<M, 0>(p, n_seg, S, st);
+    launch_decimate_warp2<M, 0>(p, n_seg, st);
 }
 
 } /* namespace */
@@ -352,34 +352,37 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
             p.prologue = pro;
             p.origin = d->consumed / (pro ? 4 : 1);
             p.steer_zero = 0; p.steer_one = 1; p.steer_k32 = 32; p.steer_k256 = 256; p.steer_k8192 = 8192;
-            /* one warp per segment, segments sized for ONE wave of resident warps
-             * (all segments are equally long, so there is no tail), but never so short that the
-             * warm-up costs more than ~1/8 of a segment */
+            /* One warp per share of the global event axis (the streams laid end to end), shares sized for ONE
+             * wave of resident warps whatever the number of streams -- equally long, so there is no tail --
+             * but never so short that the filter warm-up costs more than ~1/8 of a share (short streams: one
+             * warp per stream). */
             const int FN = hb::wfin_n(M);
-            const long long total_ev = ((long long)n_out + FN - 1) / FN;
+            const long long ev_stream = ((long long)n_out + FN - 1) / FN;
+            const long long ev_total = ev_stream * d->S;
             const long long warm_ev = hb::wwarm_chunks(M) / hb::wmacro(M);
-            long long n_seg_max = total_ev / (8 * warm_ev);
-            if (n_seg_max < 1) n_seg_max = 1;
             const size_t smem = hb::wsmem_bytes(M, pro ? 1 : 0);
             long long resident = (long long)((227 * 1024) / (smem + 1024));
             if (resident > SDRD_K1_WARPS_PER_SM) resident = SDRD_K1_WARPS_PER_SM;
-            /* SDRD_K1_WAVES_X4 (experiments): segments for this many quarter-waves of resident warps (default 4 = one wave) */
+            /* SDRD_K1_WAVES_X4 (experiments): shares for this many quarter-waves of resident warps (default 4 = one wave) */
             long long waves_x4 = 4;
             if (const char* e = getenv("SDRD_K1_WAVES_X4")) waves_x4 = atoi(e) > 0 ? atoi(e) : 4;
-            long long want = resident * d->sms * waves_x4 / 4 / d->S;
+            long long want = resident * d->sms * waves_x4 / 4;
             if (want < 1) want = 1;
-            long long n_seg = want < n_seg_max ? want : n_seg_max;
-            const long long seg_ev = (total_ev + n_seg - 1) / n_seg;
-            n_seg = (total_ev + seg_ev - 1) / seg_ev;
-            p.seg_out = (int)(seg_ev * FN);
+            long long ev_warp = (ev_total + want - 1) / want;
+            const long long ev_min = std::min<long long>(8 * warm_ev, ev_stream);
+            if (ev_warp < ev_min) ev_warp = ev_min;
+            const long long n_seg = (ev_total + ev_warp - 1) / ev_warp;
+            p.ev_stream = ev_stream;
+            p.ev_total = ev_total;
+            p.ev_warp = ev_warp;
             p.warm_chunks = hb::wwarm_chunks(M);
             switch (M) {
-                case 1: launch_decimate_warp<1>(p, (int)n_seg, d->S, st); break;
-                case 2: launch_decimate_warp<2>(p, (int)n_seg, d->S, st); break;
-                case 3: launch_decimate_warp<3>(p, (int)n_seg, d->S, st); break;
-                case 4: launch_decimate_warp<4>(p, (int)n_seg, d->S, st); break;
-                case 5: launch_decimate_warp<5>(p, (int)n_seg, d->S, st); break;
-                default: launch_decimate_warp<6>(p, (int)n_seg, d->S, st); break;
+                case 1: launch_decimate_warp<1>(p, (int)n_seg, st); break;
+                case 2: launch_decimate_warp<2>(p, (int)n_seg, st); break;
+                case 3: launch_decimate_warp<3>(p, (int)n_seg, st); break;
+                case 4: launch_decimate_warp<4>(p, (int)n_seg, st); break;
+                case 5: launch_decimate_warp<5>(p, (int)n_seg, st); break;
+                default: launch_decimate_warp<6>(p, (int)n_seg, st); break;
             }
             d->launches++;
         }

@@ -25,6 +25,14 @@ def test_decimator_variants(emu_lib, oracle, M, fcpos, variant, bits):
     cases.check_decimator(emu_lib, oracle, M, fcpos, variant, x, [0, 777, 10000, n], bits)
 
 
+@pytest.mark.parametrize("M,S,n", [(4, 3, 20011), (5, 3, 40003), (6, 3, 80001)])
+def test_decimator_shares_cross_streams(emu_lib, oracle, M, S, n):
+    """a warp's share of the global event axis ends one stream and starts the next (own warm-up per piece)"""
+    rng = np.random.default_rng(250 + M)
+    x = cases.rand_iq(rng, (S, n))
+    cases.check_decimator(emu_lib, oracle, M, 2, M & 1, x, [0, n])
+
+
 def test_decimator_input_classes(emu_lib, oracle):
     rng = np.random.default_rng(300)
     for name, x in cases.input_classes(rng, 16384).items():

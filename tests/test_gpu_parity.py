@@ -50,7 +50,8 @@ def test_decimator_short_and_empty(gpu_lib, oracle):
 
 
 def test_decimator_many_streams_many_segments(gpu_lib, oracle):
-    """stream-per-CTA-group layout: 64 streams, several segments each; spot-check streams against the oracle."""
+    """64 streams laid end to end on the global event axis, the warps' shares cross stream boundaries; every
+    stream against the oracle."""
     from sdrdaemon_b200 import capi
 
     rng = np.random.default_rng(3002)
@@ -58,13 +59,22 @@ def test_decimator_many_streams_many_segments(gpu_lib, oracle):
     x = cases.rand_iq(rng, (S, n))
     d = capi.Decimator(M, n_streams=S, max_in=n, lib=gpu_lib)
     y, _ = d.process(x)
-    for s in (0, 1, 31, 63):
+    for s in range(S):
         yo, _ = oracle.Decimator(M).process(x[s])
-        assert np.array_equal(y[s], yo)
+        assert np.array_equal(y[s], yo), f"stream {s}"
     # linearity-free property at full size: splitting the call must not change a single bit
     d.reset()
     y2 = np.concatenate([d.process(x[:, : n // 2 + 64])[0], d.process(x[:, n // 2 + 64:])[0]], axis=1)
     assert np.array_equal(y, y2)
+
+
+@pytest.mark.parametrize("M,S,n", [(4, 7, 300_007), (5, 13, 250_003), (6, 5, 700_001), (1, 3, 100_001), (6, 300, 5000)])
+def test_decimator_shares_cross_streams(gpu_lib, oracle, M, S, n):
+    """ragged stream lengths (the last event of a stream is partial) with warps whose share of the event axis
+    ends one stream and starts the next; (6, 300, 5000): more streams than one warp per stream would need."""
+    rng = np.random.default_rng(3100 + M)
+    x = cases.rand_iq(rng, (S, n))
+    cases.check_decimator(gpu_lib, oracle, M, 2, M & 1, x, [0, n // 3, n])
 
 
 def test_decimator_large_single_stream(gpu_lib, oracle):
