@@ -42,17 +42,17 @@ struct Tables {
     const uint8_t* gflog;   /* [256] */
 };
 
-/* nibble selectors for PRMT from the 3+3+2-bit digits of four packed bytes */
-SDRD_DEVICE uint32_t pack_digits(uint32_t m)
-{
-    uint32_t t = m | (m >> 4);
-    return prmt(t, 0u, 0x0020u);
-}
+/* Nibble selectors for PRMT from the 3+3+2-bit digits of four packed bytes: selector nibble i = digit of
+ * byte i.  The ALU pipe (PRMT, LOP3, SHF) is what bounds these kernels and the FMA pipe idles, so the shifts
+ * that bring two digits into one byte are done by an integer multiply: the masked word times (2^a + 2^b)
+ * puts digit i - 1 into the low and digit i into the high nibble of byte i (no two fields overlap, so the
+ * sum has no carries); for the top digit the high word of the product (IMAD.HI) does the right shift.  One
+ * PRMT then moves the two useful bytes into the low half.  2 ALU + 1 FMA instruction per digit (was 4-5 ALU). */
 SDRD_DEVICE void selectors(uint32_t x, uint32_t& s0, uint32_t& s1, uint32_t& s2)
 {
-    s0 = pack_digits(x & 0x07070707u);
-    s1 = pack_digits((x >> 3) & 0x07070707u);
-    s2 = pack_digits((x >> 6) & 0x03030303u);
+    s0 = prmt(mad_lo(x & 0x07070707u, (1u << 4) + (1u << 8), 0u), 0u, 0x0031u);   /* bits 0-2: bytes 1, 3 of the product */
+    s1 = prmt(mad_lo(x & 0x38383838u, (1u << 1) + (1u << 5), 0u), 0u, 0x0031u);   /* bits 3-5 */
+    s2 = prmt(mul_hi(x & 0xC0C0C0C0u, (1u << 26) + (1u << 22)), 0u, 0x0020u);     /* bits 6-7: bytes 0, 2 of the high word */
 }
 /* One pass: rows [row0, row0 + nrows) (nrows <= 16) of  out = C * img  accumulated into rec16
  * (16 x 128 words, zeroed by the caller).  coefT[j * cstride + r] = 32 * C[r][j]: the byte offset of

@@ -218,6 +218,17 @@ SDRD_DEVICE uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
     return d;
 #endif
 }
+/* high word of the unsigned 64-bit product (IMAD.HI.U32, FMA pipe): a right shift that costs the ALU pipe nothing */
+SDRD_DEVICE uint32_t mul_hi(uint32_t a, uint32_t b)
+{
+#if defined(SDRD_EMU)
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#else
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+#endif
+}
 /* PTX prmt (generic mode) without the selector masking __byte_perm() adds: callers guarantee that
  * bit 3 of every selector nibble is clear.  SASS: one PRMT. */
 SDRD_DEVICE uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel)
