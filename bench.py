@@ -553,7 +553,10 @@ def main():
         tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                t = json.load(open(tp))
+                # the capture is of one launch of a given shape: only quote it for that shape
+                if t.get("log2_decim", 4) == M_LOG2 and t.get("samples_per_launch", 592 * 16129 * 16) == S * n_in:
+                    traffic = t.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
