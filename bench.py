@@ -544,6 +544,28 @@ def main():
         head = torch.as_tensor(DevView(dg_ptr, (128 + N_FEC) * 512), device="cuda").cpu().numpy().reshape(1, -1)
         digests = multi.gather_digests(multi.datagram_digest(head), world * S, world, rank, device=torch.device("cuda", local))
 
+    # drop-in mode: one process holds every stream and scatters contiguous ranges to the ranks over
+    # NVLink (one NCCL group of sends); reported next to the headline, not part of `value` (there each rank
+    # generates its own streams on the device)
+    scatter = None
+    if world > 1:
+        x_all = torch.zeros((world * S if rank == 0 else 0, n_in * 2), dtype=torch.int16, device="cuda")
+        multi.scatter_streams(x_all, world * S, world, rank)  # warm-up: NCCL P2P channels
+        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sa.record()
+        for _ in range(3):
+            mine = multi.scatter_streams(x_all, world * S, world, rank)
+        sb.record()
+        torch.cuda.synchronize()
+        ts = torch.tensor([sa.elapsed_time(sb) / 3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sc_bytes = (world - 1) * S * n_in * 4
+        scatter = {"ms": round(float(ts[0]), 3), "bytes_from_rank0": sc_bytes, "GB_per_s": round(sc_bytes / float(ts[0]) / 1e6, 1),
+                   "api": "sdrdaemon_b200.multi.scatter_streams (NCCL send/recv, device buffers)"}
+        del x_all, mine
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         k1_bytes = S * n_in * k1_bytes_per_sample(M_LOG2)
@@ -572,6 +594,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "stream_digests": [hex(int(v)) for v in digests] if digests is not None else None,
+            "scatter": scatter,
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": f"hb::decimate_warp_kernel<{M_LOG2}> (K1)", "achieved": round(achieved, 1), "peak": peak,

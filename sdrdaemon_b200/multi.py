@@ -1,6 +1,9 @@
 """Multi-GPU sharding of the hot path: one process per GPU, independent IQ streams partitioned in
-contiguous ranges (stream s -> rank s // (S / G)); there is no data-path collective -- the
-only exchange is the gather of one 8-byte digest per stream (torch.distributed all_gather)."""
+contiguous ranges (stream s -> rank s // (S / G)); there is no data-path collective.  The
+exchanges are the trivial ones either side of the path: the scatter of streams that only rank 0 holds
+(drop-in mode: one host process feeds all GPUs), the gather of the datagram images back to it, and the
+gather of one 8-byte digest per stream -- torch.distributed point-to-point / all_gather, NCCL over NVLink
+on GPUs (one ncclGroup per scatter), gloo in the CPU tests."""
 from __future__ import annotations
 
 from typing import List, Optional, Tuple
@@ -42,6 +45,58 @@ def gather_digests(local: np.ndarray, n_streams: int, world: int, rank: int, dev
     dist.all_gather(out, buf)
     parts: List[np.ndarray] = [o.cpu().numpy().view(np.uint64)[:c] for o, c in zip(out, counts)]
     return np.concatenate(parts)
+
+
+def scatter_streams(x_all, n_streams: int, world: int, rank: int, src: int = 0):
+    """Rank `src` holds every stream, x_all (n_streams, ...) torch tensor (on the GPU for NCCL, on the CPU
+    for gloo); every rank returns its contiguous range of streams (a tensor shaped (count, ...)).  Other
+    ranks pass a tensor of the per-stream shape/dtype/device to receive into (x_all[:0] is enough)."""
+    import torch
+    import torch.distributed as dist
+
+    first, count = stream_range(n_streams, world, rank)
+    if world == 1:
+        return x_all[first:first + count]
+    if rank == src:
+        ops = []
+        for r in range(world):
+            a, c = stream_range(n_streams, world, r)
+            if r != src and c:
+                ops.append(dist.P2POp(dist.isend, x_all[a:a + c].contiguous(), r))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        return x_all[first:first + count]
+    mine = torch.empty((count,) + tuple(x_all.shape[1:]), dtype=x_all.dtype, device=x_all.device)
+    if count:
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, mine, src)]):
+            w.wait()
+    return mine
+
+
+def gather_datagrams(dg_local, n_streams: int, world: int, rank: int, dst: int = 0):
+    """The reverse exchange: every rank's datagram images (count, frames, blocks, 512) to rank `dst`, which
+    returns the (n_streams, frames, blocks, 512) tensor in stream order (the other ranks return None)."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return dg_local
+    if rank != dst:
+        if dg_local.shape[0]:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, dg_local.contiguous(), dst)]):
+                w.wait()
+        return None
+    out = torch.empty((n_streams,) + tuple(dg_local.shape[1:]), dtype=dg_local.dtype, device=dg_local.device)
+    ops = []
+    for r in range(world):
+        a, c = stream_range(n_streams, world, r)
+        if r == dst:
+            out[a:a + c] = dg_local
+        elif c:
+            ops.append(dist.P2POp(dist.irecv, out[a:a + c], r))
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    return out
 
 
 def rx_sharded(x_local: np.ndarray, log2_decim: int, n_fec: int, lib=None, **sink_kw) -> np.ndarray:

@@ -28,12 +28,20 @@ def _worker(rank, world, port, q):
     from sdrdaemon_b200 import capi
 
     lib = capi.load(os.path.join(ROOT, "tests", "emu", "libsdrd_emu.so"))
-    x = _inputs()
+    import torch
+
+    # drop-in mode: only rank 0 holds the streams; scatter, process the shard, gather the datagrams back
+    x_all = torch.from_numpy(_inputs()) if rank == 0 else torch.empty((0, N_IN, 2), dtype=torch.int16)
+    x = multi.scatter_streams(x_all, S, world, rank).numpy()
     first, count = multi.stream_range(S, world, rank)
-    dg = multi.rx_sharded(x[first:first + count], M, F, lib=lib)
+    assert x.shape == (count, N_IN, 2) and np.array_equal(x, _inputs()[first:first + count])
+    dg = multi.rx_sharded(x, M, F, lib=lib)
     dig = multi.gather_digests(multi.datagram_digest(dg), S, world, rank)
+    all_dg = multi.gather_datagrams(torch.from_numpy(dg), S, world, rank)
     if rank == 0:
-        q.put(dig)
+        q.put((dig, all_dg.numpy()))
+    else:
+        assert all_dg is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -52,7 +60,8 @@ def test_stream_range_partitions():
 
 def test_two_ranks_match_single_process(emu_lib):
     x = _inputs()
-    want = multi.datagram_digest(multi.rx_sharded(x, M, F, lib=emu_lib))
+    want_dg = multi.rx_sharded(x, M, F, lib=emu_lib)
+    want = multi.datagram_digest(want_dg)
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -62,8 +71,9 @@ def test_two_ranks_match_single_process(emu_lib):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=300)
+    got, got_dg = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert np.array_equal(got, want)
+    assert np.array_equal(got_dg, want_dg)  # scatter -> shards -> gather == one process over all streams
