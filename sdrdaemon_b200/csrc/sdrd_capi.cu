@@ -957,8 +957,15 @@ namespace {
 struct Scratch {
     void* p = nullptr;
     size_t n = 0;
+    int device = -1;
     int ensure(size_t need)
     {
+        if (device != rt::current_device()) { /* the thread moved to another device: start over there */
+            rt::release(p);
+            p = nullptr;
+            n = 0;
+            device = rt::current_device();
+        }
         if (need <= n) return 0;
         rt::release(p);
         p = nullptr;
@@ -969,6 +976,26 @@ struct Scratch {
     }
 };
 thread_local Scratch g_scr_a, g_scr_b, g_scr_c;
+/* copy-in / kernel / copy-out streams of the host-pointer decode */
+struct DecPipe {
+    static constexpr int NS = 16;
+    rt::stream_t s_in = 0, s_k = 0, s_out = 0;
+    rt::event_t ev_in[NS] = {}, ev_k[NS] = {};
+    bool ready = false;
+    int device = -1;
+    int init()
+    {
+        if (ready && device == rt::current_device()) return 0;
+        ready = false; /* first use, or the thread moved to another device: streams belong to a device */
+        device = rt::current_device();
+        if (rt::stream_create(&s_in) || rt::stream_create(&s_k) || rt::stream_create(&s_out)) return -1;
+        for (int i = 0; i < NS; i++)
+            if (rt::event_create(&ev_in[i]) || rt::event_create(&ev_k[i])) return -1;
+        ready = true;
+        return 0;
+    }
+};
+thread_local DecPipe g_dec_pipe;
 } /* namespace */
 
 extern "C" int sdrd_cm256_encode_dev(const uint8_t* originals, size_t block_pitch, int n_frames, int recovery_count,
@@ -1068,13 +1095,41 @@ extern "C" int sdrd_fec_decode(const uint8_t* superblocks, size_t blocks_pitch, 
     int* d_st = (int*)((uint8_t*)d_nb + round_up(int_bytes, 16));
     uint8_t* d_pay = (uint8_t*)g_scr_b.p;
     uint8_t* d_b0 = d_pay + round_up(pay_bytes, 16);
-    SDRD_TRY(rt::copy(d_sb, superblocks, in_bytes, rt::H2D, 0), "copy datagrams to device");
     SDRD_TRY(rt::copy(d_nb, n_blocks, int_bytes, rt::H2D, 0), "copy block counts to device");
-    if (int rc = sdrd_fec_decode_dev(d_sb, blocks_pitch, d_nb, n_frames, d_pay, d_b0, d_st, 0)) return rc;
-    SDRD_TRY(rt::copy(payload, d_pay, pay_bytes, rt::D2H, 0), "copy payload to host");
-    if (block0) SDRD_TRY(rt::copy(block0, d_b0, b0_bytes, rt::D2H, 0), "copy meta blocks to host");
-    SDRD_TRY(rt::copy(status, d_st, int_bytes, rt::D2H, 0), "copy status to host");
     SDRD_TRY(rt::sync(0), "fec decode");
+    /* Frames are independent: large calls go through in slices on three streams, so that the host -> device
+     * copy of slice i + 1, the kernels of slice i and the device -> host copy of slice i - 1 overlap (PCIe is
+     * full duplex; the call then costs little more than the larger of its two copies). */
+    DecPipe& dp = g_dec_pipe;
+    int n_slices = n_frames >= DecPipe::NS * 64 ? DecPipe::NS : (n_frames >= 128 ? n_frames / 64 : 1);
+    if (const char* e = getenv("SDRD_DEC_SLICES")) n_slices = std::max(1, std::min<int>(atoi(e), std::min<int>(DecPipe::NS, n_frames)));
+    if (dp.init()) return fail_cuda("creating streams");
+    const int per = (n_frames + n_slices - 1) / n_slices;
+    for (int i = 0; i < n_slices; i++) {
+        const size_t f0 = (size_t)i * per, nf = std::min<size_t>(per, (size_t)n_frames - f0);
+        SDRD_TRY(rt::copy(d_sb + f0 * blocks_pitch * SDRD_UDPSIZE, superblocks + f0 * blocks_pitch * SDRD_UDPSIZE,
+                          nf * blocks_pitch * SDRD_UDPSIZE, rt::H2D, dp.s_in),
+                 "copy datagrams to device");
+        SDRD_TRY(rt::event_record(dp.ev_in[i], dp.s_in), "record copy event");
+    }
+    for (int i = 0; i < n_slices; i++) {
+        const size_t f0 = (size_t)i * per, nf = std::min<size_t>(per, (size_t)n_frames - f0);
+        SDRD_TRY(rt::stream_wait(dp.s_k, dp.ev_in[i]), "wait for copy");
+        if (int rc = sdrd_fec_decode_dev(d_sb + f0 * blocks_pitch * SDRD_UDPSIZE, blocks_pitch, d_nb + f0, (int)nf,
+                                         d_pay + f0 * 127 * SDRD_BLOCK_BYTES, d_b0 + f0 * SDRD_BLOCK_BYTES, d_st + f0, (void*)dp.s_k))
+            return rc;
+        SDRD_TRY(rt::event_record(dp.ev_k[i], dp.s_k), "record kernel event");
+        SDRD_TRY(rt::stream_wait(dp.s_out, dp.ev_k[i]), "wait for kernels");
+        SDRD_TRY(rt::copy(payload + f0 * 127 * SDRD_BLOCK_BYTES, d_pay + f0 * 127 * SDRD_BLOCK_BYTES, nf * 127 * SDRD_BLOCK_BYTES,
+                          rt::D2H, dp.s_out),
+                 "copy payload to host");
+        if (block0)
+            SDRD_TRY(rt::copy(block0 + f0 * SDRD_BLOCK_BYTES, d_b0 + f0 * SDRD_BLOCK_BYTES, nf * SDRD_BLOCK_BYTES, rt::D2H, dp.s_out),
+                     "copy meta blocks to host");
+    }
+    SDRD_TRY(rt::stream_wait(dp.s_out, dp.ev_k[n_slices - 1]), "wait for kernels");
+    SDRD_TRY(rt::copy(status, d_st, int_bytes, rt::D2H, dp.s_out), "copy status to host");
+    SDRD_TRY(rt::sync(dp.s_out), "fec decode");
     return 0;
 }
 

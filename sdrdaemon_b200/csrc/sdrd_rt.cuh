@@ -22,6 +22,7 @@ typedef void* stream_t;
 inline bool device_ok(std::string&) { return true; }
 inline int device_count() { return 1; }
 inline int set_device(int) { return 0; }
+inline int current_device() { return 0; }
 inline int sm_count() { return 148; }
 inline int alloc(void** p, size_t n)
 {
@@ -105,6 +106,12 @@ inline bool device_ok(std::string& why)
     return true;
 }
 inline int set_device(int d) { return cudaSetDevice(d) == cudaSuccess ? 0 : -1; }
+inline int current_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
 inline int sm_count()
 {
     int dev = 0, n = 148;
