@@ -442,70 +442,70 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
             /* cm256's single-recovery shortcut: XOR of everything received, whatever the row */
             for (int k = tid; k < 128 * DCAP; k += NT) sm.coefT[k] = (uint16_t)((k % DCAP) == 0 ? TAB_ENTRY : 0);
         } else {
-            /* A[k][c] = M[x_k][e_c] = d_c / (x_k ^ y_c) with x_k = index of recovery block k (128..255),
-             * y_c = erased original c (0..127), d_c = y_c ^ 128: a Cauchy matrix with scaled columns, whose
-             * inverse is explicit (no elimination, no pivots, two barriers):
-             *   Ainv[c][k] = P_c * Q_k / (d_c * (x_k ^ y_c)),
-             *   P_c = prod_j (y_c ^ x_j) / prod_{j != c} (y_c ^ y_j),  Q_k = prod_j (x_k ^ y_j) / prod_{j != k} (x_k ^ x_j).
-             * Everything is kept as discrete logarithms (entries of the inverse are never zero). */
-            uint8_t* lA = aug;                  /* [N][N] log Ainv[c][k] */
-            uint8_t* lq = erased + 128;         /* [N] log Q_k */
-            uint8_t* lp = lq + 128;             /* [N] log (P_c / d_c) */
-            if (tid < 2 * N) {
-                const bool isx = tid < N;
-                const int me = isx ? tid : tid - N;
-                const int v = isx ? recIdxOf[me] : erased[me];
-                int acc = 0;
-                for (int j = 0; j < N; j++) {
-                    const int xo = recIdxOf[j], yo = erased[j];
-                    acc += gflog[v ^ (isx ? yo : xo)];                      /* the other family: all of it */
-                    if (j != me) acc += 255 - gflog[v ^ (isx ? xo : yo)];   /* the own family: all but itself */
+            /* A[k][c] = M[x_k][y_c] = a_c / (x_k ^ y_c) with x_k = index of recovery block k (128..255),
+             * y_c = erased original c (0..127), a_y = y ^ 128: a Cauchy matrix with scaled columns.  Both halves
+             * of the decode matrix D = [A^-1 | A^-1 M] have closed forms (no elimination, no pivots, no
+             * N-term sums per entry).  With
+             *   P_c = prod_j (y_c ^ x_j) / prod_{j != c} (y_c ^ y_j),   Q_k = prod_j (x_k ^ y_j) / prod_{j != k} (x_k ^ x_j),
+             *   g(y) = prod_c (y ^ y_c) / prod_k (y ^ x_k)   (= 1 + sum_k Q_k / (y ^ x_k), partial fractions)
+             * the weight of recovery block k in erased original c is   P_c Q_k / (a_c (x_k ^ y_c))
+             * and, because 1/((x^a)(x^b)) = (1/(x^a) + 1/(x^b)) / (a^b) in characteristic 2, the weight of a
+             * received original o is   sum_k A^-1[c][k] M[x_k][o] = P_c a_o g(y_o) / (a_c (y_c ^ y_o)).
+             * Both read  D[c][i] = exp( lp[c] + lbase[i] - log(z_i ^ y_c) )  with z_i the block index of image
+             * row i, lp[c] = log(P_c / a_c) and lbase[i] = log Q_k resp. log(a_o g(y_o)): one pass of 2N
+             * logarithms per image row, then two table look-ups per entry.  Everything is kept as discrete
+             * logarithms (none of these factors is ever zero). */
+            uint8_t* lbase = aug;               /* [128] per image row */
+            uint8_t* lp = erased + 128;         /* [N] log (P_c / a_c) */
+            if (tid < 128) {
+                const int i = tid;
+                const int z = (int)((sm.img[i * ROW_WORDS] >> 16) & 0xFFu);
+                int me = -1; /* recovery rows: their own slot is left out of the x-product */
+                bool used = true;
+                if (z >= 128) {
+                    const int wq = i >> 5;
+                    me = __popc(recMask[wq] & ((1u << (i & 31)) - 1u));
+                    for (int q = 0; q < wq; q++) me += __popc(recMask[q]);
+                } else {
+                    used = origRow[z] == i;
                 }
-                if (!isx) acc += 255 - gflog[v ^ 128];
-                (isx ? lq : lp)[me] = (uint8_t)(acc % 255);
+                int acc = 0;
+                if (used) {
+                    if (z < 128) acc = gflog[z ^ 128];
+                    for (int j = 0; j < N; j++) {
+                        acc += gflog[z ^ erased[j]];
+                        if (j != me) acc += 255 - gflog[z ^ recIdxOf[j]];
+                    }
+                }
+                lbase[i] = (uint8_t)(acc % 255);
+            } else if (tid < 128 + N) {
+                const int me = tid - 128;
+                const int v = erased[me];
+                int acc = 255 - gflog[v ^ 128];
+                for (int j = 0; j < N; j++) {
+                    acc += gflog[v ^ recIdxOf[j]];
+                    if (j != me) acc += 255 - gflog[v ^ erased[j]];
+                }
+                lp[me] = (uint8_t)(acc % 255);
             }
             __syncthreads();
-            for (int k = tid; k < N * N; k += NT) {
-                const int c = k / N, kk = k - c * N;
-                lA[k] = (uint8_t)((lp[c] + lq[kk] + 255 - gflog[recIdxOf[kk] ^ erased[c]]) % 255);
-            }
-            __syncthreads();
-            /* D[c][i], the weight of image row i in erased original c:  X_c = sum_k Ainv[c][k] * (rec_k ^
-             * sum_o M[x_k][o] * orig_o).  Thread (i, h) does image row i for the rows c in every other
-             * block of 16, h = 0 / 1. */
+            /* thread (i, h) fills image row i's column of D for the rows c in every other block of 16 */
             {
                 const int i = tid & 127, h = tid >> 7;
-                const int idx = (int)((sm.img[i * ROW_WORDS] >> 16) & 0xFFu);
-                int kind = 0, kk0 = 0; /* 0: row not used, 1: recovery slot kk0, 2: an original */
-                if (idx >= 128) {
-                    kind = 1;
-                    const int wq = i >> 5;
-                    kk0 = __popc(recMask[wq] & ((1u << (i & 31)) - 1u));
-                    for (int q = 0; q < wq; q++) kk0 += __popc(recMask[q]);
-                } else if (origRow[idx] == i) {
-                    kind = 2;
-                }
-                const int lnum = gflog[(idx ^ 128) & 0xFF]; /* log of M's numerator (only used when kind == 2) */
+                const int z = (int)((sm.img[i * ROW_WORDS] >> 16) & 0xFFu);
+                const bool used = z >= 128 || origRow[z] == i;
+                const int lb = lbase[i];
                 for (int c0 = 16 * h; c0 < N; c0 += 32) {
-                    uint32_t acc[16];
 #pragma unroll
-                    for (int cc = 0; cc < 16; cc++) acc[cc] = 0u;
-                    if (kind == 1) {
-#pragma unroll
-                        for (int cc = 0; cc < 16; cc++)
-                            if (c0 + cc < N) acc[cc] = gfexp[lA[(c0 + cc) * N + kk0]];
-                    } else if (kind == 2) {
-                        for (int kk = 0; kk < N; kk++) {
-                            int lm = lnum + 255 - gflog[recIdxOf[kk] ^ idx]; /* log M[x_kk][idx] */
-                            if (lm >= 255) lm -= 255;
-#pragma unroll
-                            for (int cc = 0; cc < 16; cc++)
-                                if (c0 + cc < N) acc[cc] ^= gfexp[lA[(c0 + cc) * N + kk] + lm];
+                    for (int cc = 0; cc < 16; cc++) {
+                        const int c = c0 + cc;
+                        if (c < N) {
+                            int t = lp[c] + lb;
+                            if (t >= 255) t -= 255;
+                            const uint32_t v = used ? gfexp[t + 255 - gflog[z ^ erased[c]]] : 0u;
+                            sm.coefT[i * DCAP + c] = (uint16_t)(TAB_ENTRY * v);
                         }
                     }
-#pragma unroll
-                    for (int cc = 0; cc < 16; cc++)
-                        if (c0 + cc < N) sm.coefT[i * DCAP + c0 + cc] = (uint16_t)(TAB_ENTRY * acc[cc]);
                 }
             }
         }
