@@ -275,6 +275,13 @@ def run_decode(args):
     ms = e0.elapsed_time(e1) / steps
     peak, peak_src = measured_peaks()
     alg = nf * (128 * 512 + 127 * 508)
+    k3_traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json")))
+        if t.get("frames_per_launch") == nf:
+            k3_traffic = t.get("dram_bytes_per_launch")
+    except Exception:
+        k3_traffic = None
     # end to end through the host-pointer C ABI (what UDPSourceFEC would call): pinned host buffers, H2D of the
     # received datagrams + kernels + D2H of the payload inside the timed region
     e2e = None
@@ -317,7 +324,7 @@ def run_decode(args):
                                  "parity": "all frames recovered == transmitted" if ok else "MISMATCH"},
                       "gpu_launches": 2 * steps, "e2e": e2e, "cpu_baseline": cpu,
                       "roofline": {"bound": "hbm", "kernel": "fec::decode_kernel<32> (K3)", "achieved": round(alg / ms / 1e6, 1),
-                                   "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": None,
+                                   "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": k3_traffic,
                                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                                    "note": "K3 is ALU-pipe bound (PRMT/LOP3 table arithmetic), see DESIGN.md"}}), flush=True)
 
@@ -575,8 +582,10 @@ def main():
 
         first, count = multi.stream_range(world * S, world, rank)
         assert count == S
-        dg_ptr, _ = sink.dev_datagrams()
-        head = torch.as_tensor(DevView(dg_ptr, (128 + N_FEC) * 512), device="cuda").cpu().numpy().reshape(1, -1)
+        dg_ptr, frame_pitch = sink.dev_datagrams()
+        fb = (128 + N_FEC) * 512  # first frame of every stream of this rank (stream pitch = frame_pitch frames)
+        allv = torch.as_tensor(DevView(dg_ptr, ((S - 1) * frame_pitch + 1) * fb), device="cuda")
+        head = torch.as_strided(allv, (S, fb), (frame_pitch * fb, 1)).cpu().numpy()
         digests = multi.gather_digests(multi.datagram_digest(head), world * S, world, rank, device=torch.device("cuda", local))
 
     # drop-in mode: one process holds every stream and scatters contiguous ranges to the ranks over
@@ -628,7 +637,10 @@ def main():
             },
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "stream_digests": [hex(int(v)) for v in digests] if digests is not None else None,
+            # one 8-byte digest per stream gathered from all ranks; the line carries the first of each rank and a fold of all
+            "stream_digests": ([hex(int(v)) for v in digests[::S]] if digests is not None else None),
+            "stream_digests_fold": (hex(int(np.bitwise_xor.reduce(digests))) if digests is not None else None),
+            "n_stream_digests": (int(len(digests)) if digests is not None else None),
             "scatter": scatter,
             "clocks": clocks,
             "roofline": {

@@ -60,8 +60,9 @@ SDRD_DEVICE void selectors(uint32_t x, uint32_t& s0, uint32_t& s1, uint32_t& s2)
  * padding}), fetched with a 16-bit shared load so that no ALU instruction is spent on it -- the ALU
  * pipe (PRMT, LOP3) is what bounds this kernel.  Two columns are folded into an accumulator with three
  * 3-input XORs. */
-SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride,
-                             int row0, int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
+template <bool FULL> /* FULL: nrows == RB, the row loop carries no predicates */
+SDRD_DEVICE void matvec_pass_t(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride,
+                               int row0, int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
     uint32_t acc[RB][4];
@@ -81,7 +82,7 @@ SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* 
         const uint16_t* co1 = co0 + cstride;
 #pragma unroll
         for (int r = 0; r < RB; r++) {
-            if (r < nrows) {
+            if (FULL || r < nrows) {
                 const unsigned char* e0 = tab + co0[r];
                 const unsigned char* e1 = tab + co1[r];
                 const uint4 a0 = *reinterpret_cast<const uint4*>(e0);
@@ -101,11 +102,18 @@ SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* 
     }
 #pragma unroll
     for (int r = 0; r < RB; r++) {
-        if (r < nrows) {
+        if (FULL || r < nrows) {
 #pragma unroll
             for (int w = 0; w < 4; w++) atomicXor(&rec16[r * ROW_WORDS + lane + 32 * w], acc[r][w]);
         }
     }
+}
+
+SDRD_DEVICE void matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride,
+                             int row0, int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
+{
+    if (nrows == RB) matvec_pass_t<true>(img, coefT, cstride, row0, nrows, tab, rec16, tid);
+    else matvec_pass_t<false>(img, coefT, cstride, row0, nrows, tab, rec16, tid);
 }
 
 /* shared-memory carve-up common to both kernels */
@@ -165,8 +173,9 @@ constexpr int ENC_NT = 512;
 inline size_t enc_smem_bytes(int cstride) { return SMEM_FIXED + (size_t)IMG_WORDS * 4 + (size_t)128 * cstride * 2; }
 
 /* 16 warps: warp w takes columns 8w .. 8w+7 of a pass */
-SDRD_DEVICE void enc_matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride, int row0,
-                                 int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
+template <bool FULL>
+SDRD_DEVICE void enc_matvec_pass_t(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride, int row0,
+                                   int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
     uint32_t acc[RB][4];
@@ -185,7 +194,7 @@ SDRD_DEVICE void enc_matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16
         const uint16_t* co1 = co0 + cstride;
 #pragma unroll
         for (int r = 0; r < RB; r++) {
-            if (r < nrows) {
+            if (FULL || r < nrows) {
                 const unsigned char* e0 = tab + co0[r];
                 const unsigned char* e1 = tab + co1[r];
                 const uint4 a0 = *reinterpret_cast<const uint4*>(e0);
@@ -205,11 +214,18 @@ SDRD_DEVICE void enc_matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16
     }
 #pragma unroll
     for (int r = 0; r < RB; r++) {
-        if (r < nrows) {
+        if (FULL || r < nrows) {
 #pragma unroll
             for (int w = 0; w < 4; w++) atomicXor(&rec16[r * ROW_WORDS + lane + 32 * w], acc[r][w]);
         }
     }
+}
+
+SDRD_DEVICE void enc_matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride, int row0,
+                                 int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
+{
+    if (nrows == RB) enc_matvec_pass_t<true>(img, coefT, cstride, row0, nrows, tab, rec16, tid);
+    else enc_matvec_pass_t<false>(img, coefT, cstride, row0, nrows, tab, rec16, tid);
 }
 
 /* Persistent: CTA c encodes work items c, c + gridDim.x, ... (item = stream * n_frames + frame).  While

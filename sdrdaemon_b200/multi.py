@@ -47,6 +47,13 @@ def gather_digests(local: np.ndarray, n_streams: int, world: int, rank: int, dev
     return np.concatenate(parts)
 
 
+def _wire(t):
+    """the same memory as bytes: NCCL has no 16-bit integer type, and the exchange only moves data"""
+    import torch
+
+    return t.contiguous().view(torch.uint8) if t.dtype not in (torch.uint8, torch.int8) else t.contiguous()
+
+
 def scatter_streams(x_all, n_streams: int, world: int, rank: int, src: int = 0):
     """Rank `src` holds every stream, x_all (n_streams, ...) torch tensor (on the GPU for NCCL, on the CPU
     for gloo); every rank returns its contiguous range of streams (a tensor shaped (count, ...)).  Other
@@ -62,13 +69,13 @@ def scatter_streams(x_all, n_streams: int, world: int, rank: int, src: int = 0):
         for r in range(world):
             a, c = stream_range(n_streams, world, r)
             if r != src and c:
-                ops.append(dist.P2POp(dist.isend, x_all[a:a + c].contiguous(), r))
+                ops.append(dist.P2POp(dist.isend, _wire(x_all[a:a + c]), r))
         for w in (dist.batch_isend_irecv(ops) if ops else []):
             w.wait()
         return x_all[first:first + count]
     mine = torch.empty((count,) + tuple(x_all.shape[1:]), dtype=x_all.dtype, device=x_all.device)
     if count:
-        for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, mine, src)]):
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, _wire(mine), src)]):
             w.wait()
     return mine
 
@@ -83,7 +90,7 @@ def gather_datagrams(dg_local, n_streams: int, world: int, rank: int, dst: int =
         return dg_local
     if rank != dst:
         if dg_local.shape[0]:
-            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, dg_local.contiguous(), dst)]):
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, _wire(dg_local), dst)]):
                 w.wait()
         return None
     out = torch.empty((n_streams,) + tuple(dg_local.shape[1:]), dtype=dg_local.dtype, device=dg_local.device)
@@ -93,7 +100,7 @@ def gather_datagrams(dg_local, n_streams: int, world: int, rank: int, dst: int =
         if r == dst:
             out[a:a + c] = dg_local
         elif c:
-            ops.append(dist.P2POp(dist.irecv, out[a:a + c], r))
+            ops.append(dist.P2POp(dist.irecv, _wire(out[a:a + c]), r))
     for w in (dist.batch_isend_irecv(ops) if ops else []):
         w.wait()
     return out
