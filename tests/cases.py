@@ -29,7 +29,20 @@ def tone_iq(n, srate, dfp, power_db=6.0, phase=0.0):
 def input_classes(rng, n):
     imp = np.zeros((n, 2), np.int16)
     imp[n // 3] = (32767, -32768)
+    # the sign pattern of the 63-tap half-band response, repeated: drives stage 1 to its worst-case gain of 3.5
+    # (sum |taps| / 8192) once per 64 samples; and random picks of the two int16 extremes
+    taps = [-7, 11, -20, 32, -49, 71, -101, 140, -190, 256, -345, 469, -656, 978, -1698, 5201]
+    h = np.zeros(64, np.int64)
+    for i, t in enumerate(taps):
+        h[2 * i] = t
+        h[62 - 2 * i] = t
+    h[31] = 8192
+    sgn = np.where(h >= 0, 32767, -32768).astype(np.int16)
+    worst = np.tile(sgn, (n + 63) // 64)[:n]
+    ext = np.where(rng.integers(0, 2, size=(n, 2)) == 1, 32767, -32768).astype(np.int16)
     return {
+        "worst_gain": np.stack([worst, worst[::-1].copy()], axis=1),
+        "extremes": ext,
         "random": rand_iq(rng, (n,)),
         "tone": tone_iq(n, 2_400_000, 100_000),
         "impulse": imp,
