@@ -662,5 +662,16 @@ def main():
         dist.destroy_process_group()
 
 
+def _keep_stdout_for_the_json_line():
+    """Rank 0's stdout must carry ONE JSON line.  Native libraries write to file descriptor 1 directly (NCCL prints
+    "NCCL version ..." there when NCCL_DEBUG is VERSION or higher): point fd 1 at stderr and keep the original
+    stdout for Python's own prints, which are the JSON lines only."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _keep_stdout_for_the_json_line()
     main()
