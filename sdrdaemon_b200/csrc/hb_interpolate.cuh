@@ -194,5 +194,249 @@ SDRD_KERNEL(NT, 2) interpolate_kernel(Params p)
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Warp-private form (the product kernel; the CTA-wide kernel above stays for A/B runs, -DSDRD_K4_WARP=0).
+ * One warp (a 32-thread CTA) walks a segment of one stream in steps of WC = 64 input samples and runs the
+ * stages one after the other, every lane busy in every stage and no CTA barrier anywhere:
+ *     stage 1: 64 steps = 32 lanes x 2     stage 3: 256 steps = 32 lanes x 8
+ *     stage 2: 128 steps = 32 lanes x 4    stage 4 / 5: 2 / 4 passes of 32 lanes x 8
+ * A lane computes its N steps from one register window of L + N entries ((L + N) / (2 N) entries read per output
+ * sample instead of (L + 2) / 4).  Each stage buffer is [L entries of history | the step's new entries]: nothing is
+ * recomputed at tile edges (the CTA-wide form recomputes a halo per tile and stage) and the history is a copy of the
+ * last L entries at the end of a step.  Buffers are XOR-swizzled for their reader (16-byte unit u lives at
+ * u ^ ((u >> 3) & SW), SW = 3 for windows 4 units apart, 1 for 2 units apart): conflict-free window loads.
+ * The last stage's samples (16 per lane and pass) go through a swizzled staging area so that the global stores are
+ * whole 512-byte rows per instruction: a global store costs one L1 wavefront per 128-byte line it touches, and 64
+ * bytes per lane straight from registers touch 16 lines per instruction.
+ * A segment starts with one warm-up step (the cascade looks back 42 input samples, HIST = 64 are there).
+ * ------------------------------------------------------------------------------------------------------------ */
+constexpr int WC = 64;
+SDRD_HD constexpr int w_nstep(int s) { return s == 1 ? 2 : s == 2 ? 4 : 8; }
+SDRD_HD constexpr int w_passes(int s) { return (WC << (s - 1)) / (32 * w_nstep(s)); }
+SDRD_HD constexpr int w_sw_of_n(int n) { return n == 8 ? 3 : n == 4 ? 1 : 0; }
+SDRD_HD constexpr int w_sw(int b) { return w_sw_of_n(w_nstep(b + 1)); }  /* buffer b is read by stage b + 1 */
+SDRD_HD constexpr int w_hist(int b) { return ring_len(b + 1); }          /* = L of the reader: windows start at the task's first step */
+SDRD_HD constexpr int w_len(int b) { return (w_hist(b) + (WC << b) + 15) & ~15; }
+SDRD_HD constexpr int w_off(int b)
+{
+    int o = 0;
+    for (int t = 0; t < b; t++) o += w_len(t);
+    return o;
+}
+SDRD_HD constexpr int w_stage_words(int S) { return 64 * w_nstep(S); } /* one pass of the last stage: 32 lanes x 2 N samples */
+SDRD_HD constexpr size_t w_smem_bytes(int S) { return (size_t)w_off(S) * 8 + (size_t)w_stage_words(S) * 4; }
+
+template <int SW>
+SDRD_DEVICE int swz(int u) { return SW ? (u ^ ((u >> 3) & SW)) : u; }
+SDRD_DEVICE void ld_unit(const int2* SDRD_RESTRICT buf, int unit, int2* w)
+{
+    const int4 v = *reinterpret_cast<const int4*>(buf + 2 * unit);
+    w[0] = make_int2(v.x, v.y);
+    w[1] = make_int2(v.z, v.w);
+}
+SDRD_DEVICE void st_unit(int2* SDRD_RESTRICT buf, int unit, int2 a, int2 b)
+{
+    *reinterpret_cast<int4*>(buf + 2 * unit) = make_int4(a.x, a.y, b.x, b.y);
+}
+
+/* N consecutive steps from the window that starts at unit u0 (a multiple of N / 2) of a buffer swizzled for N */
+template <int L, int N>
+SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, int2 (&ev)[N], int2 (&od)[N])
+{
+    constexpr int SW = w_sw_of_n(N);
+    constexpr int T = L / 2;
+    constexpr int C64[16] = SDRD_HB64_ITAPS;
+    constexpr int C32[8] = SDRD_HB32_ITAPS;
+    constexpr int C16[4] = SDRD_HB16_ITAPS;
+    constexpr int NU = (L + N) / 2; /* units in the window */
+    int2 win[L + N];
+    if (SW == 3) {
+        /* chunks of 4 units share one swizzle value: unit 4 hc + i sits at 4 hc + (i ^ g), g = (hc >> 1) & 3 */
+#pragma unroll
+        for (int c = 0; c < NU / 4; c++) {
+            const int hc = (u0 >> 2) + c;
+            const int b0 = 4 * hc + ((hc >> 1) & 3);
+#pragma unroll
+            for (int i = 0; i < 4; i++) ld_unit(buf, b0 ^ i, &win[8 * c + 2 * i]);
+        }
+    } else if (SW == 1) {
+#pragma unroll
+        for (int c = 0; c < NU / 2; c++) {
+            const int pr = (u0 >> 1) + c;
+            const int b0 = 2 * pr + ((pr >> 2) & 1);
+            ld_unit(buf, b0, &win[4 * c]);
+            ld_unit(buf, b0 ^ 1, &win[4 * c + 2]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NU; j++) ld_unit(buf, u0 + j, &win[2 * j]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t ia = 0, qa = 0;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const int c = L == 32 ? C64[t & 15] : L == 16 ? C32[t & 7] : C16[t & 3];
+            const int2 a = win[i + 1 + t], b = win[i + L - t]; /* x[k+i-L+1+t], x[k+i-t] */
+            ia += ((uint32_t)a.x + (uint32_t)b.x) * (uint32_t)c;
+            qa += ((uint32_t)a.y + (uint32_t)b.y) * (uint32_t)c;
+        }
+        od[i] = make_int2(asr32(ia, 13), asr32(qa, 13));
+        ev[i] = win[i + L - L / 2];
+    }
+}
+
+struct WarpParams {
+    const uint32_t* in;   /* stream s, sample k (k >= -HIST): in[s * in_stride + k] */
+    long long in_stride;  /* words */
+    uint32_t* out;        /* out[s * out_stride + n] */
+    long long out_stride;
+    long long n_in;       /* input samples per stream */
+    int log2_interp;      /* 1..6; stages run S = min(log2_interp, 5) */
+    int steps_per_warp;   /* steps of WC input samples per warp; warp blockIdx.x takes steps [x * spw, (x + 1) * spw) */
+};
+
+/* one stage of the step: reads buffer ST - 1, writes buffer ST (ST < S) or the output (ST == S) */
+template <int S, int ST>
+SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT stage, int lane, uint32_t* SDRD_RESTRICT out, long long n0, long long n_valid,
+                            int wo, bool emit)
+{
+    constexpr int L = ring_len(ST);
+    constexpr int N = w_nstep(ST);
+    const int2* src = buf + w_off(ST - 1);
+#pragma unroll 1
+    for (int pass = 0; pass < w_passes(ST); pass++) {
+        const int task = 32 * pass + lane;
+        int2 ev[N], od[N];
+        fir_steps<L, N>(src, (N / 2) * task, ev, od);
+        if (ST < S) {
+            constexpr int SWD = w_sw(ST);
+            int2* dst = buf + w_off(ST);
+            const int ub = w_hist(ST) / 2 + N * task; /* first unit of the task's 2 N new entries */
+            if (N == 4 && SWD == 3) { /* one chunk of 4 units */
+                const int q = ub >> 2;
+                const int b0 = 4 * q + ((q >> 1) & 3);
+#pragma unroll
+                for (int i = 0; i < 4; i++) st_unit(dst, b0 ^ i, ev[i], od[i]);
+            } else if (N == 2 && SWD == 1) { /* one pair of units */
+                const int q = ub >> 1;
+                const int b0 = 2 * q + ((q >> 2) & 1);
+                st_unit(dst, b0, ev[0], od[0]);
+                st_unit(dst, b0 ^ 1, ev[1], od[1]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) st_unit(dst, swz<SWD>(ub + i), ev[i], od[i]);
+            }
+        } else {
+            /* last stage: pack to int16 pairs (IQSample::setReal/setImag), through the staging area, whole rows out */
+            constexpr int SWO = w_sw_of_n(N);
+            constexpr int UL = N / 2; /* 16-byte units per lane */
+            uint4* sg = reinterpret_cast<uint4*>(stage);
+#pragma unroll
+            for (int i = 0; i < UL; i++)
+                sg[swz<SWO>(UL * lane + i)] = make_uint4(pack16(ev[2 * i]), pack16(od[2 * i]), pack16(ev[2 * i + 1]), pack16(od[2 * i + 1]));
+            SDRD_SYNCWARP();
+            uint4 v[UL];
+#pragma unroll
+            for (int j = 0; j < UL; j++) v[j] = sg[swz<SWO>(32 * j + lane)];
+            SDRD_SYNCWARP();
+            if (emit) {
+#pragma unroll
+                for (int j = 0; j < UL; j++) {
+                    /* sample n of the cascade is emitted at (n >> S << wo) + (n & (2^S - 1)) */
+                    const long long n = n0 + (long long)(64 * N) * pass + 4 * (32 * j + lane);
+                    if (S >= 2) {
+                        if (n + 4 <= n_valid) *reinterpret_cast<uint4*>(out + ((n >> S) << wo) + (n & ((1 << S) - 1))) = v[j];
+                    } else { /* S = 1: two input samples' pairs */
+                        if (n + 2 <= n_valid) *reinterpret_cast<uint2*>(out + ((n >> 1) << wo)) = make_uint2(v[j].x, v[j].y);
+                        if (n + 4 <= n_valid) *reinterpret_cast<uint2*>(out + (((n + 2) >> 1) << wo)) = make_uint2(v[j].z, v[j].w);
+                    }
+                }
+            }
+        }
+    }
+}
+
+#ifndef SDRD_K4_WARPS_PER_SM
+#define SDRD_K4_WARPS_PER_SM 16
+#endif
+
+template <int S>
+SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
+{
+    static_assert(S >= 1 && S <= 5, "1..5 stages");
+    SDRD_DYN_SMEM(smem);
+    int2* const buf = reinterpret_cast<int2*>(smem);
+    uint32_t* const stage = reinterpret_cast<uint32_t*>(smem + (size_t)w_off(S) * 8);
+    const int lane = (int)threadIdx.x;
+    const uint32_t* in = p.in + (long long)blockIdx.y * p.in_stride;
+    uint32_t* out = p.out + (long long)blockIdx.y * p.out_stride;
+    const int wo = p.log2_interp;
+    const long long steps_total = (p.n_in + WC - 1) / WC;
+    const long long first = (long long)blockIdx.x * p.steps_per_warp;
+    long long last = first + p.steps_per_warp;
+    if (last > steps_total) last = steps_total;
+    if (first >= last) return;
+    const long long n_valid = p.n_in << S;
+
+    /* the two input samples of this lane for a step: k = 64 step + 2 lane, + 1 (0 past the end of the stream) */
+    auto fetch = [&](long long step) -> uint2 {
+        const long long k = step * WC + 2 * lane;
+        uint2 v = make_uint2(0u, 0u);
+        if (k + 1 < p.n_in) v = *reinterpret_cast<const uint2*>(in + k);
+        else if (k < p.n_in) v.x = in[k];
+        return v;
+    };
+    uint2 nxt = fetch(first - 1);
+#pragma unroll 1
+    for (long long step = first - 1; step < last; step++) {
+        const uint2 cur = nxt;
+        if (step + 1 < last) nxt = fetch(step + 1);
+        const bool emit = step >= first; /* the first step only fills the histories */
+        st_unit(buf + w_off(0), w_hist(0) / 2 + lane, make_int2((int)(int16_t)(cur.x & 0xFFFFu), ((int)cur.x) >> 16),
+                make_int2((int)(int16_t)(cur.y & 0xFFFFu), ((int)cur.y) >> 16));
+        SDRD_SYNCWARP();
+        const long long n0 = (step * WC) << S;
+        warp_stage<S, 1>(buf, stage, lane, out, n0, n_valid, wo, emit);
+        if (S >= 2) { SDRD_SYNCWARP(); warp_stage<S, S >= 2 ? 2 : 1>(buf, stage, lane, out, n0, n_valid, wo, emit); }
+        if (S >= 3) { SDRD_SYNCWARP(); warp_stage<S, S >= 3 ? 3 : 1>(buf, stage, lane, out, n0, n_valid, wo, emit); }
+        if (S >= 4) { SDRD_SYNCWARP(); warp_stage<S, S >= 4 ? 4 : 1>(buf, stage, lane, out, n0, n_valid, wo, emit); }
+        if (S >= 5) { SDRD_SYNCWARP(); warp_stage<S, S >= 5 ? 5 : 1>(buf, stage, lane, out, n0, n_valid, wo, emit); }
+        if (wo > S && emit) { /* interpolate64_cen: 32 zero samples after every 32 (Interpolators.cpp:370,413-603) */
+            const int zq = ((1 << wo) - (1 << S)) / 4; /* zero uint4 per input sample */
+            for (int i = lane; i < WC * zq; i += 32) {
+                const long long k = step * WC + i / zq;
+                if (k < p.n_in) *reinterpret_cast<uint4*>(out + (k << wo) + (1 << S) + 4 * (i % zq)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        /* histories: the last L entries of every buffer move to its front (units: 16, 8, 4, 4, 4) */
+        SDRD_SYNCWARP();
+        {
+            int b = lane < 16 ? 0 : lane < 24 ? 1 : lane < 28 ? 2 : 3;
+            int j = lane < 16 ? lane : lane < 24 ? lane - 16 : lane < 28 ? lane - 24 : lane - 28;
+            int4 v = make_int4(0, 0, 0, 0), v4 = make_int4(0, 0, 0, 0);
+            const bool on = b < S;
+#define SDRD_K4_TL(B, OP)                                                                                              \
+            if (b == (B) && (B) < S) { constexpr int SWB = w_sw((B) < S ? (B) : 0); int2* bb = buf + w_off((B) < S ? (B) : 0); \
+                const int su = (WC << (B)) / 2 + j; OP }
+            SDRD_K4_TL(0, v = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            SDRD_K4_TL(1, v = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            SDRD_K4_TL(2, v = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            SDRD_K4_TL(3, v = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            if (S == 5 && lane < 4) v4 = *reinterpret_cast<const int4*>(buf + w_off(S == 5 ? 4 : 0) + 2 * swz<3>((WC << 4) / 2 + lane));
+            SDRD_SYNCWARP();
+            SDRD_K4_TL(0, *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(j)) = v;)
+            SDRD_K4_TL(1, *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(j)) = v;)
+            SDRD_K4_TL(2, *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(j)) = v;)
+            SDRD_K4_TL(3, *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(j)) = v;)
+            if (S == 5 && lane < 4) *reinterpret_cast<int4*>(buf + w_off(S == 5 ? 4 : 0) + 2 * swz<3>(lane)) = v4;
+#undef SDRD_K4_TL
+            (void)on;
+        }
+        SDRD_SYNCWARP();
+    }
+}
+
 } /* namespace hbi */
 } /* namespace sdrd */

@@ -521,11 +521,28 @@ extern "C" void* sdrd_int_dev_output(sdrd_int* u, size_t* stride)
 }
 
 namespace {
+#ifndef SDRD_K4_WARP
+#define SDRD_K4_WARP 1 /* 1: warp-private kernel; 0: the CTA-wide tiled kernel (kept for A/B runs) */
+#endif
 template <int NS>
 void launch_interpolate(const hbi::Params& p, int S, rt::stream_t st)
 {
+#if SDRD_K4_WARP
+    /* one wave of resident warps over all streams, each a contiguous range of 64-sample steps of one stream */
+    hbi::WarpParams w{};
+    w.in = p.in; w.in_stride = p.in_stride; w.out = p.out; w.out_stride = p.out_stride; w.n_in = p.n_in;
+    w.log2_interp = p.log2_interp;
+    const long long steps = (p.n_in + hbi::WC - 1) / hbi::WC;
+    long long warps = ((long long)rt::sm_count() * SDRD_K4_WARPS_PER_SM + S - 1) / S; /* per stream */
+    if (warps > steps) warps = steps;
+    if (warps < 1) warps = 1;
+    w.steps_per_warp = (int)((steps + warps - 1) / warps);
+    warps = (steps + w.steps_per_warp - 1) / w.steps_per_warp;
+    SDRD_LAUNCH((hbi::interpolate_warp_kernel<NS>), (int)warps, S, 32, hbi::w_smem_bytes(NS), st, w);
+#else
     const int tiles = (int)((p.n_in + hbi::tile_in(NS) - 1) / hbi::tile_in(NS));
     SDRD_LAUNCH((hbi::interpolate_kernel<NS>), tiles, S, hbi::NT, hbi::smem_bytes(NS), st, p);
+#endif
 }
 } /* namespace */
 
