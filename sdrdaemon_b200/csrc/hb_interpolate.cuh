@@ -287,6 +287,9 @@ SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, int2 (&ev)[N],
     }
 }
 
+/* {int16 I, int16 Q} in one byte-permute */
+SDRD_DEVICE uint32_t pack16p(int2 v) { return prmt((uint32_t)v.x, (uint32_t)v.y, 0x5410u); }
+
 struct WarpParams {
     const uint32_t* in;   /* stream s, sample k (k >= -HIST): in[s * in_stride + k] */
     long long in_stride;  /* words */
@@ -299,7 +302,7 @@ struct WarpParams {
 
 /* one stage of the step: reads buffer ST - 1, writes buffer ST (ST < S) or the output (ST == S) */
 template <int S, int ST>
-SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT stage, int lane, uint32_t* SDRD_RESTRICT out, long long n0, long long n_valid,
+SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT stage, int lane, uint32_t* SDRD_RESTRICT out_step, int n_left,
                             int wo, bool emit)
 {
     constexpr int L = ring_len(ST);
@@ -335,7 +338,7 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
             uint4* sg = reinterpret_cast<uint4*>(stage);
 #pragma unroll
             for (int i = 0; i < UL; i++)
-                sg[swz<SWO>(UL * lane + i)] = make_uint4(pack16(ev[2 * i]), pack16(od[2 * i]), pack16(ev[2 * i + 1]), pack16(od[2 * i + 1]));
+                sg[swz<SWO>(UL * lane + i)] = make_uint4(pack16p(ev[2 * i]), pack16p(od[2 * i]), pack16p(ev[2 * i + 1]), pack16p(od[2 * i + 1]));
             SDRD_SYNCWARP();
             uint4 v[UL];
 #pragma unroll
@@ -344,13 +347,14 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
             if (emit) {
 #pragma unroll
                 for (int j = 0; j < UL; j++) {
-                    /* sample n of the cascade is emitted at (n >> S << wo) + (n & (2^S - 1)) */
-                    const long long n = n0 + (long long)(64 * N) * pass + 4 * (32 * j + lane);
+                    /* sample n of the cascade is emitted at (n >> S << wo) + (n & (2^S - 1)); here relative to the
+                     * step's first sample (out_step, n_left: 32-bit offsets) */
+                    const int n = (64 * N) * pass + 4 * (32 * j + lane);
                     if (S >= 2) {
-                        if (n + 4 <= n_valid) *reinterpret_cast<uint4*>(out + ((n >> S) << wo) + (n & ((1 << S) - 1))) = v[j];
+                        if (n + 4 <= n_left) *reinterpret_cast<uint4*>(out_step + ((n >> S) << wo) + (n & ((1 << S) - 1))) = v[j];
                     } else { /* S = 1: two input samples' pairs */
-                        if (n + 2 <= n_valid) *reinterpret_cast<uint2*>(out + ((n >> 1) << wo)) = make_uint2(v[j].x, v[j].y);
-                        if (n + 4 <= n_valid) *reinterpret_cast<uint2*>(out + (((n + 2) >> 1) << wo)) = make_uint2(v[j].z, v[j].w);
+                        if (n + 2 <= n_left) *reinterpret_cast<uint2*>(out_step + ((n >> 1) << wo)) = make_uint2(v[j].x, v[j].y);
+                        if (n + 4 <= n_left) *reinterpret_cast<uint2*>(out_step + (((n + 2) >> 1) << wo)) = make_uint2(v[j].z, v[j].w);
                     }
                 }
             }
@@ -359,7 +363,7 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
 }
 
 #ifndef SDRD_K4_WARPS_PER_SM
-#define SDRD_K4_WARPS_PER_SM 16
+#define SDRD_K4_WARPS_PER_SM 12 /* measured x16: 12 / 16 / 20 / 24 warps -> 0.260 / 0.265 / 0.267 / 0.277 ms */
 #endif
 
 template <int S>
@@ -397,12 +401,15 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
         st_unit(buf + w_off(0), w_hist(0) / 2 + lane, make_int2((int)(int16_t)(cur.x & 0xFFFFu), ((int)cur.x) >> 16),
                 make_int2((int)(int16_t)(cur.y & 0xFFFFu), ((int)cur.y) >> 16));
         SDRD_SYNCWARP();
-        const long long n0 = (step * WC) << S;
-        warp_stage<S, 1>(buf, stage, lane, out, n0, n_valid, wo, emit);
-        if (S >= 2) { SDRD_SYNCWARP(); warp_stage<S, S >= 2 ? 2 : 1>(buf, stage, lane, out, n0, n_valid, wo, emit); }
-        if (S >= 3) { SDRD_SYNCWARP(); warp_stage<S, S >= 3 ? 3 : 1>(buf, stage, lane, out, n0, n_valid, wo, emit); }
-        if (S >= 4) { SDRD_SYNCWARP(); warp_stage<S, S >= 4 ? 4 : 1>(buf, stage, lane, out, n0, n_valid, wo, emit); }
-        if (S >= 5) { SDRD_SYNCWARP(); warp_stage<S, S >= 5 ? 5 : 1>(buf, stage, lane, out, n0, n_valid, wo, emit); }
+        /* where the step's first output sample goes, and how many stage-S samples exist from there on */
+        uint32_t* const out_step = out + ((step * WC) << wo);
+        const long long left = n_valid - ((step * WC) << S);
+        const int n_left = left > (WC << S) ? (WC << S) : (int)left;
+        warp_stage<S, 1>(buf, stage, lane, out_step, n_left, wo, emit);
+        if (S >= 2) { SDRD_SYNCWARP(); warp_stage<S, S >= 2 ? 2 : 1>(buf, stage, lane, out_step, n_left, wo, emit); }
+        if (S >= 3) { SDRD_SYNCWARP(); warp_stage<S, S >= 3 ? 3 : 1>(buf, stage, lane, out_step, n_left, wo, emit); }
+        if (S >= 4) { SDRD_SYNCWARP(); warp_stage<S, S >= 4 ? 4 : 1>(buf, stage, lane, out_step, n_left, wo, emit); }
+        if (S >= 5) { SDRD_SYNCWARP(); warp_stage<S, S >= 5 ? 5 : 1>(buf, stage, lane, out_step, n_left, wo, emit); }
         if (wo > S && emit) { /* interpolate64_cen: 32 zero samples after every 32 (Interpolators.cpp:370,413-603) */
             const int zq = ((1 << wo) - (1 << S)) / 4; /* zero uint4 per input sample */
             for (int i = lane; i < WC * zq; i += 32) {
