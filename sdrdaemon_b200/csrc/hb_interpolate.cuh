@@ -212,11 +212,17 @@ SDRD_KERNEL(NT, 2) interpolate_kernel(Params p)
  * A segment starts with one warm-up step (the cascade looks back 42 input samples, HIST = 64 are there).
  * ------------------------------------------------------------------------------------------------------------ */
 constexpr int WC = 64;
-SDRD_HD constexpr int w_nstep(int s) { return s == 1 ? 2 : s == 2 ? 4 : 8; }
+#ifndef SDRD_K4_N16
+#define SDRD_K4_N16 1 /* stages 4 and 5 take 16 steps per lane (one 128-byte swizzle row per lane and 8 steps) */
+#endif
+SDRD_HD constexpr int w_nstep(int s) { return s == 1 ? 2 : s == 2 ? 4 : (s == 3 || !SDRD_K4_N16) ? 8 : 16; }
 SDRD_HD constexpr int w_passes(int s) { return (WC << (s - 1)) / (32 * w_nstep(s)); }
-SDRD_HD constexpr int w_sw_of_n(int n) { return n == 8 ? 3 : n == 4 ? 1 : 0; }
+SDRD_HD constexpr int w_sw_of_n(int n) { return n == 16 ? 7 : n == 8 ? 3 : n == 4 ? 1 : 0; }
 SDRD_HD constexpr int w_sw(int b) { return w_sw_of_n(w_nstep(b + 1)); }  /* buffer b is read by stage b + 1 */
-SDRD_HD constexpr int w_hist(int b) { return ring_len(b + 1); }          /* = L of the reader: windows start at the task's first step */
+/* history entries in front of buffer b: L of the reader, so that a task's window starts at its first step's unit --
+ * or 16 for a reader with 16 steps per lane, whose windows then start 4 units into a swizzle row of 8 */
+SDRD_HD constexpr int w_hist(int b) { return w_nstep(b + 1) == 16 ? 16 : ring_len(b + 1); }
+SDRD_HD constexpr int w_woff(int b) { return (w_hist(b) - ring_len(b + 1)) / 2; } /* unit of task 0's window */
 SDRD_HD constexpr int w_len(int b) { return (w_hist(b) + (WC << b) + 15) & ~15; }
 SDRD_HD constexpr int w_off(int b)
 {
@@ -240,9 +246,10 @@ SDRD_DEVICE void st_unit(int2* SDRD_RESTRICT buf, int unit, int2 a, int2 b)
     *reinterpret_cast<int4*>(buf + 2 * unit) = make_int4(a.x, a.y, b.x, b.y);
 }
 
-/* N consecutive steps from the window that starts at unit u0 (a multiple of N / 2) of a buffer swizzled for N */
-template <int L, int N>
-SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, int2 (&ev)[N], int2 (&od)[N])
+/* N consecutive steps from the window that starts at unit u0 of a buffer swizzled for N (u0 = N / 2 * task, for
+ * N = 16: 4 + 8 * task); every finished step i is handed to sink(i, ev, od): ev = x[k + i - L/2], od = FIR at k + i */
+template <int L, int N, class Sink>
+SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, Sink&& sink)
 {
     constexpr int SW = w_sw_of_n(N);
     constexpr int T = L / 2;
@@ -251,7 +258,15 @@ SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, int2 (&ev)[N],
     constexpr int C16[4] = SDRD_HB16_ITAPS;
     constexpr int NU = (L + N) / 2; /* units in the window */
     int2 win[L + N];
-    if (SW == 3) {
+    if (SW == 7) {
+        /* u0 = 4 + 8 r: units 4..7 of row r, then rows r + 1, ..; unit low of row r sits at 8 r + (low ^ (r & 7)) */
+#pragma unroll
+        for (int j = 0; j < NU; j++) {
+            const int row = (u0 >> 3) + ((4 + j) >> 3);
+            const int b0 = (row << 3) | (row & 7);
+            ld_unit(buf, b0 ^ ((4 + j) & 7), &win[2 * j]);
+        }
+    } else if (SW == 3) {
         /* chunks of 4 units share one swizzle value: unit 4 hc + i sits at 4 hc + (i ^ g), g = (hc >> 1) & 3 */
 #pragma unroll
         for (int c = 0; c < NU / 4; c++) {
@@ -282,8 +297,7 @@ SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, int2 (&ev)[N],
             ia += ((uint32_t)a.x + (uint32_t)b.x) * (uint32_t)c;
             qa += ((uint32_t)a.y + (uint32_t)b.y) * (uint32_t)c;
         }
-        od[i] = make_int2(asr32(ia, 13), asr32(qa, 13));
-        ev[i] = win[i + L - L / 2];
+        sink(i, win[i + L - L / 2], make_int2(asr32(ia, 13), asr32(qa, 13)));
     }
 }
 
@@ -311,34 +325,35 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
 #pragma unroll 1
     for (int pass = 0; pass < w_passes(ST); pass++) {
         const int task = 32 * pass + lane;
-        int2 ev[N], od[N];
-        fir_steps<L, N>(src, (N / 2) * task, ev, od);
+        const int u0 = w_woff(ST - 1) + (N / 2) * task;
         if (ST < S) {
             constexpr int SWD = w_sw(ST);
             int2* dst = buf + w_off(ST);
-            const int ub = w_hist(ST) / 2 + N * task; /* first unit of the task's 2 N new entries */
-            if (N == 4 && SWD == 3) { /* one chunk of 4 units */
+            const int ub = w_hist(ST) / 2 + N * task; /* first unit of the task's 2 N new entries: one unit per step */
+            if (SWD == 7 && N == 8) { /* one whole swizzle row */
+                const int row = ub >> 3;
+                const int b0 = (row << 3) | (row & 7);
+                fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
+            } else if (N == 4 && SWD == 3) { /* one chunk of 4 units */
                 const int q = ub >> 2;
                 const int b0 = 4 * q + ((q >> 1) & 3);
-#pragma unroll
-                for (int i = 0; i < 4; i++) st_unit(dst, b0 ^ i, ev[i], od[i]);
+                fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
             } else if (N == 2 && SWD == 1) { /* one pair of units */
                 const int q = ub >> 1;
                 const int b0 = 2 * q + ((q >> 2) & 1);
-                st_unit(dst, b0, ev[0], od[0]);
-                st_unit(dst, b0 ^ 1, ev[1], od[1]);
+                fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
             } else {
-#pragma unroll
-                for (int i = 0; i < N; i++) st_unit(dst, swz<SWD>(ub + i), ev[i], od[i]);
+                fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, swz<SWD>(ub + i), ev, od); });
             }
         } else {
             /* last stage: pack to int16 pairs (IQSample::setReal/setImag), through the staging area, whole rows out */
             constexpr int SWO = w_sw_of_n(N);
             constexpr int UL = N / 2; /* 16-byte units per lane */
+            uint32_t wd[2 * N];
+            fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { wd[2 * i] = pack16p(ev); wd[2 * i + 1] = pack16p(od); });
             uint4* sg = reinterpret_cast<uint4*>(stage);
 #pragma unroll
-            for (int i = 0; i < UL; i++)
-                sg[swz<SWO>(UL * lane + i)] = make_uint4(pack16p(ev[2 * i]), pack16p(od[2 * i]), pack16p(ev[2 * i + 1]), pack16p(od[2 * i + 1]));
+            for (int i = 0; i < UL; i++) sg[swz<SWO>(UL * lane + i)] = make_uint4(wd[4 * i], wd[4 * i + 1], wd[4 * i + 2], wd[4 * i + 3]);
             SDRD_SYNCWARP();
             uint4 v[UL];
 #pragma unroll
@@ -417,29 +432,30 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
                 if (k < p.n_in) *reinterpret_cast<uint4*>(out + (k << wo) + (1 << S) + 4 * (i % zq)) = make_uint4(0u, 0u, 0u, 0u);
             }
         }
-        /* histories: the last L entries of every buffer move to its front (units: 16, 8, 4, 4, 4) */
+        /* histories: the last w_hist(b) entries of every buffer move to its front (16, 8, 4, 4..8 units) */
         SDRD_SYNCWARP();
         {
-            int b = lane < 16 ? 0 : lane < 24 ? 1 : lane < 28 ? 2 : 3;
-            int j = lane < 16 ? lane : lane < 24 ? lane - 16 : lane < 28 ? lane - 24 : lane - 28;
-            int4 v = make_int4(0, 0, 0, 0), v4 = make_int4(0, 0, 0, 0);
-            const bool on = b < S;
-#define SDRD_K4_TL(B, OP)                                                                                              \
-            if (b == (B) && (B) < S) { constexpr int SWB = w_sw((B) < S ? (B) : 0); int2* bb = buf + w_off((B) < S ? (B) : 0); \
-                const int su = (WC << (B)) / 2 + j; OP }
-            SDRD_K4_TL(0, v = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
-            SDRD_K4_TL(1, v = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
-            SDRD_K4_TL(2, v = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
-            SDRD_K4_TL(3, v = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
-            if (S == 5 && lane < 4) v4 = *reinterpret_cast<const int4*>(buf + w_off(S == 5 ? 4 : 0) + 2 * swz<3>((WC << 4) / 2 + lane));
+            int4 hv[5];
+#define SDRD_K4_TL(B, OP)                                                                                      \
+            if ((B) < S && lane < w_hist((B) < S ? (B) : 0) / 2) {                                             \
+                constexpr int BB = (B) < S ? (B) : 0;                                                          \
+                constexpr int SWB = w_sw(BB);                                                                  \
+                int2* bb = buf + w_off(BB);                                                                    \
+                const int su = (WC << BB) / 2 + lane;                                                          \
+                OP                                                                                             \
+            }
+            SDRD_K4_TL(0, hv[0] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            SDRD_K4_TL(1, hv[1] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            SDRD_K4_TL(2, hv[2] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            SDRD_K4_TL(3, hv[3] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            SDRD_K4_TL(4, hv[4] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
             SDRD_SYNCWARP();
-            SDRD_K4_TL(0, *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(j)) = v;)
-            SDRD_K4_TL(1, *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(j)) = v;)
-            SDRD_K4_TL(2, *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(j)) = v;)
-            SDRD_K4_TL(3, *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(j)) = v;)
-            if (S == 5 && lane < 4) *reinterpret_cast<int4*>(buf + w_off(S == 5 ? 4 : 0) + 2 * swz<3>(lane)) = v4;
+            SDRD_K4_TL(0, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[0];)
+            SDRD_K4_TL(1, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[1];)
+            SDRD_K4_TL(2, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[2];)
+            SDRD_K4_TL(3, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[3];)
+            SDRD_K4_TL(4, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[4];)
 #undef SDRD_K4_TL
-            (void)on;
         }
         SDRD_SYNCWARP();
     }
