@@ -248,7 +248,10 @@ SDRD_DEVICE void st_unit(int2* SDRD_RESTRICT buf, int unit, int2 a, int2 b)
 
 /* N consecutive steps from the window that starts at unit u0 of a buffer swizzled for N (u0 = N / 2 * task, for
  * N = 16: 4 + 8 * task); every finished step i is handed to sink(i, ev, od): ev = x[k + i - L/2], od = FIR at k + i */
-template <int L, int N, class Sink>
+#ifndef SDRD_K4_PACKED_X0
+#define SDRD_K4_PACKED_X0 1 /* buffer 0 keeps the raw {int16 I, int16 Q} words (half the window bytes of stage 1), sign-extended in registers */
+#endif
+template <int L, int N, bool PACKED = false, class Sink>
 SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, Sink&& sink)
 {
     constexpr int SW = w_sw_of_n(N);
@@ -258,7 +261,16 @@ SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, Sink&& sink)
     constexpr int C16[4] = SDRD_HB16_ITAPS;
     constexpr int NU = (L + N) / 2; /* units in the window */
     int2 win[L + N];
-    if (SW == 7) {
+    if (PACKED) {
+        /* entry e of buffer 0 is the 32-bit word e: the window is NU 8-byte loads, 8 bytes apart from lane to lane */
+        const uint2* rw = reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(buf) + 2 * u0);
+#pragma unroll
+        for (int j = 0; j < NU; j++) {
+            const uint2 r = rw[j];
+            win[2 * j] = make_int2((int)(int16_t)(r.x & 0xFFFFu), ((int)r.x) >> 16);
+            win[2 * j + 1] = make_int2((int)(int16_t)(r.y & 0xFFFFu), ((int)r.y) >> 16);
+        }
+    } else if (SW == 7) {
         /* u0 = 4 + 8 r: units 4..7 of row r, then rows r + 1, ..; unit low of row r sits at 8 r + (low ^ (r & 7)) */
 #pragma unroll
         for (int j = 0; j < NU; j++) {
@@ -321,6 +333,7 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
 {
     constexpr int L = ring_len(ST);
     constexpr int N = w_nstep(ST);
+    constexpr bool PK = ST == 1 && SDRD_K4_PACKED_X0;
     const int2* src = buf + w_off(ST - 1);
 #pragma unroll 1
     for (int pass = 0; pass < w_passes(ST); pass++) {
@@ -333,24 +346,24 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
             if (SWD == 7 && N == 8) { /* one whole swizzle row */
                 const int row = ub >> 3;
                 const int b0 = (row << 3) | (row & 7);
-                fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
+                fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
             } else if (N == 4 && SWD == 3) { /* one chunk of 4 units */
                 const int q = ub >> 2;
                 const int b0 = 4 * q + ((q >> 1) & 3);
-                fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
+                fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
             } else if (N == 2 && SWD == 1) { /* one pair of units */
                 const int q = ub >> 1;
                 const int b0 = 2 * q + ((q >> 2) & 1);
-                fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
+                fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
             } else {
-                fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, swz<SWD>(ub + i), ev, od); });
+                fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, swz<SWD>(ub + i), ev, od); });
             }
         } else {
             /* last stage: pack to int16 pairs (IQSample::setReal/setImag), through the staging area, whole rows out */
             constexpr int SWO = w_sw_of_n(N);
             constexpr int UL = N / 2; /* 16-byte units per lane */
             uint32_t wd[2 * N];
-            fir_steps<L, N>(src, u0, [&](int i, int2 ev, int2 od) { wd[2 * i] = pack16p(ev); wd[2 * i + 1] = pack16p(od); });
+            fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { wd[2 * i] = pack16p(ev); wd[2 * i + 1] = pack16p(od); });
             uint4* sg = reinterpret_cast<uint4*>(stage);
 #pragma unroll
             for (int i = 0; i < UL; i++) sg[swz<SWO>(UL * lane + i)] = make_uint4(wd[4 * i], wd[4 * i + 1], wd[4 * i + 2], wd[4 * i + 3]);
@@ -413,8 +426,11 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
         const uint2 cur = nxt;
         if (step + 1 < last) nxt = fetch(step + 1);
         const bool emit = step >= first; /* the first step only fills the histories */
-        st_unit(buf + w_off(0), w_hist(0) / 2 + lane, make_int2((int)(int16_t)(cur.x & 0xFFFFu), ((int)cur.x) >> 16),
-                make_int2((int)(int16_t)(cur.y & 0xFFFFu), ((int)cur.y) >> 16));
+        if (SDRD_K4_PACKED_X0)
+            reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(buf + w_off(0)) + w_hist(0))[lane] = cur;
+        else
+            st_unit(buf + w_off(0), w_hist(0) / 2 + lane, make_int2((int)(int16_t)(cur.x & 0xFFFFu), ((int)cur.x) >> 16),
+                    make_int2((int)(int16_t)(cur.y & 0xFFFFu), ((int)cur.y) >> 16));
         SDRD_SYNCWARP();
         /* where the step's first output sample goes, and how many stage-S samples exist from there on */
         uint32_t* const out_step = out + ((step * WC) << wo);
@@ -444,13 +460,21 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
                 const int su = (WC << BB) / 2 + lane;                                                          \
                 OP                                                                                             \
             }
-            SDRD_K4_TL(0, hv[0] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            if (SDRD_K4_PACKED_X0) { /* 32 history words = 8 units of raw words */
+                if (lane < w_hist(0) / 4) hv[0] = reinterpret_cast<const int4*>(reinterpret_cast<const uint32_t*>(buf + w_off(0)) + WC)[lane];
+            } else {
+                SDRD_K4_TL(0, hv[0] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
+            }
             SDRD_K4_TL(1, hv[1] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
             SDRD_K4_TL(2, hv[2] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
             SDRD_K4_TL(3, hv[3] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
             SDRD_K4_TL(4, hv[4] = *reinterpret_cast<const int4*>(bb + 2 * swz<SWB>(su));)
             SDRD_SYNCWARP();
-            SDRD_K4_TL(0, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[0];)
+            if (SDRD_K4_PACKED_X0) {
+                if (lane < w_hist(0) / 4) reinterpret_cast<int4*>(buf + w_off(0))[lane] = hv[0];
+            } else {
+                SDRD_K4_TL(0, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[0];)
+            }
             SDRD_K4_TL(1, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[1];)
             SDRD_K4_TL(2, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[2];)
             SDRD_K4_TL(3, (void)su; *reinterpret_cast<int4*>(bb + 2 * swz<SWB>(lane)) = hv[3];)
