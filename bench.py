@@ -406,7 +406,7 @@ def run_interp(args):
                                              f"{n_out * 4 / 1e6:.0f} MB out per step", "parity": parity,
                                  "l2": "outputs larger than L2 (no flush needed)"},
                       "gpu_launches": int(u.launches - l0),
-                      "roofline": {"bound": "hbm", "kernel": f"hbi::interpolate_kernel<{min(M, 5)}> (K4)", "achieved": round(alg / ms / 1e6, 1),
+                      "roofline": {"bound": "hbm", "kernel": f"hbi::interpolate_warp_kernel<{min(M, 5)}> (K4)", "achieved": round(alg / ms / 1e6, 1),
                                    "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": None,
                                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}}), flush=True)
 
