@@ -15,7 +15,9 @@
  * Reference quirk, reproduced: interpolate64_cen runs the five stages of interpolate32_cen and then
  * emits 64 samples per input sample of which the last 32 are zero (Interpolators.cpp:363-605).
  *
- * Design: the cascade's receptive field is short (42 input samples of history for five stages), so a
+ * Two kernels: the warp-private, barrier-free interpolate_warp_kernel (the product path, second half of this file)
+ * and the CTA-wide tiled interpolate_kernel below (kept for interp = 6 and for A/B runs).
+ * Tiled design: the cascade's receptive field is short (42 input samples of history for five stages), so a
  * CTA takes a tile of K = 4096 >> S input samples plus that halo, runs stage after stage through
  * shared memory as int32 {I, Q} pairs (two output pairs per thread from one register window,
  * conflict-free 16-byte shared loads),
