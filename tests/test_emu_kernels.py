@@ -53,6 +53,12 @@ def test_interpolator(emu_lib, oracle, M):
     cases.check_interpolator(emu_lib, oracle, M, x, [0, 1, 1, 40, 1300, n])  # single sample, empty, shorter than the history
 
 
+def test_interpolator_many_streams_segments(emu_lib, oracle):
+    rng = np.random.default_rng(850)
+    for M, S, n in [(4, 300, 200), (5, 40, 64 * 5 + 1), (2, 1900, 70)]:
+        cases.check_interpolator(emu_lib, oracle, M, cases.rand_iq(rng, (S, n)), [0, n // 3, n])
+
+
 def test_interpolator_golden_and_classes(emu_lib, oracle):
     import golden_cases
     from sdrdaemon_b200 import capi

@@ -127,6 +127,15 @@ def test_interpolator(gpu_lib, oracle, M):
     cases.check_interpolator(gpu_lib, oracle, M, x, [0, 1, 1, 40, 4096 + 17, n])  # single sample, empty, ragged tiles
 
 
+@pytest.mark.parametrize("M,S,n", [(4, 300, 1000), (5, 40, 64 * 37 + 1), (1, 7, 64 * 600 - 1), (3, 2000, 130)])
+def test_interpolator_many_streams_segments(gpu_lib, oracle, M, S, n):
+    """the warp-private K4: warps take contiguous ranges of 64-sample steps of one stream (each with a warm-up
+    step); few long, many short and ragged streams, state carried over two calls"""
+    rng = np.random.default_rng(950 + M)
+    x = cases.rand_iq(rng, (S, n))
+    cases.check_interpolator(gpu_lib, oracle, M, x, [0, n // 3, n])
+
+
 def test_interpolator_input_classes_and_reconfigure(gpu_lib, oracle):
     rng = np.random.default_rng(901)
     for name, x in cases.input_classes(rng, 8192).items():
