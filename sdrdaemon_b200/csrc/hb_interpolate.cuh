@@ -232,7 +232,11 @@ SDRD_HD constexpr int w_off(int b)
     for (int t = 0; t < b; t++) o += w_len(t);
     return o;
 }
-SDRD_HD constexpr int w_stage_words(int S) { return 64 * w_nstep(S); } /* one pass of the last stage: 32 lanes x 2 N samples */
+#ifndef SDRD_K4_TMA_STORE
+#define SDRD_K4_TMA_STORE 0 /* 1: every lane sends its own row of 2 N samples with one TMA bulk store instead of the staging read-back + STG.  Measured, bit-exact and SLOWER (x16 0.262 vs 0.232 ms, x2 1.08 vs 0.47 ms): a bulk copy is a uniform-datapath instruction, 32 per-lane copies are issued one lane after the other.  The form that would pay is ONE tensor-map store per pass from a 128B-swizzled staging tile. */
+#endif
+SDRD_HD constexpr int w_stage_pitch(int S) { return 2 * w_nstep(S) + 4; } /* words between the rows of two lanes (TMA form) */
+SDRD_HD constexpr int w_stage_words(int S) { return SDRD_K4_TMA_STORE ? 32 * w_stage_pitch(S) : 64 * w_nstep(S); } /* one pass of the last stage: 32 lanes x 2 N samples */
 SDRD_HD constexpr size_t w_smem_bytes(int S) { return (size_t)w_off(S) * 8 + (size_t)w_stage_words(S) * 4; }
 
 template <int SW>
@@ -366,6 +370,28 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
             constexpr int UL = N / 2; /* 16-byte units per lane */
             uint32_t wd[2 * N];
             fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { wd[2 * i] = pack16p(ev); wd[2 * i + 1] = pack16p(od); });
+#if SDRD_K4_TMA_STORE
+            /* the lane's 2 N samples are one contiguous run of the output (a row never straddles a group of 2^S when
+             * S >= 2; S = 1: two pairs, contiguous because wo = S): written to the lane's own padded row of the staging
+             * area (pitch 2 N + 4 words: conflict-free) and sent with one bulk store that bypasses the LSU data pipe */
+            (void)SWO;
+            uint32_t* row = stage + w_stage_pitch(S) * lane;
+            tma_store_wait_read(); /* the previous pass's store has read this row */
+#pragma unroll
+            for (int i = 0; i < UL; i++) reinterpret_cast<uint4*>(row)[i] = make_uint4(wd[4 * i], wd[4 * i + 1], wd[4 * i + 2], wd[4 * i + 3]);
+            fence_proxy_async_smem();
+            if (emit) {
+                const int n = (64 * N) * pass + 2 * N * lane; /* relative to the step's first sample */
+                uint32_t* dst = out_step + ((n >> S) << wo) + (n & ((1 << S) - 1));
+                if (n + 2 * N <= n_left) {
+                    tma_store_1d(dst, row, 8 * N);
+                    tma_store_commit();
+                } else { /* the ragged end of the stream (S = 1 .. 3: a row covers several input samples) */
+                    for (int w = 0; w < 2 * N; w++)
+                        if (n + w < n_left) dst[w] = row[w];
+                }
+            }
+#else
             uint4* sg = reinterpret_cast<uint4*>(stage);
 #pragma unroll
             for (int i = 0; i < UL; i++) sg[swz<SWO>(UL * lane + i)] = make_uint4(wd[4 * i], wd[4 * i + 1], wd[4 * i + 2], wd[4 * i + 3]);
@@ -388,6 +414,7 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
                     }
                 }
             }
+#endif
         }
     }
 }
@@ -485,6 +512,7 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
         }
         SDRD_SYNCWARP();
     }
+    if (SDRD_K4_TMA_STORE) tma_store_wait_read(); /* the staging rows stay allocated until the last bulk store has read them */
 }
 
 } /* namespace hbi */

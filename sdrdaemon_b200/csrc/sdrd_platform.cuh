@@ -126,6 +126,11 @@ static inline void mbar_wait(mbar_t* b, uint32_t parity)
 {
     while (((uint32_t)b->load(std::memory_order_acquire) & 1u) == parity) std::this_thread::yield();
 }
+/* TMA 1-D bulk copy shared -> global (bulk async-group): in the emulation a plain copy, complete at once */
+static inline void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) { memcpy(dst_gmem, src_smem, bytes); }
+static inline void tma_store_commit() {}
+static inline void tma_store_wait_read() {}
+static inline void fence_proxy_async_smem() {}
 } /* namespace sdrd */
 
 #else
@@ -174,6 +179,17 @@ SDRD_DEVICE void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t byte
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(b))
         : "memory");
 }
+/* TMA 1-D bulk copy shared -> global of this thread's own bytes (SASS: UBLKCP.G.S): the store does not pass
+ * through the LSU data pipe.  fence_proxy_async_smem() after the generic-proxy writes of the source, then the copy,
+ * tma_store_commit(), and tma_store_wait_read() before the source is written again. */
+SDRD_DEVICE void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+SDRD_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+SDRD_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+SDRD_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 SDRD_DEVICE void mbar_wait(mbar_t* b, uint32_t parity)
 {
     uint32_t a = smem_u32(b);
