@@ -420,7 +420,7 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
 }
 
 #ifndef SDRD_K4_WARPS_PER_SM
-#define SDRD_K4_WARPS_PER_SM 12 /* measured x16: 12 / 16 / 20 / 24 warps -> 0.260 / 0.265 / 0.267 / 0.277 ms */
+#define SDRD_K4_WARPS_PER_SM 12 /* measured x16, final form: 8 / 10 / 11 / 12 / 13 / 14 / 16 warps -> 0.234 / 0.257 / 0.242 / 0.232 / 0.269 / 0.254 / 0.233 ms (whole warps per scheduler; 2 per scheduler already reach the rate) */
 #endif
 
 template <int S>
