@@ -70,8 +70,11 @@ int sdrd_dec_create(sdrd_dec** dec, int log2_decim, int fcpos, int variant, int 
 void sdrd_dec_destroy(sdrd_dec* dec);
 /* Forget all filter state (a freshly constructed Decimators, include/Decimators.h:57-62). */
 int sdrd_dec_reset(sdrd_dec* dec);
-/* Downsampler::configure (Downsampler.cpp:32-67): change decim / fcpos between blocks.  Filter
- * history is kept as the raw input history, so the new cascade continues without a gap. */
+/* Downsampler::configure (Downsampler.cpp:32-67): change decim / fcpos between blocks.  As in the
+ * reference, only m_decim / m_fcPos change: the six half-band stage objects persist
+ * (include/Decimators.h:57-62), so a stage the new cascade uses continues from the state it was left in
+ * under an earlier configuration (zeros if it never ran) -- the first outputs after a change are
+ * bit-identical to the reference's.  Waits for the handle's pending work. */
 int sdrd_dec_configure(sdrd_dec* dec, int log2_decim, int fcpos);
 int sdrd_dec_log2_decim(const sdrd_dec* dec);
 
@@ -107,8 +110,8 @@ int sdrd_int_create(sdrd_int** up, int log2_interp, int n_streams, size_t max_in
 void sdrd_int_destroy(sdrd_int* up);
 /* Forget all filter state (a freshly constructed Interpolators, include/Interpolators.h:52-58). */
 int sdrd_int_reset(sdrd_int* up);
-/* Upsampler::configure (Upsampler.cpp:32-55): change interp between blocks; the filter state is kept
- * as input history, the new cascade continues from it. */
+/* Upsampler::configure (Upsampler.cpp:32-55): change interp between blocks.  The stage objects persist
+ * (include/Interpolators.h:52-58) exactly as for sdrd_dec_configure. */
 int sdrd_int_configure(sdrd_int* up, int log2_interp);
 int sdrd_int_log2_interp(const sdrd_int* up);
 /* Upsampler::process (include/Upsampler.h:50) for n_streams streams at once: iq_out receives

@@ -53,6 +53,10 @@ def lib() -> C.CDLL:
         L.sdro_dec_create.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sdro_dec_destroy.argtypes = [C.c_void_p]
         L.sdro_dec_reset.argtypes = [C.c_void_p]
+        L.sdro_dec_configure.restype = C.c_int
+        L.sdro_dec_configure.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.sdro_int_configure.restype = C.c_int
+        L.sdro_int_configure.argtypes = [C.c_void_p, C.c_int]
         L.sdro_int_create.restype = C.c_void_p
         L.sdro_int_create.argtypes = [C.c_int]
         L.sdro_int_destroy.argtypes = [C.c_void_p]
@@ -121,6 +125,12 @@ class Decimator:
     def reset(self) -> None:
         lib().sdro_dec_reset(self._h)
 
+    def configure(self, log2_decim: int, fcpos: int = FC_CENTER) -> None:
+        """Downsampler::configure between blocks: the six stage objects keep their state."""
+        if lib().sdro_dec_configure(self._h, log2_decim, fcpos):
+            raise ValueError("Invalid log2 decimation factor / Fc position index")
+        self.log2_decim = log2_decim
+
     def process(self, iq: np.ndarray, sample_bits: int = 16) -> Tuple[np.ndarray, int]:
         iq = _iq(iq)
         out = np.zeros((max(len(iq) >> self.log2_decim, 1) + 1, 2), dtype=np.int16)
@@ -145,6 +155,12 @@ class Interpolator:
 
     def reset(self) -> None:
         lib().sdro_int_reset(self._h)
+
+    def configure(self, log2_interp: int) -> None:
+        """Upsampler::configure between blocks: the stage objects keep their state."""
+        if lib().sdro_int_configure(self._h, log2_interp):
+            raise ValueError("Invalid log2 interpolation factor")
+        self.log2_interp = log2_interp
 
     def process(self, iq: np.ndarray) -> np.ndarray:
         iq = _iq(iq)
@@ -276,6 +292,10 @@ def ref(variant: int = HB_EO1) -> C.CDLL:
         L.ref_ds_destroy.argtypes = [C.c_void_p]
         L.ref_ds_process.restype = C.c_size_t
         L.ref_ds_process.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ref_ds_configure.restype = C.c_int
+        L.ref_ds_configure.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_us_configure.restype = C.c_int
+        L.ref_us_configure.argtypes = [C.c_void_p, C.c_int]
         L.ref_ds_process_streams.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
                                              C.c_size_t]
         L.ref_us_create.restype = C.c_void_p
@@ -314,6 +334,11 @@ class RefDownsampler:
             self._L.ref_ds_destroy(self._h)
             self._h = None
 
+    def configure(self, log2_decim: int, fcpos: int = FC_CENTER) -> None:
+        if not self._L.ref_ds_configure(self._h, log2_decim, fcpos):
+            raise ValueError("the reference refused decim/fcpos")
+        self.log2_decim = log2_decim
+
     def process(self, iq: np.ndarray, sample_bits: int = 16) -> Tuple[np.ndarray, int]:
         iq = _iq(iq)
         out = np.zeros((max(len(iq) >> self.log2_decim, 1) + 1, 2), dtype=np.int16)
@@ -334,6 +359,11 @@ class RefUpsampler:
         if getattr(self, "_h", None):
             self._L.ref_us_destroy(self._h)
             self._h = None
+
+    def configure(self, log2_interp: int) -> None:
+        if not self._L.ref_us_configure(self._h, log2_interp):
+            raise ValueError("the reference refused interp")
+        self.log2_interp = log2_interp
 
     def process(self, iq: np.ndarray) -> np.ndarray:
         iq = _iq(iq)

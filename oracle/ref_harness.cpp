@@ -70,10 +70,36 @@ size_t ref_ds_process(void* h, unsigned* sample_bits, const int16_t* iq_in, size
     return out.size();
 }
 
+/* Downsampler::configure (sdmnbase/Downsampler.cpp:32-67) with the key/value pairs the control port would
+ * deliver ("decim=..,fcpos=.."); returns 1 when the reference accepted them. */
+int ref_ds_configure(void* h, int log2_decim, int fcpos)
+{
+    parsekv::pairs_type m;
+    m["decim"] = std::to_string(log2_decim);
+    m["fcpos"] = std::to_string(fcpos);
+    std::ostringstream quiet; /* the reference logs every key to std::cerr */
+    std::streambuf* old = std::cerr.rdbuf(quiet.rdbuf());
+    const bool ok = ((Downsampler*)h)->configure(m);
+    std::cerr.rdbuf(old);
+    return ok ? 1 : 0;
+}
+
 /* ------------------------------------------------------------------ Upsampler ---- */
 
 void* ref_us_create(int log2_interp) { return new Upsampler((unsigned)log2_interp); }
 void ref_us_destroy(void* h) { delete (Upsampler*)h; }
+
+/* Upsampler::configure (sdmnbase/Upsampler.cpp:32-55) */
+int ref_us_configure(void* h, int log2_interp)
+{
+    parsekv::pairs_type m;
+    m["interp"] = std::to_string(log2_interp);
+    std::ostringstream quiet;
+    std::streambuf* old = std::cerr.rdbuf(quiet.rdbuf());
+    const bool ok = ((Upsampler*)h)->configure(m);
+    std::cerr.rdbuf(old);
+    return ok ? 1 : 0;
+}
 
 /* Upsampler::process, include/Upsampler.h:50.  Returns samples_out.size(). */
 size_t ref_us_process(void* h, const int16_t* iq_in, size_t n_in, int16_t* iq_out)

@@ -78,6 +78,16 @@ sdro_dec* sdro_dec_create(int log2_decim, int fcpos, int variant)
 }
 void sdro_dec_destroy(sdro_dec* d) { free(d); }
 void sdro_dec_reset(sdro_dec* d) { for (int i = 0; i < 6; i++) hb_reset(&d->stage[i]); }
+/* Downsampler::configure (Downsampler.cpp:32-67): only m_decim / m_fcPos change.  The six stage objects
+ * of m_decimators persist (Decimators.h:57-62): a stage the new cascade uses continues from whatever it
+ * last saw -- its state of the previous configuration, or zeros if it never ran. */
+int sdro_dec_configure(sdro_dec* d, int log2_decim, int fcpos)
+{
+    if (log2_decim < 0 || log2_decim > 6 || fcpos < 0 || fcpos > 2) return -1;
+    d->log2_decim = log2_decim;
+    d->fcpos = fcpos;
+    return 0;
+}
 
 /* feed one sample into stage k of an n_stages cascade; returns 1 when the cascade emitted */
 static int cascade_feed(sdro_dec* d, int k, int n_stages, int32_t i, int32_t q, int32_t* oi, int32_t* oq)
@@ -743,6 +753,14 @@ sdro_int* sdro_int_create(int log2_interp)
     return u;
 }
 void sdro_int_destroy(sdro_int* u) { free(u); }
+/* Upsampler::configure (Upsampler.cpp:32-55): only m_interp changes; the stage objects of
+ * m_interpolators persist (Interpolators.h:52-58). */
+int sdro_int_configure(sdro_int* u, int log2_interp)
+{
+    if (log2_interp < 0 || log2_interp > 6) return -1;
+    u->log2_interp = log2_interp;
+    return 0;
+}
 void sdro_int_reset(sdro_int* u)
 {
     static const int orders[6] = {64, 32, 16, 16, 16, 16}; /* Interpolators.h:31-33 */

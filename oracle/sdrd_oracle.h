@@ -43,6 +43,8 @@ typedef struct sdro_dec sdro_dec;
 sdro_dec* sdro_dec_create(int log2_decim, int fcpos, int variant);
 void      sdro_dec_destroy(sdro_dec* d);
 void      sdro_dec_reset(sdro_dec* d);
+/* Downsampler::configure (Downsampler.cpp:32-67) between blocks: stage states persist. 0 = ok. */
+int       sdro_dec_configure(sdro_dec* d, int log2_decim, int fcpos);
 /* Downsampler::process (Downsampler.cpp:74-162).  iq_in: n_in interleaved {I,Q} int16 samples.
  * Writes n_in >> log2_decim samples to iq_out, returns that count.  *sample_bits is the
  * reference's in/out sampleSize. Samples beyond the last whole group of 2^M are dropped
@@ -59,6 +61,8 @@ typedef struct sdro_int sdro_int;
 sdro_int* sdro_int_create(int log2_interp);
 void      sdro_int_destroy(sdro_int* u);
 void      sdro_int_reset(sdro_int* u);
+/* Upsampler::configure (Upsampler.cpp:32-55) between blocks: stage states persist. 0 = ok. */
+int       sdro_int_configure(sdro_int* u, int log2_interp);
 /* Upsampler::process (Upsampler.cpp:57-84) -> Interpolators::interpolate{2..64}_cen
  * (Interpolators.cpp:23-606).  Writes n_in << log2_interp samples, returns that count. */
 size_t    sdro_int_process(sdro_int* u, const int16_t* iq_in, size_t n_in, int16_t* iq_out);

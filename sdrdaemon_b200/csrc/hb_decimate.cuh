@@ -471,6 +471,117 @@ SDRD_KERNEL(32, SDRD_K1_WARPS_PER_SM) decimate_warp_kernel(Params p)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Explicit per-stage state: the reference keeps six persistent stage objects m_decimator2 ..
+ * m_decimator64 (include/Decimators.h:57-62) and cascade position k always runs object k
+ * (Decimators.cpp:189-201, 290-322, 356-359 ...).  While the configuration does not change, the state of
+ * every active stage is a function of the raw input history and decimate_warp_kernel re-derives it
+ * from there.  After Downsampler::configure (Downsampler.cpp:32-67) that is no longer true: a stage the
+ * new cascade uses continues from whatever it saw last -- under the previous configuration, possibly long
+ * ago, or never (zeros).  stateful_kernel runs the cascade from explicit stage states
+ *     state[stream][stage 0..5][component I/Q][64]  =  the stage's last 64 inputs, oldest first
+ * (what m_even/m_odd of IntHalfbandFilterEO1.h:68-69 resp. m_samples of IntHalfbandFilterDB.h:73 hold)
+ * and writes them back.  The library uses it for the first SDRD_DEC_HEAD raw samples after a reconfiguration
+ * (from then on every value the cascade can still reach was computed from samples of the new run, and the
+ * warp kernel takes over) and, with out == nullptr, to turn the raw history into explicit states when a
+ * configuration is left.  One CTA per stream, chunks of SCH cascade inputs through shared memory; a few
+ * thousand samples per stream and reconfiguration, so simplicity counts here, not speed.
+ * ------------------------------------------------------------------------------------------ */
+constexpr int SNT = 256;    /* threads per CTA */
+constexpr int SCH = 1024;   /* cascade-input samples per chunk */
+constexpr int SST = 64;     /* state entries per stage and component */
+constexpr int STATE_WORDS = 6 * 2 * SST; /* per stream */
+SDRD_HD constexpr int sbuf_off(int k) { return k == 0 ? 0 : sbuf_off(k - 1) + 2 * (SST + (SCH >> (k - 1))); }
+SDRD_HD constexpr size_t stateful_smem_bytes() { return (size_t)sbuf_off(6) * 4; }
+
+struct StateParams {
+    const uint32_t* in;    /* stream s, raw sample i: in[s * in_stride + i] */
+    long long in_stride;
+    uint32_t* out;         /* out[s * out_stride + n], or nullptr: only the states are wanted */
+    long long out_stride;
+    int* state;            /* [n_streams][STATE_WORDS] */
+    long long n_casc;      /* cascade-input samples per stream (raw / 4 with the prologue); a multiple of 2^M */
+    int M;                 /* half-band stages 1..6 */
+    int round_add, norm_shift, trunk_shift, prologue;
+};
+
+SDRD_KERNEL(SNT, 1) stateful_kernel(StateParams p)
+{
+    constexpr int H[16] = SDRD_HB64_TAPS;
+    SDRD_DYN_SMEM(smem);
+    int* const buf = reinterpret_cast<int*>(smem);
+    const int tid = (int)threadIdx.x;
+    const int s = (int)blockIdx.x;
+    const int M = p.M;
+    const uint32_t* in = p.in + (long long)s * p.in_stride;
+    int* state = p.state + (long long)s * STATE_WORDS;
+    /* buffer of stage k's input, component c: [SST state | chunk >> k] */
+    auto B = [&](int k, int c) -> int* { return buf + sbuf_off(k) + c * (SST + (SCH >> k)); };
+
+    for (int i = tid; i < M * 2 * SST; i += SNT) {
+        const int k = i / (2 * SST), c = (i / SST) & 1, j = i % SST;
+        B(k, c)[j] = state[(k * 2 + c) * SST + j];
+    }
+    __syncthreads();
+    for (long long c0 = 0; c0 < p.n_casc; c0 += SCH) {
+        const int len = (int)(p.n_casc - c0 < SCH ? p.n_casc - c0 : SCH);
+        for (int i = tid; i < len; i += SNT) {
+            int xi, xq;
+            if (p.prologue) {
+                const int2 r = rot4(reinterpret_cast<const uint4*>(in)[c0 + i], p.prologue);
+                xi = r.x; xq = r.y;
+            } else {
+                const uint32_t v = in[c0 + i];
+                xi = s16lo(v); xq = s16hi(v);
+            }
+            B(0, 0)[SST + i] = xi;
+            B(0, 1)[SST + i] = xq;
+        }
+        __syncthreads();
+        for (int k = 0; k < M; k++) {
+            const int nk = len >> (k + 1);
+            for (int n = tid; n < nk; n += SNT) {
+                int y[2];
+                for (int c = 0; c < 2; c++) {
+                    const int* x = B(k, c) + SST; /* x[j], j >= -SST */
+                    uint32_t acc = 0;
+                    for (int t = 0; t < 16; t++) acc += ((uint32_t)x[2 * n + 1 - 2 * t] + (uint32_t)x[2 * n - 61 + 2 * t]) * (uint32_t)H[t];
+                    acc += ((uint32_t)x[2 * n - 30] + (uint32_t)p.round_add) << HB_SHIFT;
+                    y[c] = asr32(acc, HB_SHIFT);
+                }
+                if (k + 1 < M) {
+                    B(k + 1, 0)[SST + n] = y[0];
+                    B(k + 1, 1)[SST + n] = y[1];
+                } else if (p.out) {
+                    const uint32_t a = (uint32_t)asr32((uint32_t)y[0] << p.norm_shift, p.trunk_shift);
+                    const uint32_t b = (uint32_t)asr32((uint32_t)y[1] << p.norm_shift, p.trunk_shift);
+                    p.out[(long long)s * p.out_stride + (c0 >> M) + n] = (a & 0xFFFFu) | (b << 16);
+                }
+            }
+            __syncthreads();
+        }
+        /* the last SST inputs of every stage become its state: read, barrier, write (the ranges overlap when a
+         * stage got fewer than SST inputs) */
+        int keep[6 * 2 * SST / SNT];
+        for (int r = 0; r < 6 * 2 * SST / SNT; r++) {
+            const int i = tid + r * SNT;
+            const int k = i / (2 * SST), c = (i / SST) & 1, j = i % SST;
+            keep[r] = k < M ? B(k, c)[(len >> k) + j] : 0;
+        }
+        __syncthreads();
+        for (int r = 0; r < 6 * 2 * SST / SNT; r++) {
+            const int i = tid + r * SNT;
+            const int k = i / (2 * SST), c = (i / SST) & 1, j = i % SST;
+            if (k < M) B(k, c)[j] = keep[r];
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < M * 2 * SST; i += SNT) {
+        const int k = i / (2 * SST), c = (i / SST) & 1, j = i % SST;
+        state[(k * 2 + c) * SST + j] = B(k, c)[j];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Filter-less routines of the reference: decimate1 (Decimators.cpp:22-35, left-justify sources
  * with fewer than 16 bits), decimate2_inf/sup (:38-91) and decimate4_inf/sup (:127-170).
  * Element-wise, HBM-bound; one thread per output group.

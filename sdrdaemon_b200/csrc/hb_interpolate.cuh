@@ -198,6 +198,114 @@ SDRD_KERNEL(NT, 2) interpolate_kernel(Params p)
 
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Explicit per-stage state (the Tx twin of hb::stateful_kernel): the reference keeps persistent stage objects
+ * m_interpolator2 .. m_interpolator64 (include/Interpolators.h:52-58), cascade position k always runs object k
+ * (Interpolators.cpp:36, 60-63, 93-101 ...; object 6 is never used, see the interpolate64_cen quirk above).  After
+ * Upsampler::configure (Upsampler.cpp:32-55) a stage the new cascade uses continues from what it saw last under
+ * the previous configuration (or zeros).  i_stateful_kernel runs the cascade from
+ *     state[stream][stage 0..4][component I/Q][32]  =  the stage's last 32 inputs, oldest first (m_samples)
+ * and writes the states back; out == nullptr: states only.  One CTA per stream, chunks of ICH input samples.
+ * ------------------------------------------------------------------------------------------------------------ */
+constexpr int ICH = 64;
+constexpr int IST = 32;
+constexpr int ISTATE_WORDS = 5 * 2 * IST;
+SDRD_HD constexpr int ibuf_off(int k) { return k == 0 ? 0 : ibuf_off(k - 1) + 2 * (IST + (ICH << (k - 1))); }
+SDRD_HD constexpr size_t i_stateful_smem_bytes() { return (size_t)ibuf_off(5) * 4; }
+
+struct IStateParams {
+    const uint32_t* in;   /* in[s * in_stride + k] */
+    long long in_stride;
+    uint32_t* out;        /* out[s * out_stride + n] or nullptr */
+    long long out_stride;
+    int* state;           /* [n_streams][ISTATE_WORDS] */
+    long long n_in;       /* input samples per stream */
+    int log2_interp;      /* 1..6; stages run S = min(log2_interp, 5) */
+};
+
+SDRD_KERNEL(NT, 1) i_stateful_kernel(IStateParams p)
+{
+    constexpr int C64[16] = SDRD_HB64_ITAPS;
+    constexpr int C32[8] = SDRD_HB32_ITAPS;
+    constexpr int C16[4] = SDRD_HB16_ITAPS;
+    SDRD_DYN_SMEM(smem);
+    int* const buf = reinterpret_cast<int*>(smem);
+    const int tid = (int)threadIdx.x;
+    const int s = (int)blockIdx.x;
+    const int wo = p.log2_interp;
+    const int S = wo < 5 ? wo : 5;
+    const uint32_t* in = p.in + (long long)s * p.in_stride;
+    uint32_t* out = p.out ? p.out + (long long)s * p.out_stride : nullptr;
+    int* state = p.state + (long long)s * ISTATE_WORDS;
+    auto B = [&](int k, int c) -> int* { return buf + ibuf_off(k) + c * (IST + (ICH << k)); };
+
+    for (int i = tid; i < S * 2 * IST; i += NT) {
+        const int k = i / (2 * IST), c = (i / IST) & 1, j = i % IST;
+        B(k, c)[j] = state[(k * 2 + c) * IST + j];
+    }
+    __syncthreads();
+    for (long long k0 = 0; k0 < p.n_in; k0 += ICH) {
+        const int len = (int)(p.n_in - k0 < ICH ? p.n_in - k0 : ICH);
+        for (int i = tid; i < len; i += NT) {
+            const uint32_t v = in[k0 + i];
+            B(0, 0)[IST + i] = (int)(int16_t)(v & 0xFFFFu);
+            B(0, 1)[IST + i] = ((int)v) >> 16;
+        }
+        __syncthreads();
+        for (int k = 0; k < S; k++) {
+            const int L = ring_len(k + 1);
+            const int nk = len << k; /* inputs of this stage in the chunk */
+            for (int j = tid; j < nk; j += NT) {
+                int ev[2], od[2];
+                for (int c = 0; c < 2; c++) {
+                    const int* x = B(k, c) + IST; /* x[j], j >= -IST */
+                    uint32_t acc = 0;
+                    for (int t = 0; t < L / 2; t++) {
+                        const int co = L == 32 ? C64[t & 15] : L == 16 ? C32[t & 7] : C16[t & 3];
+                        acc += ((uint32_t)x[j - L + 1 + t] + (uint32_t)x[j - t]) * (uint32_t)co;
+                    }
+                    ev[c] = x[j - L / 2];
+                    od[c] = asr32(acc, 13);
+                }
+                if (k + 1 < S) {
+                    B(k + 1, 0)[IST + 2 * j] = ev[0];
+                    B(k + 1, 1)[IST + 2 * j] = ev[1];
+                    B(k + 1, 0)[IST + 2 * j + 1] = od[0];
+                    B(k + 1, 1)[IST + 2 * j + 1] = od[1];
+                } else if (out) {
+                    /* cascade sample n is emitted at (n >> S << wo) + (n & (2^S - 1)) */
+                    const long long n = (k0 << S) + 2 * (long long)j;
+                    const long long pos = ((n >> S) << wo) + (n & ((1 << S) - 1));
+                    out[pos] = pack16(make_int2(ev[0], ev[1]));
+                    out[pos + 1] = pack16(make_int2(od[0], od[1]));
+                }
+            }
+            __syncthreads();
+        }
+        if (out && wo > S) { /* interpolate64_cen: 32 zero samples after every 32 */
+            const int zw = (1 << wo) - (1 << S);
+            for (int i = tid; i < len * zw; i += NT) out[((k0 + i / zw) << wo) + (1 << S) + i % zw] = 0u;
+        }
+        int keep[(5 * 2 * IST + NT - 1) / NT];
+        for (int r = 0; r < (5 * 2 * IST + NT - 1) / NT; r++) {
+            const int i = tid + r * NT;
+            const int k = i / (2 * IST), c = (i / IST) & 1, j = i % IST;
+            keep[r] = k < S ? B(k, c)[(len << k) + j] : 0;
+        }
+        __syncthreads();
+        for (int r = 0; r < (5 * 2 * IST + NT - 1) / NT; r++) {
+            const int i = tid + r * NT;
+            const int k = i / (2 * IST), c = (i / IST) & 1, j = i % IST;
+            if (k < S) B(k, c)[j] = keep[r];
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < S * 2 * IST; i += NT) {
+        const int k = i / (2 * IST), c = (i / IST) & 1, j = i % IST;
+        state[(k * 2 + c) * IST + j] = B(k, c)[j];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * Warp-private form (the product kernel; the CTA-wide kernel above stays for A/B runs, -DSDRD_K4_WARP=0).
  * One warp (a 32-thread CTA) walks a segment of one stream in steps of WC = 64 input samples and runs the
  * stages one after the other, every lane busy in every stage and no CTA barrier anywhere:

@@ -50,6 +50,10 @@ size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 /* raw samples of input history kept per stream: two chunks of the /4-prologue cascade */
 constexpr size_t HISTW = 16384;
 constexpr size_t MAX_CHUNK_RAW = 4 * 2048; /* largest raw chunk the kernel reads: /4 prologue, C0 = 2048 */
+/* Raw samples after which a cascade no longer reaches back across a reconfiguration: the deepest cascade (six
+ * stages) looks back 61 * 63 = 3843 raw samples, and the last 64 inputs of its last stage depend on 3939. */
+constexpr long long DEC_HEAD = 4096;
+constexpr long long INT_HEAD = 128; /* interpolator: five stages look back 42 input samples */
 
 /* CRC-32/IEEE (boost::crc_32_type, UDPSinkFEC.cpp:106-109) over the 20 meta bytes -- 20 bytes per
  * call, host side like the reference */
@@ -170,6 +174,15 @@ struct sdrd_dec {
     uint32_t* d_out = nullptr;   /* [S][out_pitch] */
     size_t in_pitch = 0, out_pitch = 0;
     long long consumed = 0;      /* raw samples consumed since reset (saturating) */
+    /* Per-stage state across configure (the reference's six persistent stage objects, Decimators.h:57-62).
+     * Either `consistent`: every stage of the current cascade is in the state the raw history implies (the warp
+     * kernel re-derives it from d_hist) and d_state holds the true state of the OTHER stages; or not: d_state
+     * holds the true state of all six stages and hb::stateful_kernel runs the cascade from it until `run` raw
+     * samples of the current configuration (>= DEC_HEAD) have made the two views agree again. */
+    int* d_state = nullptr;      /* [S][hb::STATE_WORDS] */
+    bool consistent = true;
+    long long run = 0;           /* raw samples consumed under the current configuration (saturating) */
+    rt::stream_t last_stream = 0; /* stream of the last process call (configure waits for it) */
     long long launches = 0;
     int sms = 148;
     rt::stream_t stream = 0;
@@ -213,7 +226,8 @@ extern "C" int sdrd_dec_create(sdrd_dec** out, int log2_decim, int fcpos, int va
     d->out_pitch = round_up(max_in, 8) + 8;
     if (rt::alloc((void**)&d->d_in, d->in_pitch * 4 * (size_t)n_streams) != 0 ||
         rt::alloc((void**)&d->d_hist, HISTW * 4 * (size_t)n_streams) != 0 ||
-        rt::alloc((void**)&d->d_out, d->out_pitch * 4 * (size_t)n_streams) != 0 || rt::stream_create(&d->stream) != 0) {
+        rt::alloc((void**)&d->d_out, d->out_pitch * 4 * (size_t)n_streams) != 0 ||
+        rt::alloc((void**)&d->d_state, (size_t)hb::STATE_WORDS * 4 * (size_t)n_streams) != 0 || rt::stream_create(&d->stream) != 0) {
         int rc = fail_cuda("allocating decimator buffers");
         sdrd_dec_destroy(d);
         return rc;
@@ -235,6 +249,7 @@ extern "C" void sdrd_dec_destroy(sdrd_dec* d)
     rt::release(d->d_in);
     rt::release(d->d_hist);
     rt::release(d->d_out);
+    rt::release(d->d_state);
     rt::stream_destroy(d->stream);
     delete d;
 }
@@ -242,16 +257,60 @@ extern "C" void sdrd_dec_destroy(sdrd_dec* d)
 extern "C" int sdrd_dec_reset(sdrd_dec* d)
 {
     if (!d) return fail(SDRD_EINVAL, "null handle");
+    if (d->last_stream != d->stream) SDRD_TRY(rt::sync(d->last_stream), "reset history");
     SDRD_TRY(rt::fill(d->d_hist, 0, HISTW * 4 * (size_t)d->S, d->stream), "reset history");
+    SDRD_TRY(rt::fill(d->d_state, 0, (size_t)hb::STATE_WORDS * 4 * (size_t)d->S, d->stream), "reset stage states");
     SDRD_TRY(rt::sync(d->stream), "reset history");
     d->consumed = 0;
+    d->consistent = true;
+    d->run = 0;
     return 0;
+}
+
+/* half-band stages and /4 prologue of a configuration (0 stages: the filter-less routines) */
+static void dec_shape(int log2_decim, int fcpos, int* M, int* pro)
+{
+    *pro = fcpos == SDRD_FC_CENTER ? 0 : (fcpos == SDRD_FC_INFRA ? 1 : 2);
+    if (log2_decim == 0 || (*pro && log2_decim <= 2)) {
+        *M = 0;
+        *pro = 0;
+    } else {
+        *M = *pro ? log2_decim - 2 : log2_decim;
+    }
 }
 
 extern "C" int sdrd_dec_configure(sdrd_dec* d, int log2_decim, int fcpos)
 {
     if (!d) return fail(SDRD_EINVAL, "null handle");
     if (int rc = check_decim(log2_decim, fcpos)) return rc;
+    if (log2_decim == d->log2_decim && fcpos == d->fcpos) return 0;
+    if (d->consumed > 0) {
+        /* Leaving a configuration: the stages it ran keep their state in the reference (Decimators.h:57-62).  While
+         * `consistent` that state exists only implicitly, as the raw history: make it explicit by running the old
+         * cascade over the last min(run, DEC_HEAD) raw samples, starting from the states as they were when the run
+         * began (run < DEC_HEAD only happens for the first run after a reset: zeros). */
+        int M, pro;
+        dec_shape(d->log2_decim, d->fcpos, &M, &pro);
+        if (d->consistent && M > 0 && d->run > 0) {
+            if (d->last_stream != d->stream) SDRD_TRY(rt::sync(d->last_stream), "configure");
+            const long long n_raw = std::min<long long>(d->run, DEC_HEAD);
+            hb::StateParams p{};
+            p.in = d->d_hist + (HISTW - (size_t)n_raw);
+            p.in_stride = (long long)HISTW;
+            p.out = nullptr;
+            p.state = d->d_state;
+            p.n_casc = n_raw / (pro ? 4 : 1);
+            p.M = M;
+            p.round_add = d->variant == SDRD_HB_DB ? 1 : 0;
+            p.prologue = pro;
+            SDRD_LAUNCH(hb::stateful_kernel, d->S, 1, hb::SNT, hb::stateful_smem_bytes(), d->stream, p);
+            d->launches++;
+            if (!SDRD_LAUNCH_OK()) return fail_cuda("stage-state kernel launch");
+            SDRD_TRY(rt::sync(d->stream), "configure");
+        }
+        d->consistent = false;
+        d->run = 0;
+    }
     d->log2_decim = log2_decim;
     d->fcpos = fcpos;
     return 0;
@@ -342,31 +401,48 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
         int norm, trunk;
         unsigned ss_out;
         shift_rule(ss, L, &norm, &trunk, &ss_out);
-        if (n_out) {
+        /* After a reconfiguration the first DEC_HEAD raw samples run from the explicit stage states; the head ends
+         * on a multiple of 4 outputs so that the warp kernel's vector accesses behind it stay aligned. */
+        size_t head = 0;
+        if (!d->consistent && n_out) {
+            const size_t G = (size_t)4 << L;
+            const size_t want = round_up((size_t)(DEC_HEAD - d->run), G);
+            head = std::min(consumed_now, want);
+            hb::StateParams sp{};
+            sp.in = in0; sp.in_stride = (long long)d->in_pitch;
+            sp.out = out0; sp.out_stride = (long long)d->out_pitch;
+            sp.state = d->d_state;
+            sp.n_casc = (long long)(head / (pro ? 4 : 1));
+            sp.M = M;
+            sp.round_add = d->variant == SDRD_HB_DB ? 1 : 0;
+            sp.norm_shift = norm; sp.trunk_shift = trunk;
+            sp.prologue = pro;
+            SDRD_LAUNCH(hb::stateful_kernel, d->S, 1, hb::SNT, hb::stateful_smem_bytes(), st, sp);
+            d->launches++;
+        }
+        const size_t n_out_fast = n_out - (head >> L);
+        if (n_out_fast) {
             hb::Params p{};
-            p.in = in0; p.in_stride = (long long)d->in_pitch;
-            p.out = out0; p.out_stride = (long long)d->out_pitch;
-            p.n_out = (long long)n_out;
+            p.in = in0 + head; p.in_stride = (long long)d->in_pitch;
+            p.out = out0 + (head >> L); p.out_stride = (long long)d->out_pitch;
+            p.n_out = (long long)n_out_fast;
             p.round_add = d->variant == SDRD_HB_DB ? 1 : 0;
             p.norm_shift = norm; p.trunk_shift = trunk;
             p.prologue = pro;
-            p.origin = d->consumed / (pro ? 4 : 1);
+            p.origin = (d->consumed + (long long)head) / (pro ? 4 : 1);
             p.steer_zero = 0; p.steer_one = 1; p.steer_k32 = 32; p.steer_k256 = 256; p.steer_k8192 = 8192;
             /* One warp per share of the global event axis (the streams laid end to end), shares sized for ONE
              * wave of resident warps whatever the number of streams -- equally long, so there is no tail --
              * but never so short that the filter warm-up costs more than ~1/8 of a share (short streams: one
              * warp per stream). */
             const int FN = hb::wfin_n(M);
-            const long long ev_stream = ((long long)n_out + FN - 1) / FN;
+            const long long ev_stream = ((long long)n_out_fast + FN - 1) / FN;
             const long long ev_total = ev_stream * d->S;
             const long long warm_ev = hb::wwarm_chunks(M) / hb::wmacro(M);
             const size_t smem = hb::wsmem_bytes(M, pro ? 1 : 0);
             long long resident = (long long)((227 * 1024) / (smem + 1024));
             if (resident > SDRD_K1_WARPS_PER_SM) resident = SDRD_K1_WARPS_PER_SM;
-            /* SDRD_K1_WAVES_X4 (experiments): shares for this many quarter-waves of resident warps (default 4 = one wave) */
-            long long waves_x4 = 4;
-            if (const char* e = getenv("SDRD_K1_WAVES_X4")) waves_x4 = atoi(e) > 0 ? atoi(e) : 4;
-            long long want = resident * d->sms * waves_x4 / 4;
+            long long want = resident * d->sms;
             if (want < 1) want = 1;
             long long ev_warp = (ev_total + want - 1) / want;
             const long long ev_min = std::min<long long>(8 * warm_ev, ev_stream);
@@ -397,6 +473,10 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
                  "save history");
     d->consumed += (long long)consumed_now;
     if (d->consumed > (1LL << 50)) d->consumed = 1LL << 50;
+    d->run += (long long)consumed_now;
+    if (d->run > (1LL << 50)) d->run = 1LL << 50;
+    if (d->run >= DEC_HEAD) d->consistent = true;
+    d->last_stream = st;
     if (n_out_p) *n_out_p = n_out;
     if (sample_bits) *sample_bits = ss;
     return 0;
@@ -438,6 +518,11 @@ struct sdrd_int {
     uint32_t* d_hist = nullptr;  /* [S][hbi::HIST] */
     uint32_t* d_out = nullptr;   /* [S][out_pitch] */
     size_t in_pitch = 0, out_pitch = 0;
+    /* per-stage state across configure, as in sdrd_dec (Interpolators.h:52-58) */
+    int* d_state = nullptr;      /* [S][hbi::ISTATE_WORDS] */
+    bool consistent = true;
+    long long consumed = 0, run = 0;
+    rt::stream_t last_stream = 0;
     long long launches = 0;
     rt::stream_t stream = 0;
 };
@@ -465,7 +550,8 @@ extern "C" int sdrd_int_create(sdrd_int** out, int log2_interp, int n_streams, s
     u->out_pitch = round_up(max_in, 4) << 6; /* room for any interp up to 64 (configure may raise it) */
     if (rt::alloc((void**)&u->d_in, u->in_pitch * 4 * (size_t)n_streams) != 0 ||
         rt::alloc((void**)&u->d_hist, hbi::HIST * 4 * (size_t)n_streams) != 0 ||
-        rt::alloc((void**)&u->d_out, u->out_pitch * 4 * (size_t)n_streams) != 0 || rt::stream_create(&u->stream) != 0) {
+        rt::alloc((void**)&u->d_out, u->out_pitch * 4 * (size_t)n_streams) != 0 ||
+        rt::alloc((void**)&u->d_state, (size_t)hbi::ISTATE_WORDS * 4 * (size_t)n_streams) != 0 || rt::stream_create(&u->stream) != 0) {
         int rc = fail_cuda("allocating interpolator buffers");
         sdrd_int_destroy(u);
         return rc;
@@ -486,6 +572,7 @@ extern "C" void sdrd_int_destroy(sdrd_int* u)
     rt::release(u->d_in);
     rt::release(u->d_hist);
     rt::release(u->d_out);
+    rt::release(u->d_state);
     rt::stream_destroy(u->stream);
     delete u;
 }
@@ -493,8 +580,12 @@ extern "C" void sdrd_int_destroy(sdrd_int* u)
 extern "C" int sdrd_int_reset(sdrd_int* u)
 {
     if (!u) return fail(SDRD_EINVAL, "null handle");
+    if (u->last_stream != u->stream) SDRD_TRY(rt::sync(u->last_stream), "reset history");
     SDRD_TRY(rt::fill(u->d_hist, 0, hbi::HIST * 4 * (size_t)u->S, u->stream), "reset history");
+    SDRD_TRY(rt::fill(u->d_state, 0, (size_t)hbi::ISTATE_WORDS * 4 * (size_t)u->S, u->stream), "reset stage states");
     SDRD_TRY(rt::sync(u->stream), "reset history");
+    u->consistent = true;
+    u->consumed = u->run = 0;
     return 0;
 }
 
@@ -502,6 +593,27 @@ extern "C" int sdrd_int_configure(sdrd_int* u, int log2_interp)
 {
     if (!u) return fail(SDRD_EINVAL, "null handle");
     if (int rc = check_interp(log2_interp)) return rc;
+    if (log2_interp == u->log2_interp) return 0;
+    if (u->consumed > 0) {
+        /* leaving a configuration: make the state of the stages it ran explicit (see sdrd_dec_configure) */
+        if (u->consistent && u->log2_interp > 0 && u->run > 0) {
+            if (u->last_stream != u->stream) SDRD_TRY(rt::sync(u->last_stream), "configure");
+            const long long n = std::min<long long>(u->run, (long long)hbi::HIST);
+            hbi::IStateParams p{};
+            p.in = u->d_hist + ((size_t)hbi::HIST - (size_t)n);
+            p.in_stride = (long long)hbi::HIST;
+            p.out = nullptr;
+            p.state = u->d_state;
+            p.n_in = n;
+            p.log2_interp = u->log2_interp;
+            SDRD_LAUNCH(hbi::i_stateful_kernel, u->S, 1, hbi::NT, hbi::i_stateful_smem_bytes(), u->stream, p);
+            u->launches++;
+            if (!SDRD_LAUNCH_OK()) return fail_cuda("stage-state kernel launch");
+            SDRD_TRY(rt::sync(u->stream), "configure");
+        }
+        u->consistent = false;
+        u->run = 0;
+    }
     u->log2_interp = log2_interp;
     return 0;
 }
@@ -564,24 +676,47 @@ static int int_run(sdrd_int* u, size_t n_in, size_t* n_out_p, rt::stream_t st)
                                 rt::D2D, st),
                      "copy samples");
         } else {
-            hbi::Params p{};
-            p.in = u->d_in + hbi::HIST;
-            p.in_stride = (long long)u->in_pitch;
-            p.out = u->d_out;
-            p.out_stride = (long long)u->out_pitch;
-            p.n_in = (long long)n_in;
-            p.log2_interp = L;
-            switch (L < 5 ? L : 5) {
-                case 1: launch_interpolate<1>(p, u->S, st); break;
-                case 2: launch_interpolate<2>(p, u->S, st); break;
-                case 3: launch_interpolate<3>(p, u->S, st); break;
-                case 4: launch_interpolate<4>(p, u->S, st); break;
-                default: launch_interpolate<5>(p, u->S, st); break;
+            /* after a reconfiguration the first INT_HEAD input samples run from the explicit stage states */
+            size_t head = 0;
+            if (!u->consistent) {
+                head = std::min(n_in, round_up((size_t)(INT_HEAD - u->run), 4));
+                hbi::IStateParams sp{};
+                sp.in = u->d_in + hbi::HIST;
+                sp.in_stride = (long long)u->in_pitch;
+                sp.out = u->d_out;
+                sp.out_stride = (long long)u->out_pitch;
+                sp.state = u->d_state;
+                sp.n_in = (long long)head;
+                sp.log2_interp = L;
+                SDRD_LAUNCH(hbi::i_stateful_kernel, u->S, 1, hbi::NT, hbi::i_stateful_smem_bytes(), st, sp);
+                u->launches++;
             }
-            u->launches++;
+            if (n_in > head) {
+                hbi::Params p{};
+                p.in = u->d_in + hbi::HIST + head;
+                p.in_stride = (long long)u->in_pitch;
+                p.out = u->d_out + (head << L);
+                p.out_stride = (long long)u->out_pitch;
+                p.n_in = (long long)(n_in - head);
+                p.log2_interp = L;
+                switch (L < 5 ? L : 5) {
+                    case 1: launch_interpolate<1>(p, u->S, st); break;
+                    case 2: launch_interpolate<2>(p, u->S, st); break;
+                    case 3: launch_interpolate<3>(p, u->S, st); break;
+                    case 4: launch_interpolate<4>(p, u->S, st); break;
+                    default: launch_interpolate<5>(p, u->S, st); break;
+                }
+                u->launches++;
+            }
             if (!SDRD_LAUNCH_OK()) return fail_cuda("kernel launch");
         }
     }
+    u->consumed += (long long)n_in;
+    if (u->consumed > (1LL << 50)) u->consumed = 1LL << 50;
+    u->run += (long long)n_in;
+    if (u->run > (1LL << 50)) u->run = 1LL << 50;
+    if (u->run >= INT_HEAD) u->consistent = true;
+    u->last_stream = st;
     /* the last HIST input samples become the next call's history */
     SDRD_TRY(rt::copy2d(u->d_hist, hbi::HIST * 4, u->d_in + n_in, u->in_pitch * 4, hbi::HIST * 4, (size_t)u->S, rt::D2D, st),
              "save history");

@@ -55,6 +55,40 @@ def check_interpolator_golden(int_factory):
     assert n_checked == 28
 
 
+def check_reconfigure_golden(dec_factory, int_factory):
+    """Mid-stream Downsampler::configure / Upsampler::configure sequences recorded from the reference build
+    (make_golden_reconfigure.py).  dec_factory(M, fcpos, variant) / int_factory(M) return objects with
+    .configure(...) and .process(x)."""
+    g = load("reconfigure_ref.npz")
+    n_checked = 0
+    for key in g.files:
+        if not key.endswith("_plan"):
+            continue
+        base = key[:-5]
+        x, plan, want = g[base + "_in"], g[key], g[base + "_out"]
+        ys, pos = [], 0
+        if base.startswith("dec_"):
+            variant = int(base.split("_")[1][1:])
+            d = dec_factory(int(plan[0][0]), int(plan[0][1]), variant)
+            for M, fc, k in plan:
+                d.configure(int(M), int(fc))
+                ys.append(d.process(x[pos:pos + k], 16)[0])
+                pos += int(k)
+        else:
+            u = int_factory(int(plan[0][0]))
+            for M, k in plan:
+                u.configure(int(M))
+                ys.append(u.process(x[pos:pos + k]))
+                pos += int(k)
+        y = np.concatenate(ys)
+        assert y.shape == want.shape, (base, y.shape, want.shape)
+        if not np.array_equal(y, want):
+            bad = np.nonzero((y != want).any(axis=1))[0]
+            raise AssertionError(f"{base}: {len(bad)} samples differ from the reference build, first at {bad[:5]}")
+        n_checked += 1
+    assert n_checked == 8
+
+
 def check_sink_golden(sink_factory):
     """sink_factory(F, tv_sec, tv_usec) -> object with .write(x) -> (n_frames, 128+F, 512)."""
     g = load("sink_ref.npz")

@@ -45,6 +45,31 @@ def test_decimator_short_and_empty(emu_lib, oracle):
     cases.check_decimator(emu_lib, oracle, 6, 2, 0, x, [0, 10, 10, 70, 135, 1000])  # below one group, empty, ragged
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_decimator_reconfigure(emu_lib, oracle, variant):
+    """stage states persist across Downsampler::configure (the verified round-1 mismatch)"""
+    rng = np.random.default_rng(310 + variant)
+    for plan in cases.dec_reconfigure_plans():
+        n = sum(k for _, _, k in plan)
+        cases.check_decimator_reconfigure(emu_lib, oracle, variant, cases.rand_iq(rng, (2, n)), plan)
+
+
+def test_reconfigure_golden(emu_lib):
+    """the sequences recorded from the reference build (tests/golden/reconfigure_ref.npz)"""
+    import golden_cases
+    from sdrdaemon_b200 import capi
+
+    golden_cases.check_reconfigure_golden(lambda M, fc, v: capi.Decimator(M, fc, v, max_in=1 << 15, lib=emu_lib),
+                                          lambda M: capi.Interpolator(M, max_in=1024, lib=emu_lib))
+
+
+def test_interpolator_reconfigure(emu_lib, oracle):
+    rng = np.random.default_rng(320)
+    for plan in cases.int_reconfigure_plans():
+        n = sum(k for _, k in plan)
+        cases.check_interpolator_reconfigure(emu_lib, oracle, cases.rand_iq(rng, (2, n)), plan)
+
+
 @pytest.mark.parametrize("M", [0, 1, 2, 3, 4, 5, 6])
 def test_interpolator(emu_lib, oracle, M):
     rng = np.random.default_rng(800 + M)

@@ -22,6 +22,12 @@ def test_interpolator_golden(gpu_lib):
     golden_cases.check_interpolator_golden(lambda M: capi.Interpolator(M, max_in=2048, lib=gpu_lib))
 
 
+def test_reconfigure_golden(gpu_lib):
+    """mid-stream Downsampler::configure / Upsampler::configure sequences recorded from the reference build"""
+    golden_cases.check_reconfigure_golden(lambda M, fc, v: capi.Decimator(M, fc, v, max_in=1 << 15, lib=gpu_lib),
+                                          lambda M: capi.Interpolator(M, max_in=1024, lib=gpu_lib))
+
+
 def test_sink_golden(gpu_lib):
     def factory(F, tv_sec, tv_usec):
         class S:

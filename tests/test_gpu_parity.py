@@ -49,6 +49,31 @@ def test_decimator_short_and_empty(gpu_lib, oracle):
     cases.check_decimator(gpu_lib, oracle, 1, 2, 0, x, [0, 1, 2, 3, 1000])
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_decimator_reconfigure(gpu_lib, oracle, variant):
+    """Downsampler::configure mid-stream: the six stage objects persist (Decimators.h:57-62); sequences
+    1 -> 2 -> 4 -> 2 -> 6 -> 0 -> 3 ... with all three fcpos, blocks shorter and longer than the stateful head."""
+    rng = np.random.default_rng(3200 + variant)
+    for plan in cases.dec_reconfigure_plans():
+        n = sum(k for _, _, k in plan)
+        cases.check_decimator_reconfigure(gpu_lib, oracle, variant, cases.rand_iq(rng, (3, n)), plan)
+    # the reference's block size, many streams, the warp kernel taking over behind the head inside one call
+    plan = [(4, 2, 65536), (2, 2, 65536), (5, 0, 65536), (5, 0, 65536), (6, 2, 65536), (1, 2, 65536), (3, 1, 65536)]
+    cases.check_decimator_reconfigure(gpu_lib, oracle, variant, cases.rand_iq(rng, (40, 7 * 65536)), plan)
+    for bits in (8, 12):
+        plan = [(3, 2, 5000), (5, 2, 70000), (2, 2, 3000), (4, 1, 9000)]
+        cases.check_decimator_reconfigure(gpu_lib, oracle, variant, cases.rand_iq(rng, (2, 87000), bits), plan, bits)
+
+
+def test_interpolator_reconfigure(gpu_lib, oracle):
+    rng = np.random.default_rng(3210)
+    for plan in cases.int_reconfigure_plans():
+        n = sum(k for _, k in plan)
+        cases.check_interpolator_reconfigure(gpu_lib, oracle, cases.rand_iq(rng, (3, n)), plan)
+    plan = [(4, 4096), (2, 4096), (5, 4096), (6, 1000), (1, 4096), (3, 130), (3, 4096)]
+    cases.check_interpolator_reconfigure(gpu_lib, oracle, cases.rand_iq(rng, (40, sum(k for _, k in plan))), plan)
+
+
 def test_decimator_many_streams_many_segments(gpu_lib, oracle):
     """64 streams laid end to end on the global event axis, the warps' shares cross stream boundaries; every
     stream against the oracle."""

@@ -30,6 +30,11 @@ def test_interpolator_vs_reference_build(oracle):
             assert np.array_equal(o.process(x[a:b]), r.process(x[a:b])), (M, a, b)
 
 
+def test_reconfigure_golden(oracle):
+    """stage states persist across configure: the oracle against sequences recorded from the reference build"""
+    golden_cases.check_reconfigure_golden(lambda M, fc, v: oracle.Decimator(M, fc, v), lambda M: oracle.Interpolator(M))
+
+
 def test_sink_golden(oracle):
     def factory(F, tv_sec, tv_usec):
         class S:
@@ -107,6 +112,29 @@ def test_oracle_vs_reference_decimator(oracle, variant):
                 ya, sa = a.process(x[lo:hi])
                 yb, sb = b.process(x[lo:hi])
                 assert sa == sb and np.array_equal(ya, yb), (variant, M, fc)
+
+
+@needs_ref
+@pytest.mark.parametrize("variant", [0, 1])
+def test_oracle_vs_reference_reconfigure(oracle, variant):
+    """Downsampler::configure / Upsampler::configure mid-stream, fresh random input, every plan of cases.py"""
+    rng = np.random.default_rng(41 + variant)
+    for plan in cases.dec_reconfigure_plans():
+        a, b = oracle.Decimator(plan[0][0], plan[0][1], variant), oracle.RefDownsampler(plan[0][0], plan[0][1], variant)
+        for M, fc, n in plan:
+            x = cases.rand_iq(rng, (n,))
+            a.configure(M, fc)
+            b.configure(M, fc)
+            ya, sa = a.process(x)
+            yb, sb = b.process(x)
+            assert sa == sb and np.array_equal(ya, yb), (variant, M, fc, n)
+    for plan in cases.int_reconfigure_plans():
+        a, b = oracle.Interpolator(plan[0][0]), oracle.RefUpsampler(plan[0][0], variant)
+        for M, n in plan:
+            x = cases.rand_iq(rng, (n,))
+            a.configure(M)
+            b.configure(M)
+            assert np.array_equal(a.process(x), b.process(x)), (variant, M, n)
 
 
 @needs_ref
