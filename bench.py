@@ -556,7 +556,7 @@ def main():
 
         def e2e_step():
             lib.check(lib.sdrd_rx_process(rx._h, host_in.data_ptr(), n_in, n_in, host_out.data_ptr(), args.frames + 1,
-                                          C.byref(nfr)))
+                                          C.byref(nfr), None))
 
         e2e_step()
         if world > 1:

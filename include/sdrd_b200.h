@@ -16,6 +16,12 @@
  *     stream in HBM) and take the CUDA stream as `void*` (cudaStream_t, may be NULL).
  *   - There is no CPU fallback: without a usable sm_100 device every create call fails with
  *     SDRD_ENODEV.
+ *   - Errors: a call refused with SDRD_EINVAL / SDRD_ERANGE has not changed the handle (arguments are
+ *     checked before any state moves).  After SDRD_ECUDA / SDRD_ENOMEM the handle's stream state is
+ *     undefined: call the handle's reset function (or destroy it) before using it again.
+ *   - Devices and threads: a handle belongs to the device that was current when it was created; its entry
+ *     points may be called from any thread whatever that thread's current device (they switch and switch
+ *     back).  A handle is not re-entrant: one call at a time per handle, as for the reference's objects.
  */
 #ifndef SDRD_B200_H
 #define SDRD_B200_H
@@ -87,6 +93,11 @@ int sdrd_dec_log2_decim(const sdrd_dec* dec);
  * reference's loop bounds do (Decimators.cpp:412). */
 int sdrd_dec_process(sdrd_dec* dec, const int16_t* iq_in, size_t n_in, size_t in_stride, int16_t* iq_out,
                      size_t out_stride, size_t* n_out, unsigned* sample_bits);
+
+/* Downsampler::rescale (Downsampler.cpp:69-72) = the static Decimators::decimate1 (Decimators.cpp:22-35): sources
+ * with fewer than 16 bits are left-justified in place; no filter state is read or changed, whatever the handle's
+ * current decimation.  iq_inout: n samples per stream (HOST), pitch `stride` samples. */
+int sdrd_dec_rescale(sdrd_dec* dec, int16_t* iq_inout, size_t n, size_t stride, unsigned* sample_bits);
 
 /* Device-resident form.  The caller writes the next n_in samples of every stream to
  * sdrd_dec_dev_input() (pitch *stride samples) and reads the result from sdrd_dec_dev_output(). */
@@ -187,13 +198,22 @@ void sdrd_rx_destroy(sdrd_rx* rx);
 int sdrd_rx_reset(sdrd_rx* rx);
 sdrd_dec* sdrd_rx_dec(sdrd_rx* rx);   /* borrowed */
 sdrd_sink* sdrd_rx_sink(sdrd_rx* rx); /* borrowed: use the sdrd_sink_set_* calls on it */
-/* iq_in as sdrd_dec_process, datagrams / frame_capacity / n_frames as sdrd_sink_write. */
+/* iq_in as sdrd_dec_process, datagrams / frame_capacity / n_frames as sdrd_sink_write.
+ * sample_bits: in/out as for sdrd_dec_process (the source's get_sample_bits() in, the decimator's sampleSize
+ * out; NULL = 16).  As the reference's main loop does after every block (sdrdaemonrx.cpp:618-643), the sink's
+ * sample bits / bytes are set from it before the block is framed: the decimator's output size, or the source's
+ * own when decim = 0; bytes = (bits - 1) / 8 + 1.  Centre frequency and sample rate stay what
+ * sdrd_sink_set_meta(sdrd_rx_sink(rx), ...) last set.
+ * A call that is refused (SDRD_EINVAL / SDRD_ERANGE) leaves the handle untouched. */
 int sdrd_rx_process(sdrd_rx* rx, const int16_t* iq_in, size_t n_in, size_t in_stride, uint8_t* datagrams,
-                    size_t frame_capacity, size_t* n_frames);
+                    size_t frame_capacity, size_t* n_frames, unsigned* sample_bits);
+/* Calls of at least min_call_bytes input bytes (all streams) go through in 8 slices so that the host -> device
+ * copy of slice i + 1 overlaps the kernels and the copy-back of slice i (default 32 MiB; 0 restores it). */
+int sdrd_rx_set_slice_bytes(sdrd_rx* rx, size_t min_call_bytes);
 /* Device-resident form: input at sdrd_dec_dev_input(sdrd_rx_dec(rx)), datagram images left at
  * sdrd_rx_dev_datagrams() (stream pitch *frame_pitch frames of (128 + nb_fec) x 512 bytes). */
 void* sdrd_rx_dev_datagrams(sdrd_rx* rx, size_t* frame_pitch);
-int sdrd_rx_process_dev(sdrd_rx* rx, size_t n_in, size_t* n_frames, void* cuda_stream);
+int sdrd_rx_process_dev(sdrd_rx* rx, size_t n_in, size_t* n_frames, unsigned* sample_bits, void* cuda_stream);
 long long sdrd_rx_launches(const sdrd_rx* rx);
 
 /* ------------------------------------------------------------------------------------------

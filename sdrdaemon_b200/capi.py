@@ -37,6 +37,7 @@ SYMBOLS = [
     ("sdrd_dec_configure", C.c_int, [_P, C.c_int, C.c_int]),
     ("sdrd_dec_log2_decim", C.c_int, [_P]),
     ("sdrd_dec_process", C.c_int, [_P, _P, _SZ, _SZ, _P, _SZ, _SZP, _UP]),
+    ("sdrd_dec_rescale", C.c_int, [_P, _P, _SZ, _SZ, _UP]),
     ("sdrd_dec_dev_input", _P, [_P, _SZP]),
     ("sdrd_dec_dev_output", _P, [_P, _SZP]),
     ("sdrd_dec_process_dev", C.c_int, [_P, _SZ, _SZP, _UP, _P]),
@@ -79,9 +80,10 @@ SYMBOLS = [
     ("sdrd_rx_reset", C.c_int, [_P]),
     ("sdrd_rx_dec", _P, [_P]),
     ("sdrd_rx_sink", _P, [_P]),
-    ("sdrd_rx_process", C.c_int, [_P, _P, _SZ, _SZ, _P, _SZ, _SZP]),
+    ("sdrd_rx_process", C.c_int, [_P, _P, _SZ, _SZ, _P, _SZ, _SZP, _UP]),
+    ("sdrd_rx_set_slice_bytes", C.c_int, [_P, _SZ]),
     ("sdrd_rx_dev_datagrams", _P, [_P, _SZP]),
-    ("sdrd_rx_process_dev", C.c_int, [_P, _SZ, _SZP, _P]),
+    ("sdrd_rx_process_dev", C.c_int, [_P, _SZ, _SZP, _UP, _P]),
     ("sdrd_rx_launches", C.c_longlong, [_P]),
     ("sdrd_fec_decode", C.c_int, [_P, _SZ, _P, C.c_int, _P, _P, _P]),
     ("sdrd_fec_decode_dev", C.c_int, [_P, _SZ, _P, C.c_int, _P, _P, _P, _P]),
@@ -422,7 +424,13 @@ class Rx:
     def frames_for(self, n_in: int) -> int:
         return self.sink.frames_for(n_in >> self.log2_decim)
 
-    def process(self, iq: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def set_slice_bytes(self, min_call_bytes: int) -> None:
+        """calls of at least this many input bytes go through in 8 overlapped slices (0: the default, 32 MiB)"""
+        self.lib.check(self.lib.sdrd_rx_set_slice_bytes(self._h, min_call_bytes))
+
+    def process(self, iq: np.ndarray, out: Optional[np.ndarray] = None, sample_bits: int = 16) -> np.ndarray:
+        """sample_bits: the source's bits per component; the decimator's output size is left in
+        self.sample_bits_out and written into the frames' meta data (sdrdaemonrx.cpp:618-643)."""
         single = np.asarray(iq).ndim == 2
         a = _iq3(iq)
         s, n, _ = a.shape
@@ -431,7 +439,10 @@ class Rx:
         if out is None:
             out = np.zeros((s, cap, bpf, UDPSIZE), dtype=np.uint8)
         nfr = C.c_size_t(0)
-        self.lib.check(self.lib.sdrd_rx_process(self._h, a.ctypes.data, n, n, out.ctypes.data, out.shape[1], C.byref(nfr)))
+        ss = C.c_uint(sample_bits)
+        self.lib.check(self.lib.sdrd_rx_process(self._h, a.ctypes.data, n, n, out.ctypes.data, out.shape[1], C.byref(nfr),
+                                                C.byref(ss)))
+        self.sample_bits_out = ss.value
         res = out[:, : nfr.value]
         return res[0] if single else res
 
@@ -445,9 +456,11 @@ class Rx:
         p = self.lib.sdrd_rx_dev_datagrams(self._h, C.byref(st))
         return p, st.value
 
-    def process_dev(self, n_in: int, stream: int = 0) -> int:
+    def process_dev(self, n_in: int, stream: int = 0, sample_bits: int = 16) -> int:
         nfr = C.c_size_t(0)
-        self.lib.check(self.lib.sdrd_rx_process_dev(self._h, n_in, C.byref(nfr), _P(stream)))
+        ss = C.c_uint(sample_bits)
+        self.lib.check(self.lib.sdrd_rx_process_dev(self._h, n_in, C.byref(nfr), C.byref(ss), _P(stream)))
+        self.sample_bits_out = ss.value
         return nfr.value
 
 

@@ -378,7 +378,8 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
     int* origCnt = lists + 128;           /* [128] times original b was received */
     unsigned* recMask = reinterpret_cast<unsigned*>(lists + 256);  /* [4] bit i: datagram i is a recovery block */
     unsigned* missMask = recMask + 4;                              /* [4] bit b: original b missing */
-    int* flags = lists + 264;             /* [0] duplicate seen, [1] singular */
+    int* flags = lists + 264;             /* [0] repeated original, [1] repeated recovery row (singular system) */
+    unsigned* recSeen = reinterpret_cast<unsigned*>(lists + 266);  /* [4] bit r: recovery row 128 + r received */
     uint8_t* recRowOf = reinterpret_cast<uint8_t*>(lists + 272);   /* [128] k -> image row */
     uint8_t* recIdxOf = recRowOf + 128;                            /* [128] k -> block index (128..255) */
     uint8_t* erased = recIdxOf + 128;                              /* [128] c -> erased original index */
@@ -389,6 +390,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
 
     int nb = p.n_blocks[f];
     if (nb > 128) nb = 128; /* blocks beyond the first 128 received are dropped (.cpp:143) */
+    if (nb > p.blocks_pitch) nb = (int)p.blocks_pitch; /* never read past the frame's slots */
     if (nb < 0) nb = 0;
     {
         const long long first = p.frame_start ? p.frame_start[f] : (long long)f * p.blocks_pitch;
@@ -402,7 +404,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
         origCnt[tid] = 0;
     }
     if (tid < 8) recMask[tid] = 0u; /* recMask + missMask */
-    if (tid < 2) flags[tid] = 0;
+    if (tid < 6) flags[tid] = 0;    /* flags + recSeen */
     __syncthreads();
 
     /* classify the received datagrams by header.blockIndex (.cpp:143-166) */
@@ -413,6 +415,8 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
             atomicAdd(&origCnt[idx], 1);
         } else {
             atomicOr(&recMask[tid >> 5], 1u << (tid & 31));
+            /* the same recovery row twice (a duplicated datagram): two equal rows, the system is singular */
+            if (atomicOr(&recSeen[(idx - 128) >> 5], 1u << (idx & 31)) & (1u << (idx & 31))) flags[1] = 1;
         }
     }
     __syncthreads();
@@ -446,6 +450,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
     if (nb < 128) st = ST_INCOMPLETE;
     else if (N == 0) st = ST_COMPLETE;
     else if (flags[0] || n_missing < N) st = ST_FAILED; /* repeated original: cm256_decode refuses */
+    else if (flags[1] && N > 1) st = ST_FAILED;         /* repeated recovery row: no solution; the originals pass through */
     else if (N > DCAP) st = ST_NEEDS_BIG;
     else {
         st = ST_RECOVERED;

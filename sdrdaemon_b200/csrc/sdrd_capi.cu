@@ -47,6 +47,24 @@ int fail_cuda(const char* what) { return fail(SDRD_ECUDA, std::string(what) + ":
 
 size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
+/* A handle's buffers and streams live on the device that was current when it was created: every entry point
+ * that takes a handle makes that device current for its duration, whatever the calling thread had selected. */
+struct DeviceGuard {
+    int prev;
+    bool switched = false;
+    explicit DeviceGuard(int dev) : prev(rt::current_device())
+    {
+        if (dev >= 0 && dev != prev) switched = rt::set_device(dev) == 0;
+    }
+    ~DeviceGuard()
+    {
+        if (switched) rt::set_device(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define SDRD_ON_DEVICE_OF(h) DeviceGuard device_guard_((h)->device)
+
 /* raw samples of input history kept per stream: two chunks of the /4-prologue cascade */
 constexpr size_t HISTW = 16384;
 constexpr size_t MAX_CHUNK_RAW = 4 * 2048; /* largest raw chunk the kernel reads: /4 prologue, C0 = 2048 */
@@ -168,6 +186,7 @@ void launch_decimate_warp(const hb::Params& p, int n_seg, rt::stream_t st)
 
 struct sdrd_dec {
     int log2_decim = 0, fcpos = SDRD_FC_CENTER, variant = SDRD_HB_EO1, S = 1;
+    int device = -1;             /* the device the handle lives on */
     size_t max_in = 0;
     uint32_t* d_in = nullptr;    /* [S][in_pitch]: HISTW history words, then the new samples */
     uint32_t* d_hist = nullptr;  /* [S][HISTW] */
@@ -219,6 +238,7 @@ extern "C" int sdrd_dec_create(sdrd_dec** out, int log2_decim, int fcpos, int va
     d->fcpos = fcpos;
     d->variant = variant;
     d->S = n_streams;
+    d->device = rt::current_device();
     d->max_in = max_in;
     d->sms = rt::sm_count();
     /* the kernel reads whole chunks (up to 4*C0 raw samples with the /4 prologue) */
@@ -245,6 +265,7 @@ extern "C" int sdrd_dec_create(sdrd_dec** out, int log2_decim, int fcpos, int va
 extern "C" void sdrd_dec_destroy(sdrd_dec* d)
 {
     if (!d) return;
+    SDRD_ON_DEVICE_OF(d);
     rt::sync(d->stream);
     rt::release(d->d_in);
     rt::release(d->d_hist);
@@ -257,6 +278,7 @@ extern "C" void sdrd_dec_destroy(sdrd_dec* d)
 extern "C" int sdrd_dec_reset(sdrd_dec* d)
 {
     if (!d) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(d);
     if (d->last_stream != d->stream) SDRD_TRY(rt::sync(d->last_stream), "reset history");
     SDRD_TRY(rt::fill(d->d_hist, 0, HISTW * 4 * (size_t)d->S, d->stream), "reset history");
     SDRD_TRY(rt::fill(d->d_state, 0, (size_t)hb::STATE_WORDS * 4 * (size_t)d->S, d->stream), "reset stage states");
@@ -282,6 +304,7 @@ static void dec_shape(int log2_decim, int fcpos, int* M, int* pro)
 extern "C" int sdrd_dec_configure(sdrd_dec* d, int log2_decim, int fcpos)
 {
     if (!d) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(d);
     if (int rc = check_decim(log2_decim, fcpos)) return rc;
     if (log2_decim == d->log2_decim && fcpos == d->fcpos) return 0;
     if (d->consumed > 0) {
@@ -329,6 +352,15 @@ extern "C" void* sdrd_dec_dev_output(sdrd_dec* d, size_t* stride)
     if (!d) return nullptr;
     if (stride) *stride = d->out_pitch;
     return d->d_out;
+}
+
+/* samples a process call of n_in samples per stream produces under the current configuration */
+static size_t dec_out_count(const sdrd_dec* d, size_t n_in)
+{
+    const int L = d->log2_decim;
+    if (L == 0) return n_in;
+    if (d->fcpos != SDRD_FC_CENTER && L == 1) return n_in / 2; /* out.resize(len/2), Decimators.cpp:41 */
+    return n_in >> L;
 }
 
 /* in_off / first / last: a call may be processed in consecutive slices of the input buffer (sdrd_rx_process
@@ -485,6 +517,7 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
 extern "C" int sdrd_dec_process_dev(sdrd_dec* d, size_t n_in, size_t* n_out, unsigned* sample_bits, void* cuda_stream)
 {
     if (!d) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(d);
     return dec_run(d, n_in, n_out, sample_bits, (rt::stream_t)cuda_stream);
 }
 
@@ -492,18 +525,49 @@ extern "C" int sdrd_dec_process(sdrd_dec* d, const int16_t* iq_in, size_t n_in, 
                                 size_t out_stride, size_t* n_out_p, unsigned* sample_bits)
 {
     if (!d) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(d);
     if ((!iq_in && n_in) || !iq_out) return fail(SDRD_EINVAL, "null sample pointer");
     if (n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
     if (d->S > 1 && in_stride < n_in) return fail(SDRD_EINVAL, "in_stride smaller than n_in");
+    /* everything that can be refused is refused before the filter state moves */
+    if (d->S > 1 && out_stride < dec_out_count(d, n_in)) return fail(SDRD_EINVAL, "out_stride smaller than the output length");
+    if (sample_bits && (*sample_bits < 1 || *sample_bits > 16)) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
     SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, rt::H2D, d->stream),
              "copy samples to device");
     size_t n_out = 0;
     if (int rc = dec_run(d, n_in, &n_out, sample_bits, d->stream)) return rc;
-    if (d->S > 1 && out_stride < n_out) return fail(SDRD_EINVAL, "out_stride smaller than the output length");
     SDRD_TRY(rt::copy2d(iq_out, out_stride * 4, d->d_out, d->out_pitch * 4, n_out * 4, (size_t)d->S, rt::D2H, d->stream),
              "copy samples to host");
     SDRD_TRY(rt::sync(d->stream), "decimate");
     if (n_out_p) *n_out_p = n_out;
+    return 0;
+}
+
+extern "C" int sdrd_dec_rescale(sdrd_dec* d, int16_t* iq, size_t n, size_t stride, unsigned* sample_bits)
+{
+    if (!d) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(d);
+    if (!iq && n) return fail(SDRD_EINVAL, "null sample pointer");
+    if (n > d->max_in) return fail(SDRD_ERANGE, "n exceeds the max_in given at create time");
+    if (d->S > 1 && stride < n) return fail(SDRD_EINVAL, "stride smaller than n");
+    const unsigned ss = sample_bits ? *sample_bits : 16u;
+    if (ss < 1 || ss > 16) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
+    if (!n || ss == 16) return 0; /* decimate1 does nothing for 16-bit sources; sampleSize stays as it is */
+    /* the staging input buffer is free between calls: the history lives in d_hist */
+    rt::stream_t st = d->stream;
+    SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, iq, stride * 4, n * 4, (size_t)d->S, rt::H2D, st), "copy samples to device");
+    hb::PlainParams p{};
+    p.in = d->d_in + HISTW; p.in_stride = (long long)d->in_pitch;
+    p.out = d->d_out; p.out_stride = (long long)d->out_pitch;
+    p.n_units = (long long)n; p.mode = 0;
+    p.norm_shift = (int)(16 - ss);
+    const int gx = (int)std::min<size_t>((n + 255) / 256, (size_t)d->sms * 8);
+    SDRD_LAUNCH(hb::plain_kernel, gx, d->S, 256, 0, st, p);
+    d->launches++;
+    if (!SDRD_LAUNCH_OK()) return fail_cuda("kernel launch");
+    SDRD_TRY(rt::copy2d(iq, stride * 4, d->d_out, d->out_pitch * 4, n * 4, (size_t)d->S, rt::D2H, st), "copy samples to host");
+    SDRD_TRY(rt::sync(st), "rescale");
+    d->last_stream = st;
     return 0;
 }
 
@@ -513,6 +577,7 @@ extern "C" int sdrd_dec_process(sdrd_dec* d, const int16_t* iq_in, size_t n_in, 
 
 struct sdrd_int {
     int log2_interp = 0, S = 1;
+    int device = -1;             /* the device the handle lives on */
     size_t max_in = 0;
     uint32_t* d_in = nullptr;    /* [S][in_pitch]: hbi::HIST history words, then the new samples */
     uint32_t* d_hist = nullptr;  /* [S][hbi::HIST] */
@@ -545,6 +610,7 @@ extern "C" int sdrd_int_create(sdrd_int** out, int log2_interp, int n_streams, s
     if (!u) return fail(SDRD_ENOMEM, "out of host memory");
     u->log2_interp = log2_interp;
     u->S = n_streams;
+    u->device = rt::current_device();
     u->max_in = max_in;
     u->in_pitch = hbi::HIST + round_up(max_in, 4) + 4;
     u->out_pitch = round_up(max_in, 4) << 6; /* room for any interp up to 64 (configure may raise it) */
@@ -568,6 +634,7 @@ extern "C" int sdrd_int_create(sdrd_int** out, int log2_interp, int n_streams, s
 extern "C" void sdrd_int_destroy(sdrd_int* u)
 {
     if (!u) return;
+    SDRD_ON_DEVICE_OF(u);
     rt::sync(u->stream);
     rt::release(u->d_in);
     rt::release(u->d_hist);
@@ -580,6 +647,7 @@ extern "C" void sdrd_int_destroy(sdrd_int* u)
 extern "C" int sdrd_int_reset(sdrd_int* u)
 {
     if (!u) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(u);
     if (u->last_stream != u->stream) SDRD_TRY(rt::sync(u->last_stream), "reset history");
     SDRD_TRY(rt::fill(u->d_hist, 0, hbi::HIST * 4 * (size_t)u->S, u->stream), "reset history");
     SDRD_TRY(rt::fill(u->d_state, 0, (size_t)hbi::ISTATE_WORDS * 4 * (size_t)u->S, u->stream), "reset stage states");
@@ -592,6 +660,7 @@ extern "C" int sdrd_int_reset(sdrd_int* u)
 extern "C" int sdrd_int_configure(sdrd_int* u, int log2_interp)
 {
     if (!u) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(u);
     if (int rc = check_interp(log2_interp)) return rc;
     if (log2_interp == u->log2_interp) return 0;
     if (u->consumed > 0) {
@@ -727,6 +796,7 @@ static int int_run(sdrd_int* u, size_t n_in, size_t* n_out_p, rt::stream_t st)
 extern "C" int sdrd_int_process_dev(sdrd_int* u, size_t n_in, size_t* n_out, void* cuda_stream)
 {
     if (!u) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(u);
     return int_run(u, n_in, n_out, (rt::stream_t)cuda_stream);
 }
 
@@ -734,6 +804,7 @@ extern "C" int sdrd_int_process(sdrd_int* u, const int16_t* iq_in, size_t n_in, 
                                 size_t out_stride, size_t* n_out_p)
 {
     if (!u) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(u);
     if ((!iq_in && n_in) || !iq_out) return fail(SDRD_EINVAL, "null sample pointer");
     if (n_in > u->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
     if (u->S > 1 && in_stride < n_in) return fail(SDRD_EINVAL, "in_stride smaller than n_in");
@@ -755,6 +826,7 @@ extern "C" int sdrd_int_process(sdrd_int* u, const int16_t* iq_in, size_t n_in, 
 
 struct sdrd_sink {
     int S = 1;
+    int device = -1;             /* the device the handle lives on */
     size_t max_samples = 0;
     uint32_t* d_samples = nullptr;  /* host-API staging [S][samples_pitch] */
     size_t samples_pitch = 0;
@@ -789,6 +861,7 @@ extern "C" int sdrd_sink_create(sdrd_sink** out, int n_streams, size_t max_sampl
     if (!k) return fail(SDRD_ENOMEM, "out of host memory");
     k->S = n_streams;
     k->max_samples = max_samples;
+    k->device = rt::current_device();
     k->samples_pitch = round_up(max_samples, 4);
     k->frame_cap = (max_samples + fec::FRAME_SAMPLES - 1) / fec::FRAME_SAMPLES + 1;
     if (get_tables(&k->tab) != 0) {
@@ -809,6 +882,7 @@ extern "C" int sdrd_sink_create(sdrd_sink** out, int n_streams, size_t max_sampl
 extern "C" void sdrd_sink_destroy(sdrd_sink* k)
 {
     if (!k) return;
+    SDRD_ON_DEVICE_OF(k);
     rt::sync(k->stream);
     rt::release(k->d_samples);
     rt::release(k->d_pending);
@@ -820,6 +894,7 @@ extern "C" void sdrd_sink_destroy(sdrd_sink* k)
 extern "C" int sdrd_sink_reset(sdrd_sink* k)
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(k);
     k->n_pending = 0;
     k->frame_count = 0;
     return 0;
@@ -827,6 +902,7 @@ extern "C" int sdrd_sink_reset(sdrd_sink* k)
 extern "C" int sdrd_sink_set_meta(sdrd_sink* k, uint32_t f_khz, uint32_t rate, uint8_t sbytes, uint8_t sbits)
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(k);
     k->center_freq_khz = f_khz;
     k->sample_rate = rate;
     k->sample_bytes = sbytes;
@@ -836,6 +912,7 @@ extern "C" int sdrd_sink_set_meta(sdrd_sink* k, uint32_t f_khz, uint32_t rate, u
 extern "C" int sdrd_sink_set_nb_fec(sdrd_sink* k, int nb_fec)
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(k);
     if (nb_fec < 0 || nb_fec > SDRD_MAX_FEC) return fail(SDRD_EINVAL, "nb_fec must be 0..128 (128 + nb_fec <= 256 blocks)");
     k->nb_fec = nb_fec;
     return 0;
@@ -843,6 +920,7 @@ extern "C" int sdrd_sink_set_nb_fec(sdrd_sink* k, int nb_fec)
 extern "C" int sdrd_sink_set_time(sdrd_sink* k, int use_fixed, uint32_t tv_sec, uint32_t tv_usec)
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(k);
     k->fixed_time = use_fixed != 0;
     k->tv_sec = tv_sec;
     k->tv_usec = tv_usec;
@@ -957,6 +1035,7 @@ extern "C" int sdrd_sink_write(sdrd_sink* k, const int16_t* iq, size_t n, size_t
                                size_t frame_capacity, size_t* n_frames_p)
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(k);
     if (!iq && n) return fail(SDRD_EINVAL, "null sample pointer");
     if (n > k->max_samples) return fail(SDRD_ERANGE, "n_samples exceeds the max_samples given at create time");
     SDRD_TRY(rt::copy2d(k->d_samples, k->samples_pitch * 4, iq, stride * 4, n * 4, (size_t)k->S, rt::H2D, k->stream),
@@ -973,6 +1052,7 @@ extern "C" int sdrd_sink_write_dev(sdrd_sink* k, const void* samples, size_t n, 
                                    void* cuda_stream)
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(k);
     if (!samples && n) return fail(SDRD_EINVAL, "null sample pointer");
     return sink_run(k, reinterpret_cast<const uint32_t*>(samples), stride, n, n_frames, (rt::stream_t)cuda_stream);
 }
@@ -989,10 +1069,12 @@ extern "C" long long sdrd_sink_launches(const sdrd_sink* k) { return k ? k->laun
 /* ========================================================================================== */
 
 struct sdrd_rx {
+    int device = -1;             /* the device the handle lives on */
     sdrd_dec* dec = nullptr;
     sdrd_sink* sink = nullptr;
     rt::stream_t copy_stream = 0;   /* host -> device copies of sdrd_rx_process, ahead of the kernels */
     rt::event_t copied[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t slice_threshold = (size_t)32 << 20; /* calls of at least this many input bytes go through in 8 slices */
 };
 
 extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int variant, int n_streams, size_t max_in)
@@ -1001,6 +1083,7 @@ extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int vari
     *out = nullptr;
     sdrd_rx* r = new (std::nothrow) sdrd_rx();
     if (!r) return fail(SDRD_ENOMEM, "out of host memory");
+    r->device = rt::current_device();
     int rc = sdrd_dec_create(&r->dec, log2_decim, fcpos, variant, n_streams, max_in);
     if (!rc) rc = sdrd_sink_create(&r->sink, n_streams, max_in);
     if (!rc && rt::stream_create(&r->copy_stream) != 0) rc = fail_cuda("creating the copy stream");
@@ -1016,6 +1099,7 @@ extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int vari
 extern "C" void sdrd_rx_destroy(sdrd_rx* r)
 {
     if (!r) return;
+    SDRD_ON_DEVICE_OF(r);
     if (r->copy_stream) rt::sync(r->copy_stream);
     sdrd_dec_destroy(r->dec);
     sdrd_sink_destroy(r->sink);
@@ -1026,8 +1110,16 @@ extern "C" void sdrd_rx_destroy(sdrd_rx* r)
 extern "C" int sdrd_rx_reset(sdrd_rx* r)
 {
     if (!r) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(r);
     if (int rc = sdrd_dec_reset(r->dec)) return rc;
     return sdrd_sink_reset(r->sink);
+}
+extern "C" int sdrd_rx_set_slice_bytes(sdrd_rx* r, size_t min_call_bytes)
+{
+    if (!r) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(r);
+    r->slice_threshold = min_call_bytes ? min_call_bytes : ((size_t)32 << 20);
+    return 0;
 }
 extern "C" sdrd_dec* sdrd_rx_dec(sdrd_rx* r) { return r ? r->dec : nullptr; }
 extern "C" sdrd_sink* sdrd_rx_sink(sdrd_rx* r) { return r ? r->sink : nullptr; }
@@ -1039,23 +1131,50 @@ extern "C" void* sdrd_rx_dev_datagrams(sdrd_rx* r, size_t* frame_pitch)
     return r->sink->d_dgrams;
 }
 
-extern "C" int sdrd_rx_process_dev(sdrd_rx* r, size_t n_in, size_t* n_frames, void* cuda_stream)
+/* sdrdaemonrx.cpp:618-643: the sink's sample size follows the decimator -- with decim = 0 it stays the source's
+ * (rescale left-justifies the samples but the meta data keep get_sample_bits()), otherwise it is what process
+ * returned; sample bytes = (bits - 1) / 8 + 1 */
+static void rx_set_sample_size(sdrd_rx* r, unsigned ss_in, unsigned ss_out)
+{
+    const unsigned bits = r->dec->log2_decim == 0 ? ss_in : ss_out;
+    r->sink->sample_bits = (uint8_t)bits;
+    r->sink->sample_bytes = (uint8_t)((bits - 1) / 8 + 1);
+}
+
+extern "C" int sdrd_rx_process_dev(sdrd_rx* r, size_t n_in, size_t* n_frames, unsigned* sample_bits, void* cuda_stream)
 {
     if (!r) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(r);
     rt::stream_t st = (rt::stream_t)cuda_stream;
+    const unsigned ss_in = sample_bits ? *sample_bits : 16u;
+    if (ss_in < 1 || ss_in > 16) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
+    if (n_in > r->dec->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
     size_t n_out = 0;
-    unsigned ss = 16;
+    unsigned ss = ss_in;
     if (int rc = dec_run(r->dec, n_in, &n_out, &ss, st)) return rc;
+    rx_set_sample_size(r, ss_in, ss);
+    if (sample_bits) *sample_bits = ss;
     return sink_run(r->sink, r->dec->d_out, r->dec->out_pitch, n_out, n_frames, st);
 }
 
 extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, size_t in_stride, uint8_t* datagrams,
-                               size_t frame_capacity, size_t* n_frames_p)
+                               size_t frame_capacity, size_t* n_frames_p, unsigned* sample_bits)
 {
     if (!r) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(r);
     if (!iq_in && n_in) return fail(SDRD_EINVAL, "null sample pointer");
     sdrd_dec* d = r->dec;
     if (n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    if (d->S > 1 && in_stride < n_in) return fail(SDRD_EINVAL, "in_stride smaller than n_in");
+    const unsigned ss_in = sample_bits ? *sample_bits : 16u;
+    if (ss_in < 1 || ss_in > 16) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
+    /* everything that can be refused is refused before the decimator and sink state move */
+    {
+        const size_t will_close = sdrd_sink_frames_for(r->sink, dec_out_count(d, n_in));
+        if (will_close > frame_capacity) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of completed frames");
+        if (will_close > r->sink->frame_cap) return fail(SDRD_ERANGE, "write completes more frames than the handle was sized for");
+        if (will_close && !datagrams) return fail(SDRD_EINVAL, "null datagram buffer");
+    }
     rt::stream_t st = d->stream;
     /* Large calls go through in slices: the copy of slice i + 1 (copy stream) runs while slice i is being
      * decimated, framed, encoded and its datagrams copied back (compute stream), so the call costs little
@@ -1063,13 +1182,12 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
     const int L = d->log2_decim;
     int n_slices = 1;
     /* SDRD_RX_SLICE_BYTES: tests lower the threshold to exercise the sliced path on small inputs */
-    const char* thr_env = getenv("SDRD_RX_SLICE_BYTES");
-    const size_t slice_threshold = thr_env ? (size_t)strtoull(thr_env, nullptr, 10) : ((size_t)32 << 20);
-    if ((size_t)d->S * n_in * 4 >= slice_threshold) n_slices = 8;
+    if ((size_t)d->S * n_in * 4 >= r->slice_threshold) n_slices = 8;
     size_t slice = n_in / (size_t)n_slices;
     slice -= slice % (((size_t)1 << L) * 4); /* whole decimation groups, 16-byte aligned */
     if (slice == 0) n_slices = 1;
     size_t n_frames = 0;
+    unsigned ss_out = ss_in;
     const size_t frame_bytes = (size_t)(128 + r->sink->nb_fec) * SDRD_UDPSIZE;
     for (int i = 0; i < n_slices; i++) {
         const size_t off = (size_t)i * slice;
@@ -1089,8 +1207,10 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
         const size_t len = i == n_slices - 1 ? n_in - off : slice;
         if (n_slices > 1) SDRD_TRY(rt::stream_wait(st, r->copied[i]), "wait for copy");
         size_t n_out = 0, nf = 0;
-        unsigned ss = 16;
+        unsigned ss = ss_in;
         if (int rc = dec_run(d, len, &n_out, &ss, st, off, i == 0, i == n_slices - 1)) return rc;
+        rx_set_sample_size(r, ss_in, ss);
+        ss_out = ss;
         if (int rc = sink_run(r->sink, d->d_out + (off >> L), d->out_pitch, n_out, &nf, st)) return rc;
         if (nf) {
             if (n_frames + nf > frame_capacity) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of completed frames");
@@ -1102,6 +1222,7 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
     }
     SDRD_TRY(rt::sync(st), "rx process");
     if (n_frames_p) *n_frames_p = n_frames;
+    if (sample_bits) *sample_bits = ss_out;
     return 0;
 }
 
@@ -1115,12 +1236,20 @@ struct Scratch {
     void* p = nullptr;
     size_t n = 0;
     int device = -1;
+    ~Scratch() { drop(); } /* thread exit */
+    void drop()
+    {
+        if (p) {
+            DeviceGuard g(device);
+            rt::release(p);
+        }
+        p = nullptr;
+        n = 0;
+    }
     int ensure(size_t need)
     {
         if (device != rt::current_device()) { /* the thread moved to another device: start over there */
-            rt::release(p);
-            p = nullptr;
-            n = 0;
+            drop();
             device = rt::current_device();
         }
         if (need <= n) return 0;
@@ -1140,10 +1269,27 @@ struct DecPipe {
     rt::event_t ev_in[NS] = {}, ev_k[NS] = {};
     bool ready = false;
     int device = -1;
+    ~DecPipe() { drop(); } /* thread exit */
+    void drop()
+    {
+        if (device < 0) return;
+        DeviceGuard g(device);
+        rt::stream_destroy(s_in);
+        rt::stream_destroy(s_k);
+        rt::stream_destroy(s_out);
+        for (int i = 0; i < NS; i++) {
+            rt::event_destroy(ev_in[i]);
+            rt::event_destroy(ev_k[i]);
+            ev_in[i] = ev_k[i] = 0;
+        }
+        s_in = s_k = s_out = 0;
+        ready = false;
+        device = -1;
+    }
     int init()
     {
         if (ready && device == rt::current_device()) return 0;
-        ready = false; /* first use, or the thread moved to another device: streams belong to a device */
+        drop(); /* first use, or the thread moved to another device: streams and events belong to a device */
         device = rt::current_device();
         if (rt::stream_create(&s_in) || rt::stream_create(&s_k) || rt::stream_create(&s_out)) return -1;
         for (int i = 0; i < NS; i++)
@@ -1259,7 +1405,6 @@ extern "C" int sdrd_fec_decode(const uint8_t* superblocks, size_t blocks_pitch, 
      * full duplex; the call then costs little more than the larger of its two copies). */
     DecPipe& dp = g_dec_pipe;
     int n_slices = n_frames >= DecPipe::NS * 64 ? DecPipe::NS : (n_frames >= 128 ? n_frames / 64 : 1);
-    if (const char* e = getenv("SDRD_DEC_SLICES")) n_slices = std::max(1, std::min<int>(atoi(e), std::min<int>(DecPipe::NS, n_frames)));
     if (dp.init()) return fail_cuda("creating streams");
     const int per = (n_frames + n_slices - 1) / n_slices;
     for (int i = 0; i < n_slices; i++) {
@@ -1296,6 +1441,7 @@ extern "C" int sdrd_fec_decode(const uint8_t* superblocks, size_t blocks_pitch, 
 
 struct sdrd_src {
     size_t max_dg = 0;
+    int device = -1;             /* the device the handle lives on */
     /* the open slot: its first <= 128 datagrams (host copy), counters as SDRdaemonFECBuffer keeps them */
     std::vector<uint8_t> carry;      /* 128 x 512 */
     int frame_head = -1, block_count = 0, recovery_count = 0;
@@ -1322,6 +1468,7 @@ extern "C" int sdrd_src_create(sdrd_src** out, size_t max_datagrams)
     sdrd_src* k = new (std::nothrow) sdrd_src();
     if (!k) return fail(SDRD_ENOMEM, "out of host memory");
     k->max_dg = max_datagrams;
+    k->device = rt::current_device();
     k->carry.assign((size_t)128 * SDRD_UDPSIZE, 0);
     if (rt::alloc((void**)&k->d_dg, (128 + max_datagrams) * (size_t)SDRD_UDPSIZE) != 0 ||
         rt::alloc((void**)&k->d_start, (max_datagrams + 1) * sizeof(long long)) != 0 ||
@@ -1338,6 +1485,7 @@ extern "C" int sdrd_src_create(sdrd_src** out, size_t max_datagrams)
 extern "C" void sdrd_src_destroy(sdrd_src* k)
 {
     if (!k) return;
+    SDRD_ON_DEVICE_OF(k);
     rt::sync(k->stream);
     rt::release(k->d_dg);
     rt::release(k->d_start);
@@ -1352,6 +1500,7 @@ extern "C" void sdrd_src_destroy(sdrd_src* k)
 extern "C" int sdrd_src_reset(sdrd_src* k)
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(k);
     k->frame_head = -1;
     k->block_count = k->recovery_count = 0;
     k->cur_nb_blocks = k->cur_nb_recovery = 0;
@@ -1381,6 +1530,7 @@ extern "C" int sdrd_src_feed(sdrd_src* k, const uint8_t* dg, size_t n, uint8_t* 
                              size_t* n_frames_p, int* status, int* nb_blocks, int* nb_recovery)
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(k);
     if (n_frames_p) *n_frames_p = 0;
     if (n == 0) return 0;
     if (!dg) return fail(SDRD_EINVAL, "null datagram pointer");
@@ -1392,25 +1542,30 @@ extern "C" int sdrd_src_feed(sdrd_src* k, const uint8_t* dg, size_t n, uint8_t* 
     std::vector<long long> start;
     std::vector<int> nb, fr_blocks, fr_recovery;
     long long slot_start = 0; /* position of the open slot's first datagram in the device array */
+    /* the counters move on a copy: they are committed, together with the carried datagrams, only once the call
+     * can no longer fail (a refused call leaves the handle exactly as it was) */
+    struct Book {
+        int frame_head, block_count, recovery_count, cur_nb_blocks, cur_nb_recovery, min_nb_blocks, max_nb_recovery;
+    } bk = {k->frame_head, k->block_count, k->recovery_count, k->cur_nb_blocks, k->cur_nb_recovery, k->min_nb_blocks, k->max_nb_recovery};
     for (size_t i = 0; i < n; i++) {
         const uint8_t* sb = dg + i * SDRD_UDPSIZE;
         const int frame_index = sb[0] | (sb[1] << 8);
-        if (k->frame_head != frame_index) {
+        if (bk.frame_head != frame_index) {
             start.push_back(slot_start);
-            nb.push_back(k->block_count < 128 ? k->block_count : 128);
-            fr_blocks.push_back(k->block_count);
-            fr_recovery.push_back(k->recovery_count);
-            k->cur_nb_blocks = k->block_count;
-            k->cur_nb_recovery = k->recovery_count;
-            if (k->cur_nb_blocks < k->min_nb_blocks) k->min_nb_blocks = k->cur_nb_blocks;
-            if (k->cur_nb_recovery > k->max_nb_recovery) k->max_nb_recovery = k->cur_nb_recovery;
-            k->block_count = 0;
-            k->recovery_count = 0;
-            k->frame_head = frame_index;
+            nb.push_back(bk.block_count < 128 ? bk.block_count : 128);
+            fr_blocks.push_back(bk.block_count);
+            fr_recovery.push_back(bk.recovery_count);
+            bk.cur_nb_blocks = bk.block_count;
+            bk.cur_nb_recovery = bk.recovery_count;
+            if (bk.cur_nb_blocks < bk.min_nb_blocks) bk.min_nb_blocks = bk.cur_nb_blocks;
+            if (bk.cur_nb_recovery > bk.max_nb_recovery) bk.max_nb_recovery = bk.cur_nb_recovery;
+            bk.block_count = 0;
+            bk.recovery_count = 0;
+            bk.frame_head = frame_index;
             slot_start = (long long)carried + (long long)i;
         }
-        if (k->block_count < 128 && sb[2] >= 128) k->recovery_count++;
-        k->block_count++;
+        if (bk.block_count < 128 && sb[2] >= 128) bk.recovery_count++;
+        bk.block_count++;
     }
     const size_t nf = start.size();
     if (nf > frame_capacity) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of frames closed by this call");
@@ -1456,7 +1611,14 @@ extern "C" int sdrd_src_feed(sdrd_src* k, const uint8_t* dg, size_t n, uint8_t* 
             if (nb_recovery) nb_recovery[f] = fr_recovery[f];
         }
     }
-    /* ---- keep the open slot's first <= 128 datagrams for the next call ---- */
+    /* ---- commit: counters, and the open slot's first <= 128 datagrams for the next call ---- */
+    k->frame_head = bk.frame_head;
+    k->block_count = bk.block_count;
+    k->recovery_count = bk.recovery_count;
+    k->cur_nb_blocks = bk.cur_nb_blocks;
+    k->cur_nb_recovery = bk.cur_nb_recovery;
+    k->min_nb_blocks = bk.min_nb_blocks;
+    k->max_nb_recovery = bk.max_nb_recovery;
     {
         const int have = k->block_count < 128 ? k->block_count : 128;
         if (nf == 0) {

@@ -207,17 +207,14 @@ public:
         samples_out.resize(n_out);
         sampleSize = ss;
     }
-    /* decimation 1 path (Downsampler.cpp:69-72): in place */
+    /* decimation 1 path (Downsampler.cpp:69-72): Decimators::decimate1 in place, no filter state involved */
     void rescale(unsigned int& sampleSize, IQSampleVector& samples_inout)
     {
-        IQSampleVector out;
-        unsigned keep = m_decim;
-        if (m_decim != 0 && m_dec) sdrd_dec_configure(m_dec, 0, (int)m_fcPos);
-        m_decim = 0;
-        process(sampleSize, samples_inout, out);
-        if (keep != 0 && m_dec) sdrd_dec_configure(m_dec, (int)keep, (int)m_fcPos);
-        m_decim = keep;
-        samples_inout.swap(out);
+        if (!m_dec) return;
+        unsigned ss = sampleSize;
+        if (sdrd_dec_rescale(m_dec, reinterpret_cast<int16_t*>(samples_inout.data()), samples_inout.size(), samples_inout.size(), &ss) != 0)
+            m_error = sdrd_last_error();
+        sampleSize = ss;
     }
     operator bool() const { return m_error.empty(); }
     std::string error()
@@ -384,7 +381,7 @@ public:
     typedef void (*datagram_tap)(void* user, const uint8_t* datagram, int frame_blocks, int block);
 
     UDPSinkFEC(const std::string& address, unsigned int port, std::size_t max_block = 1 << 20)
-        : UDPSink(address, port, SDRD_UDPSIZE), m_sink(nullptr), m_nbBlocksFEC(1), m_txDelay(0), m_running(true),
+        : UDPSink(address, port, SDRD_UDPSIZE), m_sink(nullptr), m_nbBlocksFEC(0) /* UDPSinkFEC.cpp:31 */, m_txDelay(0), m_running(true),
           m_tap(nullptr), m_tapUser(nullptr), m_puncture(-1)
     {
         if (sdrd_sink_create(&m_sink, 1, max_block) != 0) m_error = sdrd_last_error();
@@ -609,8 +606,9 @@ private:
             return;
         }
         m_lastStatus = status;
-        /* meta data of a frame whose block 0 arrived or was recovered (SDRdaemonFECBuffer.cpp:215-247) */
-        if (nb == 128 && (m_metaRetrieved || status == SDRD_FRAME_RECOVERED)) {
+        /* meta data only of a complete frame whose block 0 ARRIVED (SDRdaemonFECBuffer.cpp:237-246; accepting a
+         * recovered block 0 is commented out in the reference, :215-218) */
+        if (nb == 128 && m_metaRetrieved) {
             if (memcmp(block0, &m_currentMeta, 12) != 0) memcpy(&m_currentMeta, block0, sizeof(m_currentMeta));
             m_sampleBytes = m_currentMeta.m_sampleBytes & 0x0F;
             m_sampleBits = m_currentMeta.m_sampleBits;
@@ -646,7 +644,7 @@ public:
         }
         if (m.find("txdelay") != m.end()) {
             int txDelay = atoi(m["txdelay"].c_str());
-            if (txDelay >= 0) m_txDelay = (unsigned)txDelay;
+            m_txDelay = txDelay < 0 ? 0u : (unsigned)txDelay; /* DeviceSource.cpp:61-66 */
         }
         return configure(m);
     }

@@ -2,6 +2,8 @@
 through the C ABI (sdrdaemon_b200.capi) and compares with the oracle on the same seeded input."""
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 from sdrdaemon_b200 import capi
@@ -183,7 +185,7 @@ def erasure_cases(rng, frames, F):
     cases = []
     n = len(frames)
     for f in range(n):
-        k = f % 12
+        k = f % 13
         if k == 0:
             sel = list(range(128))
         elif k == 1:
@@ -216,10 +218,17 @@ def erasure_cases(rng, frames, F):
             ne = min(16, F)
             er = set(rng.choice(128, ne, replace=False).tolist())
             sel = [i for i in range(128) if i not in er] + list(range(128, 128 + ne))
-        else:
+        elif k == 11:
             ne = min(33, F)
             er = set(rng.choice(128, ne, replace=False).tolist())
             sel = [i for i in range(128) if i not in er] + list(range(128 + F - ne, 128 + F))
+        else:
+            # a duplicated recovery datagram: two equal rows, no solution -- cm256_decode's elimination cannot
+            # succeed, the frame is reported as failed and the originals that arrived pass through
+            ne = min(6, F)
+            er = set(rng.choice(128, ne, replace=False).tolist())
+            rec = list(range(128, 128 + ne - 1))
+            sel = [i for i in range(128) if i not in er] + rec[:2] + [rec[0]] + rec[2:]
         cases.append(sel)
     return cases
 
@@ -296,3 +305,74 @@ def check_receiver(lib, ob, dg, cuts):
     assert src.min_nb_blocks() == 256 and fb.min_nb_blocks() == 256  # the getters reset
     src.close()
     return n_checked
+
+
+def check_rx_sample_bits(lib, ob, M, bits, x, F=4):
+    """The fused Rx path with an 8- or 12-bit source (sdrdaemonrx.cpp:618-643): the decimator runs with the source's
+    sample size, and the frames' meta data carry the decimator's output size (the source's own when decim = 0)."""
+    S, n, _ = x.shape
+    rx = capi.Rx(M, n_streams=S, max_in=n, n_fec=F, lib=lib)
+    got = rx.process(x, sample_bits=bits)
+    for s in range(S):
+        y, ss = ob.Decimator(M).process(x[s], bits)
+        mb = bits if M == 0 else ss
+        assert rx.sample_bits_out == ss, (rx.sample_bits_out, ss)
+        sk = ob.Sink(n_fec=F, sample_bits=mb, sample_bytes=(mb - 1) // 8 + 1)
+        sk.write(y)
+        want = np.stack(sk.frames)
+        assert got[s].shape == want.shape, (got[s].shape, want.shape)
+        assert np.array_equal(got[s], want), f"decim {M}, {bits}-bit source, stream {s}: datagrams differ"
+    rx.close()
+
+
+def check_refused_calls_leave_state(lib, ob):
+    """A call refused with SDRD_EINVAL / SDRD_ERANGE must not move the handle's state."""
+    rng = np.random.default_rng(99)
+    # receiver: frame_capacity too small -> ERANGE, then the same burst again with room
+    x, frames = make_frames(ob, rng, 3, 8)
+    dg = np.concatenate([frames[0][:100], frames[1], frames[2][:50]])
+    src = capi.Source(max_datagrams=len(dg), lib=lib)
+    src.feed(dg[:60])
+    n_fr = C.c_size_t(0)
+    pay = np.zeros((1, 127, 508), np.uint8)
+    st = np.zeros(1, np.int32)
+    rc = lib.sdrd_src_feed(src._h, dg[60:].ctypes.data, len(dg) - 60, pay.ctypes.data, None, 1, C.byref(n_fr), st.ctypes.data, None, None)
+    assert rc == capi_code("SDRD_ERANGE"), rc
+    p2, _, st2, nbl, _ = src.feed(dg[60:])
+    ref = capi.Source(max_datagrams=len(dg), lib=lib)
+    ref.feed(dg[:60])
+    p3, _, st3, nbl3, _ = ref.feed(dg[60:])
+    assert np.array_equal(p2, p3) and list(st2) == list(st3) and list(nbl) == list(nbl3) == [100, 136]
+    assert src.stats() == ref.stats()
+    # fused rx: frame_capacity too small -> ERANGE before the decimator or the sink have moved
+    M, F = 2, 4
+    n = (2 * FRAME + 100) << M
+    xs = rand_iq(rng, (1, n))
+    rx = capi.Rx(M, max_in=n, n_fec=F, lib=lib)
+    out = np.zeros((1, 1, 128 + F, 512), np.uint8)
+    nfr = C.c_size_t(0)
+    rc = lib.sdrd_rx_process(rx._h, xs.ctypes.data, n, n, out.ctypes.data, 1, C.byref(nfr), None)
+    assert rc == capi_code("SDRD_ERANGE"), rc
+    got = rx.process(xs)
+    y, _ = ob.Decimator(M).process(xs[0])
+    sk = ob.Sink(n_fec=F)
+    sk.write(y)
+    assert np.array_equal(got[0], np.stack(sk.frames))
+    # decimator: out_stride too small with two streams -> EINVAL, history untouched
+    xd = rand_iq(rng, (2, 4000))
+    d = capi.Decimator(3, n_streams=2, max_in=4000, lib=lib)
+    d.process(xd[:, :2000])
+    yb = np.zeros((2, 10, 2), np.int16)
+    no = C.c_size_t(0)
+    ss = C.c_uint(16)
+    rc = lib.sdrd_dec_process(d._h, np.ascontiguousarray(xd[:, 2000:]).ctypes.data, 2000, 2000, yb.ctypes.data, 10, C.byref(no), C.byref(ss))
+    assert rc == capi_code("SDRD_EINVAL"), rc
+    y2, _ = d.process(xd[:, 2000:])
+    for s in range(2):
+        o = ob.Decimator(3)
+        o.process(xd[s, :2000])
+        assert np.array_equal(y2[s], o.process(xd[s, 2000:])[0])
+
+
+def capi_code(name):
+    return {"SDRD_EINVAL": -1, "SDRD_ENODEV": -2, "SDRD_ECUDA": -3, "SDRD_ENOMEM": -4, "SDRD_ERANGE": -5}[name]

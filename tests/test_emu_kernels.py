@@ -153,13 +153,12 @@ def test_golden_through_emulation(emu_lib):
     golden_cases.check_fecbuffer_golden(lambda sb: capi.fec_decode(sb[None], [len(sb)], lib=emu_lib)[0][0])
 
 
-def test_rx_pipeline_sliced(emu_lib, oracle, monkeypatch):
+def test_rx_pipeline_sliced(emu_lib, oracle):
     """sdrd_rx_process in 8 overlapped slices (what large calls do) gives the same datagrams"""
-    monkeypatch.setenv("SDRD_RX_SLICE_BYTES", "1")
-    test_rx_pipeline(emu_lib, oracle)
+    test_rx_pipeline(emu_lib, oracle, slice_bytes=1)
 
 
-def test_rx_pipeline(emu_lib, oracle):
+def test_rx_pipeline(emu_lib, oracle, slice_bytes=0):
     from sdrdaemon_b200 import capi
 
     rng = np.random.default_rng(700)
@@ -167,9 +166,39 @@ def test_rx_pipeline(emu_lib, oracle):
     n = (cases.FRAME + 300) << M
     x = cases.rand_iq(rng, (S, 2 * n))
     rx = capi.Rx(M, n_streams=S, max_in=n, n_fec=F, lib=emu_lib)
+    rx.set_slice_bytes(slice_bytes)
     got = np.concatenate([rx.process(x[:, :n]), rx.process(x[:, n:])], axis=1)
     for s in range(S):
         y, _ = oracle.Decimator(M).process(x[s])
         sk = oracle.Sink(n_fec=F)
         sk.write(y)
         assert np.array_equal(got[s], np.stack(sk.frames))
+
+
+@pytest.mark.parametrize("M,bits", [(0, 8), (0, 12), (2, 8), (4, 8), (4, 12), (6, 12)])
+def test_rx_pipeline_sample_bits(emu_lib, oracle, M, bits):
+    """8- / 12-bit sources through the fused path (sample_bits was hard-coded to 16)"""
+    rng = np.random.default_rng(720 + M + bits)
+    n = (cases.FRAME + 50) << M
+    cases.check_rx_sample_bits(emu_lib, oracle, M, bits, cases.rand_iq(rng, (2, n), bits))
+
+
+def test_refused_calls_leave_state(emu_lib, oracle):
+    cases.check_refused_calls_leave_state(emu_lib, oracle)
+
+
+def test_rescale_keeps_filter_state(emu_lib, oracle):
+    """Downsampler::rescale (static decimate1) between two process calls must not disturb the cascade"""
+    from sdrdaemon_b200 import capi
+
+    rng = np.random.default_rng(730)
+    x = cases.rand_iq(rng, (1, 6000), 12)
+    d = capi.Decimator(3, max_in=6000, lib=emu_lib)
+    o = oracle.Decimator(3)
+    y1, _ = d.process(x[:, :3000], 12)
+    z = x[0, :500].copy()
+    ss = cases.C.c_uint(12)
+    emu_lib.check(emu_lib.sdrd_dec_rescale(d._h, z.ctypes.data, 500, 500, cases.C.byref(ss)))
+    assert np.array_equal(z, (x[0, :500].astype(np.int32) << 4).astype(np.int16)) and ss.value == 12
+    y2, _ = d.process(x[:, 3000:], 12)
+    assert np.array_equal(y1[0], o.process(x[0, :3000], 12)[0]) and np.array_equal(y2[0], o.process(x[0, 3000:], 12)[0])

@@ -295,16 +295,16 @@ def test_receiver_batched(gpu_lib, oracle):
         assert cases.check_receiver(gpu_lib, oracle, dg, [0, 3, 3, 129, 500, 501, 1200, n]) >= 13
 
 
-def test_rx_pipeline_sliced(gpu_lib, oracle, monkeypatch):
+def test_rx_pipeline_sliced(gpu_lib, oracle):
     """the overlapped (sliced) form of sdrd_rx_process, forced on a small input, DB variant, 3 streams"""
     from sdrdaemon_b200 import capi
 
-    monkeypatch.setenv("SDRD_RX_SLICE_BYTES", "1")
     rng = np.random.default_rng(710)
     M, F, S = 3, 8, 3
     n = (2 * cases.FRAME + 1234) << M
     x = cases.rand_iq(rng, (S, 2 * n))
     rx = capi.Rx(M, n_streams=S, max_in=n, n_fec=F, variant=1, lib=gpu_lib)
+    rx.set_slice_bytes(1)
     got = np.concatenate([rx.process(x[:, :n]), rx.process(x[:, n:])], axis=1)
     for s in range(S):
         y, _ = oracle.Decimator(M, 2, 1).process(x[s])
@@ -350,3 +350,32 @@ def test_rx_pipeline_config3_shape(gpu_lib, oracle):
     sb = np.concatenate([got[:, 0, 20:128], got[:, 0, 128:148]], axis=1)
     pay, b0, st = capi.fec_decode(sb, 128, lib=gpu_lib)
     assert (st == 2).all() and np.array_equal(pay, got[:, 0, 1:128, 4:])
+
+
+@pytest.mark.parametrize("M,bits", [(0, 8), (0, 12), (1, 8), (2, 12), (4, 8), (4, 12), (5, 8), (6, 12)])
+def test_rx_pipeline_sample_bits(gpu_lib, oracle, M, bits):
+    """8- / 12-bit sources (RTL-SDR, Airspy) through the fused path: the decimator runs with the source's sample size
+    and the meta data carry its output size (sdrdaemonrx.cpp:618-643)"""
+    rng = np.random.default_rng(7200 + M + bits)
+    n = (2 * cases.FRAME + 50) << M
+    cases.check_rx_sample_bits(gpu_lib, oracle, M, bits, cases.rand_iq(rng, (3, n), bits))
+
+
+def test_refused_calls_leave_state(gpu_lib, oracle):
+    cases.check_refused_calls_leave_state(gpu_lib, oracle)
+
+
+def test_rescale_keeps_filter_state(gpu_lib, oracle):
+    from sdrdaemon_b200 import capi
+
+    rng = np.random.default_rng(7300)
+    x = cases.rand_iq(rng, (1, 200000), 8)
+    d = capi.Decimator(5, max_in=100000, lib=gpu_lib)
+    o = oracle.Decimator(5)
+    y1, _ = d.process(x[:, :100000], 8)
+    z = x[0, :70000].copy()
+    ss = cases.C.c_uint(8)
+    gpu_lib.check(gpu_lib.sdrd_dec_rescale(d._h, z.ctypes.data, len(z), len(z), cases.C.byref(ss)))
+    assert np.array_equal(z, (x[0, :70000].astype(np.int32) << 8).astype(np.int16)) and ss.value == 8
+    y2, _ = d.process(x[:, 100000:], 8)
+    assert np.array_equal(y1[0], o.process(x[0, :100000], 8)[0]) and np.array_equal(y2[0], o.process(x[0, 100000:], 8)[0])
