@@ -147,6 +147,34 @@ long long sdrd_int_launches(const sdrd_int* up);
 int sdrd_cm256_encode(const uint8_t* originals, size_t block_pitch, int n_frames, int recovery_count,
                       uint8_t* recovery);
 
+/* The library-level seam under the FEC classes: cm256cc's descriptor API exactly as the reference calls it
+ *   CM256::cm256_encode(params, blocks, recoveryBlocks)   sdmnbase/UDPSinkFEC.cpp:228-246
+ *   CM256::cm256_decode(params, blocks)                   sdmnbase/SDRdaemonFECBuffer.cpp:148-163,176,197
+ * (and the C form cm256_encode / cm256_decode of gr-sdrdaemon/lib/SDRdaemonFECBuffer.cpp:40,191).
+ * include/cm256.h wraps these two calls in the `CM256` class and the C functions, so that the reference's
+ * UDPSinkFEC.cpp / SDRdaemonFECBuffer.cpp compile unmodified against this library.
+ *   - HOST pointers; one superframe per call; returns 0 on success, non-zero otherwise, like cm256.
+ *   - This library implements sdrdaemon's superframe only: OriginalCount must be 128, BlockBytes 1..508
+ *     (UDPSinkFEC.cpp:228-230, SDRdaemonFECBuffer.cpp:32-34); other shapes are refused with SDRD_EINVAL.
+ *   - encode: blocks[j].Block is original j (Index is ignored, as in cm256); recovery receives RecoveryCount
+ *     contiguous blocks of BlockBytes.
+ *   - decode: blocks[0 .. 127] are the received blocks in any order, Index < 128 = original, else recovery row.
+ *     On success every recovery descriptor's buffer holds a recovered original and its Index is rewritten to
+ *     that original's index (erased indices ascending, paired with the recovery descriptors in array order).
+ *     A repeated original or a repeated recovery row is refused.  params.RecoveryCount == 1 takes cm256's XOR
+ *     shortcut (the lone recovery block is assumed to be row 128). */
+typedef struct sdrd_cm256_block {
+    void* Block;
+    unsigned char Index;
+} sdrd_cm256_block;
+typedef struct sdrd_cm256_params {
+    int OriginalCount;
+    int RecoveryCount;
+    int BlockBytes;
+} sdrd_cm256_params;
+int sdrd_cm256_encode_blocks(sdrd_cm256_params params, const sdrd_cm256_block* originals, void* recovery);
+int sdrd_cm256_decode_blocks(sdrd_cm256_params params, sdrd_cm256_block* blocks);
+
 /* ------------------------------------------------------------------------------------------
  * Sender: UDPSinkFEC framing + encode
  *   replaces  UDPSinkFEC::write (sdmnbase/UDPSinkFEC.cpp:79-191) and the encode half of

@@ -28,6 +28,10 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
     if ref and os.path.isdir("/root/reference/sdmnbase"):
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        # the reference's sender / receiver sources over include/cm256.h and its two main programs over the host
+        # layer (both link the product library: it has to be built first)
+        if os.path.exists(os.path.join(HERE, "..", "sdrdaemon_b200", "libsdrd_b200.so")):
+            subprocess.run(["make", "-s", "-C", HERE, "seam", "mains"], check=True)
 
 
 class _Block(C.Structure):

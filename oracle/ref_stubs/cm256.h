@@ -6,6 +6,14 @@
 #ifndef SDRD_STUB_CM256_H
 #define SDRD_STUB_CM256_H
 #include "../sdrd_oracle.h"
+/* the C form (f4exb/cm256) that gr-sdrdaemon/lib/SDRdaemonFECBuffer.cpp:40,191 uses */
+typedef sdro_cm256_params cm256_encoder_params;
+typedef sdro_cm256_block cm256_block;
+static inline int cm256_init(void) { return 0; }
+static inline int cm256_encode(cm256_encoder_params params, cm256_block* originals, void* recoveryBlocks)
+{ return sdro_cm256_encode(params, originals, recoveryBlocks); }
+static inline int cm256_decode(cm256_encoder_params params, cm256_block* blocks)
+{ return sdro_cm256_decode(params, blocks); }
 class CM256 {
 public:
     typedef sdro_cm256_params cm256_encoder_params;

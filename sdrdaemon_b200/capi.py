@@ -90,6 +90,20 @@ SYMBOLS = [
 ]
 
 
+class Cm256Block(C.Structure):
+    _fields_ = [("Block", C.c_void_p), ("Index", C.c_ubyte)]
+
+
+class Cm256Params(C.Structure):
+    _fields_ = [("OriginalCount", C.c_int), ("RecoveryCount", C.c_int), ("BlockBytes", C.c_int)]
+
+
+SYMBOLS += [
+    ("sdrd_cm256_encode_blocks", C.c_int, [Cm256Params, C.POINTER(Cm256Block), _P]),
+    ("sdrd_cm256_decode_blocks", C.c_int, [Cm256Params, C.POINTER(Cm256Block)]),
+]
+
+
 class SdrdError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"sdrd error {code}: {msg}")
@@ -233,6 +247,32 @@ def cm256_encode(originals: np.ndarray, n_fec: int, lib: Optional[Library] = Non
         base = o.ctypes.data + 4
     lib.check(lib.sdrd_cm256_encode(base, b, nf, n_fec, rec.ctypes.data))
     return rec
+
+
+def cm256_encode_blocks(blocks, n_fec: int, block_bytes: int = BLOCK_BYTES, lib: Optional[Library] = None) -> np.ndarray:
+    """cm256_encode through the descriptor API: blocks = list of 128 uint8 arrays (any memory layout)."""
+    lib = lib or load()
+    desc = (Cm256Block * 128)()
+    keep = [np.ascontiguousarray(b, dtype=np.uint8) for b in blocks]
+    for j, b in enumerate(keep):
+        desc[j].Block = b.ctypes.data
+        desc[j].Index = j
+    out = np.zeros((n_fec, block_bytes), dtype=np.uint8)
+    lib.check(lib.sdrd_cm256_encode_blocks(Cm256Params(128, n_fec, block_bytes), desc, out.ctypes.data))
+    return out
+
+
+def cm256_decode_blocks(blocks: np.ndarray, indices, recovery_count: int, lib: Optional[Library] = None):
+    """cm256_decode through the descriptor API, in place on a copy: returns (rc, blocks, rewritten indices)."""
+    lib = lib or load()
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8).copy()
+    k, b = blocks.shape
+    desc = (Cm256Block * k)()
+    for i in range(k):
+        desc[i].Block = blocks[i].ctypes.data
+        desc[i].Index = int(indices[i])
+    rc = lib.sdrd_cm256_decode_blocks(Cm256Params(k, recovery_count, b), desc)
+    return rc, blocks, [desc[i].Index for i in range(k)]
 
 
 def fec_decode(superblocks: np.ndarray, n_blocks, lib: Optional[Library] = None):

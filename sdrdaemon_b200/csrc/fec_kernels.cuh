@@ -351,6 +351,13 @@ struct DecParams {
     uint32_t* block0;          /* frame f: block0 + f * 127 words, may be null */
     int* status;               /* [n_frames] */
     int pass;                  /* 0: frames needing more than DCAP rows are flagged and left; 1: only flagged frames */
+    /* Bare cm256_decode form (sdrd_cm256_decode_blocks): when `recovered` is set nothing is written to payload /
+     * block0; instead the block solved into recovery descriptor k (arrival order) -- erased original k in ascending
+     * order -- goes to recovered[(f * 128 + k) * 127 ..], for EVERY k: copying back only the last N descriptors is
+     * SDRdaemonFECBuffer's doing (.cpp:208-213), not the library's. */
+    uint32_t* recovered;
+    int general_single;        /* 1: a lone recovery block is solved like any other (cm256 takes its XOR shortcut only
+                                  when params.RecoveryCount == 1, not when one recovery block happens to be present) */
     Tables tab;
 };
 
@@ -459,7 +466,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
 
     if (do_decode) {
         /* coefficient matrix D [N][128 columns = image rows] */
-        if (N == 1) {
+        if (N == 1 && !p.general_single) {
             /* cm256's single-recovery shortcut: XOR of everything received, whatever the row */
             for (int k = tid; k < 128 * DCAP; k += NT) sm.coefT[k] = (uint16_t)((k % DCAP) == 0 ? TAB_ENTRY : 0);
         } else {
@@ -537,7 +544,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
     uint32_t* b0 = p.block0 ? p.block0 + (long long)f * 127 : nullptr;
 
     /* originals that arrived go out as they are; blocks that did not arrive read as zero (.cpp:109) */
-    for (int b = tid >> 5; b < 128; b += NT / 32) { /* one warp per block: four coalesced stores, no index division */
+    for (int b = tid >> 5; b < 128 && !p.recovered; b += NT / 32) { /* one warp per block: four coalesced stores, no index division */
         const int row = origRow[b];
         uint32_t* dstb = b == 0 ? b0 : pay + (b - 1) * 127;
         if (!dstb || !(b == 0 || row >= 0 || !do_decode)) continue;
@@ -555,7 +562,15 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
             __syncthreads();
             matvec_pass(sm.img, sm.coefT, DCAP, row0, nrows, sm.tab, sm.rec16, tid);
             __syncthreads();
-            for (int r = tid >> 5; r < nrows; r += NT / 32) {
+            for (int r = tid >> 5; r < nrows && p.recovered; r += NT / 32) {
+                uint32_t* dstb = p.recovered + ((long long)f * 128 + row0 + r) * 127;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = (tid & 31) + 32 * q;
+                    if (i < 127) dstb[i] = sm.rec16[r * ROW_WORDS + 1 + i];
+                }
+            }
+            for (int r = tid >> 5; r < nrows && !p.recovered; r += NT / 32) {
                 const int b = erased[row0 + r];
                 /* The reference copies back only the LAST N descriptors (.cpp:208-213), i.e. it
                  * assumes the recovery blocks arrived after the originals; a recovery block that
@@ -572,7 +587,7 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
             __syncthreads();
         }
         /* erased originals beyond the N recovered ones stay zero */
-        for (int c = N; c < n_missing; c++) {
+        for (int c = N; c < n_missing && !p.recovered; c++) {
             const int b = erased[c];
             for (int i = tid; i < 127; i += NT) {
                 if (b == 0) {

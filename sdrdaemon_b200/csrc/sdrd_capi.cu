@@ -1435,6 +1435,113 @@ extern "C" int sdrd_fec_decode(const uint8_t* superblocks, size_t blocks_pitch, 
     return 0;
 }
 
+/* ---- cm256cc's descriptor API, one superframe per call (the seam include/cm256.h binds) ---- */
+
+static int check_cm256_shape(const sdrd_cm256_params& p)
+{
+    /* cm256's own parameter checks first, then the shape this library implements */
+    if (p.OriginalCount <= 0 || p.RecoveryCount <= 0 || p.BlockBytes <= 0) return fail(SDRD_EINVAL, "cm256: counts and block size must be positive");
+    if (p.OriginalCount + p.RecoveryCount > 256) return fail(SDRD_EINVAL, "cm256: OriginalCount + RecoveryCount exceeds 256");
+    if (p.OriginalCount != SDRD_NB_ORIGINAL || p.BlockBytes > SDRD_BLOCK_BYTES)
+        return fail(SDRD_EINVAL, "cm256: this library implements sdrdaemon's superframe only (OriginalCount 128, BlockBytes <= 508)");
+    return 0;
+}
+
+extern "C" int sdrd_cm256_encode_blocks(sdrd_cm256_params p, const sdrd_cm256_block* originals, void* recovery)
+{
+    if (int rc = check_cm256_shape(p)) return rc;
+    if (!originals || !recovery) return fail(SDRD_EINVAL, "cm256: null pointer");
+    for (int j = 0; j < 128; j++)
+        if (!originals[j].Block) return fail(SDRD_EINVAL, "cm256: null block pointer");
+    /* the blocks of a UDPSinkFEC slot lie 512 bytes apart (UDPSinkFEC.cpp:233-243): no gather needed then */
+    const uint8_t* b0 = (const uint8_t*)originals[0].Block;
+    const ptrdiff_t pitch = (const uint8_t*)originals[1].Block - b0;
+    bool uniform = p.BlockBytes == SDRD_BLOCK_BYTES && pitch >= SDRD_BLOCK_BYTES && (pitch & 3) == 0;
+    for (int j = 2; j < 128 && uniform; j++) uniform = (const uint8_t*)originals[j].Block - b0 == pitch * j;
+    if (uniform) return sdrd_cm256_encode(b0, (size_t)pitch, 1, p.RecoveryCount, (uint8_t*)recovery);
+    /* shorter blocks are zero-extended: the code is byte-wise linear, the padding encodes to zeros */
+    std::vector<uint8_t> tmp((size_t)128 * SDRD_BLOCK_BYTES, 0), out((size_t)p.RecoveryCount * SDRD_BLOCK_BYTES);
+    for (int j = 0; j < 128; j++) memcpy(&tmp[(size_t)j * SDRD_BLOCK_BYTES], originals[j].Block, (size_t)p.BlockBytes);
+    if (int rc = sdrd_cm256_encode(tmp.data(), SDRD_BLOCK_BYTES, 1, p.RecoveryCount, out.data())) return rc;
+    for (int r = 0; r < p.RecoveryCount; r++)
+        memcpy((uint8_t*)recovery + (size_t)r * p.BlockBytes, &out[(size_t)r * SDRD_BLOCK_BYTES], (size_t)p.BlockBytes);
+    return 0;
+}
+
+extern "C" int sdrd_cm256_decode_blocks(sdrd_cm256_params p, sdrd_cm256_block* blocks)
+{
+    if (int rc = check_cm256_shape(p)) return rc;
+    if (!blocks) return fail(SDRD_EINVAL, "cm256: null pointer");
+    /* classification as cm256's decoder initialisation does it */
+    bool present[128] = {false};
+    int rec_pos[128], n_rec = 0;
+    bool rec_seen[128] = {false};
+    for (int i = 0; i < 128; i++) {
+        if (!blocks[i].Block) return fail(SDRD_EINVAL, "cm256: null block pointer");
+        const int idx = blocks[i].Index;
+        if (idx < 128) {
+            if (present[idx]) return fail(SDRD_EINVAL, "cm256: repeated original block");
+            present[idx] = true;
+        } else {
+            /* no bound against RecoveryCount: sdrdaemon passes the NUMBER of recovery blocks received there
+             * (SDRdaemonFECBuffer.cpp:176), their rows are anywhere in 128 .. 255 */
+            if (rec_seen[idx - 128]) return fail(SDRD_EINVAL, "cm256: repeated recovery block (singular system)");
+            rec_seen[idx - 128] = true;
+            rec_pos[n_rec++] = i;
+        }
+    }
+    if (n_rec == 0) return 0; /* nothing erased */
+    if (p.RecoveryCount == 1 && n_rec > 1)
+        return fail(SDRD_EINVAL, "cm256: RecoveryCount is 1 but several recovery blocks were passed");
+    std::string why;
+    if (!rt::device_ok(why)) return fail(SDRD_ENODEV, why);
+    /* the frame as K3 takes it: 128 datagram images in array order, header word = {0, Index, 0} */
+    std::vector<uint8_t> img((size_t)128 * SDRD_UDPSIZE, 0);
+    for (int i = 0; i < 128; i++) {
+        img[(size_t)i * SDRD_UDPSIZE + 2] = blocks[i].Index;
+        memcpy(&img[(size_t)i * SDRD_UDPSIZE + 4], blocks[i].Block, (size_t)p.BlockBytes);
+    }
+    const size_t rec_bytes = (size_t)128 * SDRD_BLOCK_BYTES;
+    if (g_scr_a.ensure(img.size() + 64) || g_scr_b.ensure(rec_bytes)) return fail_cuda("allocating scratch");
+    uint8_t* d_img = (uint8_t*)g_scr_a.p;
+    int* d_nb = (int*)(d_img + img.size());
+    int* d_st = d_nb + 1;
+    const int nb = 128;
+    SDRD_TRY(rt::copy(d_img, img.data(), img.size(), rt::H2D, 0), "copy blocks to device");
+    SDRD_TRY(rt::copy(d_nb, &nb, sizeof nb, rt::H2D, 0), "copy block count");
+    fec::DecParams kp{};
+    if (int rc = get_tables(&kp.tab)) return rc;
+    kp.sb = reinterpret_cast<const uint32_t*>(d_img);
+    kp.blocks_pitch = 128;
+    kp.n_blocks = d_nb;
+    kp.payload = nullptr;
+    kp.block0 = nullptr;
+    kp.status = d_st;
+    kp.recovered = reinterpret_cast<uint32_t*>(g_scr_b.p);
+    kp.general_single = p.RecoveryCount != 1;
+    kp.pass = 0;
+    SDRD_LAUNCH(fec::decode_kernel<32>, 1, 1, fec::NT, fec::dec_smem_bytes<32>(), 0, kp);
+    if (n_rec > 32) {
+        kp.pass = 1;
+        SDRD_LAUNCH(fec::decode_kernel<128>, 1, 1, fec::NT, fec::dec_smem_bytes<128>(), 0, kp);
+    }
+    if (!SDRD_LAUNCH_OK()) return fail_cuda("decode kernel launch");
+    std::vector<uint8_t> out((size_t)n_rec * SDRD_BLOCK_BYTES);
+    int st = 0;
+    SDRD_TRY(rt::copy(out.data(), g_scr_b.p, out.size(), rt::D2H, 0), "copy recovered blocks to host");
+    SDRD_TRY(rt::copy(&st, d_st, sizeof st, rt::D2H, 0), "copy status");
+    SDRD_TRY(rt::sync(0), "cm256 decode");
+    if (st != fec::ST_RECOVERED) return fail(SDRD_EINVAL, "cm256: the block set cannot be decoded");
+    /* in place: recovery descriptor k (array order) receives erased original k (ascending), Index rewritten */
+    int e = 0;
+    for (int k = 0; k < n_rec; k++) {
+        while (present[e]) e++;
+        memcpy(blocks[rec_pos[k]].Block, &out[(size_t)k * SDRD_BLOCK_BYTES], (size_t)p.BlockBytes);
+        blocks[rec_pos[k]].Index = (unsigned char)e++;
+    }
+    return 0;
+}
+
 /* ========================================================================================== */
 /* batched receiver framing                                                                    */
 /* ========================================================================================== */

@@ -45,6 +45,19 @@
 
 #include "../../include/sdrd_b200.h"
 
+#if defined(SDRD_HOST_REFERENCE_TYPES)
+/* Built inside the reference tree (host/compat/ in front of the reference's include/): the glue types are the
+ * reference's own dependency-free headers -- IQSample / IQSampleVector / SampleVector (include/SDRDaemon.h:52-70)
+ * and DataBuffer<T> (include/DataBuffer.h:29-126) -- so that sdrdaemonrx.cpp / sdrdaemontx.cpp see exactly the types
+ * they were written against; only the compute classes below are this library's. */
+#include "DataBuffer.h"
+#include "SDRDaemon.h"
+namespace sdrd_b200 {
+using ::DataBuffer;
+using ::IQSample;
+using ::IQSampleVector;
+static_assert(sizeof(IQSample) == 4, "IQSample is 4 bytes on the wire");
+#else
 namespace sdrd_b200 {
 
 /* ---------------------------------------------------------------- sample types --------------- */
@@ -120,6 +133,7 @@ private:
     std::mutex m_mutex;
     std::condition_variable m_cond;
 };
+#endif
 
 /* "key=value,key=value" (separators , or &), the grammar of include/parsekv.h:40-43 */
 namespace parsekv {
@@ -631,6 +645,13 @@ public:
     DeviceSource() : m_confFreq(0), m_decim(0), m_nbFECBlocks(1), m_txDelay(0), m_fcPos(2), m_buf(0), m_stop_flag(0), m_downsampler(0) {}
     virtual ~DeviceSource() {}
     void associateDownsampler(Downsampler* downsampler) { m_downsampler = downsampler; }
+    /* include/DeviceSource.h:65-78 binds the nanomsg control socket there; the control plane is out of scope
+     * (DESIGN 7): the call is accepted and does nothing, dynamic reconfiguration goes through configure() */
+    void setConfigurationPort(std::uint32_t) {}
+    /* include/DeviceSource.h:96-99 */
+    std::uint64_t get_received_frequency() const { return m_confFreq; }
+    /* include/DeviceSource.h:112 */
+    virtual void print_specific_parms() {}
     /* sdmnbase/DeviceSource.cpp:25-72 */
     bool configure(std::string& configureStr)
     {
@@ -689,6 +710,17 @@ public:
     }
     virtual ~TestSource() { stop(); }
     using DeviceSource::configure;
+    /* sdmnbase/TestSource.cpp:271-275, 371-393 */
+    virtual void print_specific_parms()
+    {
+        fprintf(stderr, "Delta phase:       %g radians\n", (double)m_deltaPhase);
+        fprintf(stderr, "Amplitude:         %g\n", (double)m_amplitude);
+    }
+    static void get_device_names(std::vector<std::string>& devices)
+    {
+        devices.clear();
+        devices.push_back("Test Test dummy device 0000001 0");
+    }
     virtual std::uint32_t get_sample_bits() { return 16; }
     virtual std::uint32_t get_sample_rate() { return (uint32_t)m_srate; }
     virtual std::uint32_t get_frequency() { return (uint32_t)m_freq; }
@@ -785,11 +817,20 @@ private:
 /* include/DeviceSink.h (the members the path uses) */
 class DeviceSink {
 public:
-    DeviceSink() : m_buf(0), m_stop_flag(0) {}
+    DeviceSink() : m_confFreq(0), m_buf(0), m_stop_flag(0), m_upsampler(0), m_udpSource(0) {}
     virtual ~DeviceSink() {}
+    /* include/DeviceSink.h:55-83: the upsampler is configured through the sink's configuration string ("interp"),
+     * the UDP source only feeds the status message of the (out of scope) control port */
+    void associateUpsampler(Upsampler* upsampler) { m_upsampler = upsampler; }
+    void associateUDPSource(UDPSource* udpSource) { m_udpSource = udpSource; }
+    void setConfigurationPort(std::uint32_t) {} /* nanomsg control socket: out of scope, see DeviceSource */
     virtual bool configure(std::string& configureStr) = 0;
+    virtual std::uint32_t get_device_sample_bits() { return 16; }
     virtual std::uint32_t get_sample_rate() = 0;
     virtual std::uint64_t get_frequency() = 0;
+    std::uint64_t get_transmit_frequency() const { return m_confFreq; }
+    virtual void print_specific_parms() {}
+    std::string get_device_name() const { return m_devname; }
     virtual bool start(DataBuffer<IQSample>* buf, std::atomic_bool* stop_flag) = 0;
     virtual bool stop() = 0;
     virtual operator bool() const = 0;
@@ -801,16 +842,23 @@ public:
     }
 
 protected:
-    std::string m_error;
+    std::string m_devname, m_error;
+    uint64_t m_confFreq;
     DataBuffer<IQSample>* m_buf;
     std::atomic_bool* m_stop_flag;
+    Upsampler* m_upsampler;
+    UDPSource* m_udpSource;
 };
 
 /* include/FileSink.h + sdmnbase/FileSink.cpp: .sdriq = {u32 rate, u64 freq, time_t stamp} then raw
  * int16 I/Q (FileSink.cpp:179-193,242-246).  Keys: file, srate, freq. */
 class FileSink : public DeviceSink {
 public:
-    FileSink() : m_srate(48000), m_freq(435000000), m_thread(0), m_fixedStamp(-1) {}
+    FileSink(int dev_index = 0) : m_srate(48000), m_freq(435000000), m_thread(0), m_fixedStamp(-1)
+    {
+        (void)dev_index;
+        m_devname = "FileSink";
+    }
     virtual ~FileSink() { stop(); }
     virtual bool configure(std::string& configureStr)
     {
@@ -820,9 +868,15 @@ public:
         if (m.find("srate") != m.end()) m_srate = (uint32_t)atoi(m["srate"].c_str());
         if (m.find("freq") != m.end()) m_freq = strtoull(m["freq"].c_str(), 0, 10);
         if (m.find("stamp") != m.end()) m_fixedStamp = atoll(m["stamp"].c_str());
+        /* DeviceSink::configure (sdmnbase/DeviceSink.cpp:26-66): the associated upsampler takes "interp" */
+        if (m_upsampler && !m_upsampler->configure(m)) { m_error = m_upsampler->error(); return false; }
+        m_confFreq = m_freq;
         if (m_fileName.empty()) { m_error = "No file name"; return false; }
         return openFile();
     }
+    /* sdmnbase/FileSink.cpp:58-61,73-76 */
+    static void get_device_names(std::vector<std::string>& devices) { devices.push_back("file"); }
+    virtual void print_specific_parms() { fprintf(stderr, "File name:         %s\n", m_fileName.c_str()); }
     virtual std::uint32_t get_sample_rate() { return m_srate; }
     virtual std::uint64_t get_frequency() { return m_freq; }
     virtual operator bool() const { return m_error.empty(); }
@@ -858,14 +912,20 @@ private:
         m_ofstream.write((const char*)&stamp, sizeof(stamp));
         return true;
     }
+    /* FileSink::run (sdmnbase/FileSink.cpp:216-277) polls the queue instead of blocking in pull(), so that a stop
+     * request is seen while the queue is empty; what is still queued at that moment is written out (the reference
+     * drops it) */
     static void run(FileSink* self)
     {
-        while (!self->m_stop_flag->load() || self->m_buf->queued_samples() > 0) {
-            if (self->m_buf->pull_end_reached()) break;
+        auto write_one = [self]() {
             IQSampleVector v = self->m_buf->pull();
-            if (v.empty()) break;
-            self->m_ofstream.write((const char*)v.data(), (std::streamsize)(v.size() * sizeof(IQSample)));
+            if (!v.empty()) self->m_ofstream.write((const char*)v.data(), (std::streamsize)(v.size() * sizeof(IQSample)));
+        };
+        while (!self->m_stop_flag->load() && !self->m_buf->pull_end_reached()) {
+            if (self->m_buf->queued_samples() > 0) write_one();
+            else usleep(500);
         }
+        while (self->m_buf->queued_samples() > 0) write_one();
         self->m_ofstream.flush();
     }
     std::string m_fileName;

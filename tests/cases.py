@@ -376,3 +376,52 @@ def check_refused_calls_leave_state(lib, ob):
 
 def capi_code(name):
     return {"SDRD_EINVAL": -1, "SDRD_ENODEV": -2, "SDRD_ECUDA": -3, "SDRD_ENOMEM": -4, "SDRD_ERANGE": -5}[name]
+
+
+def check_cm256_blocks(lib, ob):
+    """cm256cc's descriptor API (what include/cm256.h binds): sdrd_cm256_encode_blocks / sdrd_cm256_decode_blocks
+    against the restated cm256_encode / cm256_decode -- same recovered bytes in the same descriptors, same rewritten
+    Index values, same refusals."""
+    rng = np.random.default_rng(555)
+    o = rng.integers(0, 256, size=(128, 508), dtype=np.uint8)
+    for F in (1, 5, 32, 128):
+        want = ob.cm256_encode(o, F)
+        assert np.array_equal(capi.cm256_encode_blocks(list(o), F, lib=lib), want)            # scattered buffers
+        img = np.zeros((128, 512), np.uint8)                                                   # UDPSinkFEC's 512-byte pitch
+        img[:, 4:] = o
+        assert np.array_equal(capi.cm256_encode_blocks([img[j, 4:] for j in range(128)], F, lib=lib), want)
+    short = o[:, :100].copy()                                                                  # BlockBytes < 508
+    assert np.array_equal(capi.cm256_encode_blocks(list(short), 7, block_bytes=100, lib=lib), ob.cm256_encode(short, 7))
+    rec = ob.cm256_encode(o, 64)
+    for trial, ne in enumerate((1, 2, 7, 20, 32, 33, 64)):
+        er = sorted(rng.choice(128, ne, replace=False).tolist())
+        rows = sorted(rng.choice(64, ne, replace=False).tolist()) if ne > 1 else [0]
+        blocks = np.concatenate([np.delete(o, er, axis=0), rec[rows]])
+        idx = [i for i in range(128) if i not in er] + [128 + r for r in rows]
+        if trial % 2:  # any arrival order
+            perm = rng.permutation(128)
+            blocks, idx = blocks[perm], [idx[i] for i in perm]
+        rc, out, new_idx = capi.cm256_decode_blocks(blocks, idx, ne, lib=lib)
+        rco, outo, new_idxo = ob.cm256_decode(blocks, idx, 128, ne)
+        assert rc == rco == 0 and new_idx == new_idxo and np.array_equal(out, outo), (ne, rc, rco)
+        for k in range(128):
+            assert np.array_equal(out[k], o[new_idx[k]])
+    # a lone recovery block that is NOT row 128: solved properly when RecoveryCount says more blocks exist,
+    # XOR shortcut (upstream's assumption) when RecoveryCount == 1 -- both as the restated library does
+    blocks = np.concatenate([np.delete(o, [9], axis=0), rec[3:4]])
+    idx = [i for i in range(128) if i != 9] + [131]
+    for rcount in (4, 1):
+        rc, out, new_idx = capi.cm256_decode_blocks(blocks, idx, rcount, lib=lib)
+        rco, outo, new_idxo = ob.cm256_decode(blocks, idx, 128, rcount)
+        assert rc == rco == 0 and new_idx == new_idxo and np.array_equal(out, outo), rcount
+        assert np.array_equal(out[127], o[9]) == (rcount == 4)
+    # nothing erased: untouched; refusals: repeated original, repeated recovery row, foreign shapes
+    rc, out, new_idx = capi.cm256_decode_blocks(o, list(range(128)), 3, lib=lib)
+    assert rc == 0 and np.array_equal(out, o) and new_idx == list(range(128))
+    dup = [0] + list(range(127))
+    assert capi.cm256_decode_blocks(o, dup, 3, lib=lib)[0] != 0 and ob.cm256_decode(o, dup, 128, 3)[0] != 0
+    blocks = np.concatenate([o[:126], rec[2:3], rec[2:3]])
+    idxd = list(range(126)) + [130, 130]
+    assert capi.cm256_decode_blocks(blocks, idxd, 2, lib=lib)[0] != 0 and ob.cm256_decode(blocks, idxd, 128, 2)[0] != 0
+    assert capi.cm256_decode_blocks(o[:64], list(range(64)), 2, lib=lib)[0] != 0   # OriginalCount != 128
+    assert lib.sdrd_cm256_encode_blocks(capi.Cm256Params(128, 129, 508), None, None) != 0
