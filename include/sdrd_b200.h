@@ -192,8 +192,13 @@ int sdrd_sink_set_meta(sdrd_sink* sink, uint32_t center_freq_khz, uint32_t sampl
                        uint8_t sample_bits);
 /* UDPSinkFEC::setNbBlocksFEC */
 int sdrd_sink_set_nb_fec(sdrd_sink* sink, int nb_fec);
-/* Timestamp written into block 0 of frames started from now on.  Without it the wall clock is read
- * (gettimeofday, UDPSinkFEC.cpp:95) once per write call. use_fixed = 0 returns to the wall clock. */
+/* Time stamp written into block 0 of frames started from now on.  The reference reads the wall clock when the
+ * first sample of a frame is written (gettimeofday, UDPSinkFEC.cpp:89-95).  `use_fixed` is a set of two flags:
+ *   bit 0  the time of a call is (tv_sec, tv_usec) instead of the wall clock read at the call;
+ *   bit 1  per-frame stamps: a frame begun `o` samples into a call is stamped  time of the call + o / sample_rate
+ *          (whole microseconds) -- what a caller feeding the sink in real time, block by block, sees from the
+ *          reference.  Without it every frame begun in one call carries the call's time.
+ * 0 = wall clock, one stamp per call (default). */
 int sdrd_sink_set_time(sdrd_sink* sink, int use_fixed, uint32_t tv_sec, uint32_t tv_usec);
 /* Datagrams per completed frame with the current FEC setting: 128 + nb_fec. */
 int sdrd_sink_blocks_per_frame(const sdrd_sink* sink);

@@ -389,8 +389,10 @@ class Sink:
     def set_nb_fec(self, n_fec: int):
         self.lib.check(self.lib.sdrd_sink_set_nb_fec(self._h, n_fec))
 
-    def set_time(self, tv_sec: int, tv_usec: int = 0, fixed: bool = True):
-        self.lib.check(self.lib.sdrd_sink_set_time(self._h, 1 if fixed else 0, tv_sec, tv_usec))
+    def set_time(self, tv_sec: int, tv_usec: int = 0, fixed: bool = True, per_frame: bool = False):
+        """fixed: the time of a call is (tv_sec, tv_usec) instead of the wall clock; per_frame: every frame begun in a
+        call is stamped with the call's time + its sample offset / sample_rate (UDPSinkFEC.cpp:89-95)"""
+        self.lib.check(self.lib.sdrd_sink_set_time(self._h, (1 if fixed else 0) | (2 if per_frame else 0), tv_sec, tv_usec))
 
     @property
     def blocks_per_frame(self) -> int:

@@ -136,6 +136,17 @@ SDRD_DEVICE Smem carve(unsigned char* base, int cstride)
     s.extra = reinterpret_cast<uint8_t*>(s.coefT + 128 * cstride);
     return s;
 }
+/* CRC-32/IEEE (boost::crc_32_type, UDPSinkFEC.cpp:106-109) over the 20 meta bytes held in five words */
+SDRD_DEVICE uint32_t crc32_meta(const uint32_t* w5)
+{
+    uint32_t c = 0xFFFFFFFFu;
+    for (int i = 0; i < 20; i++) {
+        c ^= (w5[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+    }
+    return c ^ 0xFFFFFFFFu;
+}
+
 SDRD_DEVICE void load_tables(const Smem& s, const Tables& t, int tid)
 {
     for (int i = tid; i < 256; i += NT) {
@@ -157,6 +168,10 @@ struct EncParams {
     int n_pending;
     uint32_t meta_first[6];    /* block-0 payload (24 bytes) of a frame begun in an earlier call */
     uint32_t meta_next[6];     /* block-0 payload of frames begun in this call */
+    /* per-frame time stamps: the reference reads the clock when the first sample of a frame is written
+     * (UDPSinkFEC.cpp:89-95).  With stamp_rate != 0 a frame begun `o` samples into this call is stamped
+     * meta_next's time + o / stamp_rate (whole microseconds) and its CRC-32 is computed here. */
+    uint32_t stamp_rate;
     unsigned frame_index0;     /* frame counter of the first frame completed by this call */
     uint32_t* dgrams;          /* stream s, frame f: dgrams + s * dgram_stride + f * (128 + F) * 128 */
     long long dgram_stride;    /* words */
@@ -252,11 +267,21 @@ SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
         const unsigned frame_index = (p.frame_index0 + (unsigned)f) & 0xFFFFu;
         if (p.mode == 0) {
             /* UDPSinkFEC::write: block 0 = meta data, blocks 1..127 = 127 samples each */
-            const uint32_t* meta = (f == 0 && p.n_pending > 0) ? p.meta_first : p.meta_next;
+            const bool begun_earlier = f == 0 && p.n_pending > 0;
+            const uint32_t* meta = begun_earlier ? p.meta_first : p.meta_next;
             for (int k = tid; k < ROW_WORDS; k += ENC_NT) {
                 uint32_t v = 0;
                 if (k == 0) v = frame_index;
                 else if (k <= 6) v = meta[k - 1];
+                if (p.stamp_rate && !begun_earlier && k >= 4 && k <= 6) {
+                    /* frame begun (long long)f * FRAME_SAMPLES - n_pending samples into this call */
+                    uint32_t m5[5] = {meta[0], meta[1], meta[2], 0u, 0u};
+                    const unsigned long long o = (unsigned long long)((long long)f * FRAME_SAMPLES - p.n_pending);
+                    const unsigned long long us = (unsigned long long)meta[4] + o * 1000000ull / p.stamp_rate;
+                    m5[3] = meta[3] + (uint32_t)(us / 1000000ull);
+                    m5[4] = (uint32_t)(us % 1000000ull);
+                    v = k == 4 ? m5[3] : k == 5 ? m5[4] : crc32_meta(m5);
+                }
                 im[k] = v;
             }
             for (int k = tid; k < 127; k += ENC_NT) im[(k + 1) * ROW_WORDS] = frame_index | ((uint32_t)(k + 1) << 16);

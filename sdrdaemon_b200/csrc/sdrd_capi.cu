@@ -839,6 +839,7 @@ struct sdrd_sink {
     uint8_t sample_bytes = 2, sample_bits = 16;
     int nb_fec = 0;
     bool fixed_time = false;
+    bool frame_clock = false;       /* stamp every frame begun in a call with the call's time + its sample offset / rate */
     uint32_t tv_sec = 0, tv_usec = 0;
     uint32_t pending_meta[6] = {0, 0, 0, 0, 0, 0};
     unsigned frame_count = 0;       /* m_frameCount, uint16 wrap */
@@ -921,7 +922,9 @@ extern "C" int sdrd_sink_set_time(sdrd_sink* k, int use_fixed, uint32_t tv_sec, 
 {
     if (!k) return fail(SDRD_EINVAL, "null handle");
     SDRD_ON_DEVICE_OF(k);
-    k->fixed_time = use_fixed != 0;
+    if (use_fixed < 0 || use_fixed > 3) return fail(SDRD_EINVAL, "time mode must be 0..3");
+    k->fixed_time = (use_fixed & 1) != 0;
+    k->frame_clock = (use_fixed & 2) != 0;
     k->tv_sec = tv_sec;
     k->tv_usec = tv_usec;
     return 0;
@@ -933,14 +936,12 @@ extern "C" size_t sdrd_sink_frames_for(const sdrd_sink* k, size_t n)
 }
 
 /* MetaDataFEC (include/UDPSinkFEC.h:77-99) as six little-endian words */
-static void build_meta(const sdrd_sink* k, uint32_t out[6])
+static void build_meta(const sdrd_sink* k, uint32_t out[6], uint32_t sec, uint32_t usec, unsigned long long offset_samples = 0)
 {
-    uint32_t sec = k->tv_sec, usec = k->tv_usec;
-    if (!k->fixed_time) {
-        struct timeval tv;
-        gettimeofday(&tv, 0);
-        sec = (uint32_t)tv.tv_sec;
-        usec = (uint32_t)tv.tv_usec;
+    if (offset_samples && k->frame_clock && k->sample_rate) {
+        const unsigned long long us = (unsigned long long)usec + offset_samples * 1000000ull / k->sample_rate;
+        sec += (uint32_t)(us / 1000000ull);
+        usec = (uint32_t)(us % 1000000ull);
     }
     uint8_t m[24];
     auto put = [&](int o, uint32_t v) { m[o] = (uint8_t)v; m[o + 1] = (uint8_t)(v >> 8); m[o + 2] = (uint8_t)(v >> 16); m[o + 3] = (uint8_t)(v >> 24); };
@@ -964,8 +965,16 @@ static int sink_run(sdrd_sink* k, const uint32_t* samples, size_t stride, size_t
     const int new_pending = (int)(total % fec::FRAME_SAMPLES);
     if (n_frames > k->frame_cap) return fail(SDRD_ERANGE, "write completes more frames than the handle was sized for");
     const int F = k->nb_fec;
+    /* the time of this call: the wall clock (gettimeofday, UDPSinkFEC.cpp:95) or the fixed value */
+    uint32_t sec = k->tv_sec, usec = k->tv_usec;
+    if (!k->fixed_time) {
+        struct timeval tv;
+        gettimeofday(&tv, 0);
+        sec = (uint32_t)tv.tv_sec;
+        usec = (uint32_t)tv.tv_usec;
+    }
     uint32_t meta_next[6];
-    build_meta(k, meta_next);
+    build_meta(k, meta_next, sec, usec);
     const size_t frame_words = (size_t)(128 + F) * fec::ROW_WORDS;
     const size_t dgram_stride = k->frame_cap * frame_words;
     if (n_frames) {
@@ -988,6 +997,7 @@ static int sink_run(sdrd_sink* k, const uint32_t* samples, size_t stride, size_t
         p.n_pending = k->n_pending;
         memcpy(p.meta_first, k->pending_meta, 24);
         memcpy(p.meta_next, meta_next, 24);
+        p.stamp_rate = k->frame_clock ? k->sample_rate : 0u;
         p.frame_index0 = k->frame_count;
         p.dgrams = k->d_dgrams;
         p.dgram_stride = (long long)dgram_stride;
@@ -1009,7 +1019,8 @@ static int sink_run(sdrd_sink* k, const uint32_t* samples, size_t stride, size_t
         SDRD_TRY(rt::copy2d(k->d_pending, (size_t)fec::FRAME_SAMPLES * 4, samples + from, stride * 4, (size_t)new_pending * 4,
                             (size_t)k->S, rt::D2D, st),
                  "carry samples");
-        memcpy(k->pending_meta, meta_next, 24);
+        /* the unfinished frame began `from` samples into this call */
+        build_meta(k, k->pending_meta, sec, usec, (unsigned long long)from);
     }
     k->n_pending = new_pending;
     k->frame_count = (k->frame_count + (unsigned)n_frames) & 0xFFFFu;

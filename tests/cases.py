@@ -425,3 +425,28 @@ def check_cm256_blocks(lib, ob):
     assert capi.cm256_decode_blocks(blocks, idxd, 2, lib=lib)[0] != 0 and ob.cm256_decode(blocks, idxd, 128, 2)[0] != 0
     assert capi.cm256_decode_blocks(o[:64], list(range(64)), 2, lib=lib)[0] != 0   # OriginalCount != 128
     assert lib.sdrd_cm256_encode_blocks(capi.Cm256Params(128, 129, 508), None, None) != 0
+
+
+def check_sink_frame_clock(lib, ob, splits, rate=48000, F=4, base=(1700000000, 999000)):
+    """Per-frame time stamps: the reference reads the clock when a frame's first sample is written
+    (UDPSinkFEC.cpp:89-95).  With the sample-clock mode a frame begun `o` samples into a call carries the call's
+    time + o / sample_rate; the oracle is driven frame by frame with exactly those stamps."""
+    rng = np.random.default_rng(4242)
+    n = splits[-1]
+    x = rand_iq(rng, (1, n))
+    sk = capi.Sink(max_samples=max(b - a for a, b in zip(splits[:-1], splits[1:])), n_fec=F, sample_rate=rate, lib=lib)
+    sk.set_time(base[0], base[1], fixed=True, per_frame=True)
+    got = np.concatenate([sk.write(x[:, a:b]) for a, b in zip(splits[:-1], splits[1:])], axis=1)[0]
+    o = ob.Sink(n_fec=F, sample_rate=rate)
+    for k in range(n // FRAME):
+        start = k * FRAME
+        call0 = max(a for a in splits[:-1] if a <= start)   # the call in which the frame's first sample arrives
+        us = base[1] + (start - call0) * 1000000 // rate
+        o.set_time(base[0] + us // 1000000, us % 1000000)
+        o.write(x[0, start:start + FRAME])
+    want = np.stack(o.frames)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.array_equal(got, want), "per-frame time stamps differ"
+    stamps = {(int.from_bytes(f[0, 16:20].tobytes(), "little"), int.from_bytes(f[0, 20:24].tobytes(), "little")) for f in got}
+    assert len(stamps) > 1
+    sk.close()

@@ -202,3 +202,8 @@ def test_rescale_keeps_filter_state(emu_lib, oracle):
     assert np.array_equal(z, (x[0, :500].astype(np.int32) << 4).astype(np.int16)) and ss.value == 12
     y2, _ = d.process(x[:, 3000:], 12)
     assert np.array_equal(y1[0], o.process(x[0, :3000], 12)[0]) and np.array_equal(y2[0], o.process(x[0, 3000:], 12)[0])
+
+
+def test_sink_per_frame_time_stamps(emu_lib, oracle):
+    F = cases.FRAME
+    cases.check_sink_frame_clock(emu_lib, oracle, [0, 100, 100 + 3 * F, 100 + 3 * F + 50, 5 * F + 7, 6 * F + 7])

@@ -379,3 +379,10 @@ def test_rescale_keeps_filter_state(gpu_lib, oracle):
     assert np.array_equal(z, (x[0, :70000].astype(np.int32) << 8).astype(np.int16)) and ss.value == 8
     y2, _ = d.process(x[:, 100000:], 8)
     assert np.array_equal(y1[0], o.process(x[0, :100000], 8)[0]) and np.array_equal(y2[0], o.process(x[0, 100000:], 8)[0])
+
+
+def test_sink_per_frame_time_stamps(gpu_lib, oracle):
+    """one time stamp per frame (UDPSinkFEC.cpp:89-95) for callers that batch many frames into one write"""
+    F = cases.FRAME
+    cases.check_sink_frame_clock(gpu_lib, oracle, [0, 100, 100 + 3 * F, 100 + 3 * F + 50, 5 * F + 7, 6 * F + 7])
+    cases.check_sink_frame_clock(gpu_lib, oracle, [0, 40 * F + 11, 41 * F, 90 * F + 5], rate=625000, F=16)
