@@ -454,3 +454,35 @@ def cpu_rx_streams(iq: np.ndarray, log2_decim: int, n_fec: int, n_threads: int, 
                                   C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32)]
     fr = L.sdro_rx_streams(log2_decim, fcpos, HB_EO1, n_fec, s, n_threads, a.ctypes.data, n, n, block, C.byref(dig))
     return int(fr), int(dig.value), "port"
+
+
+def rx_stream_crcs(iq: np.ndarray, log2_decim: int, n_fec: int, n_threads: int, fcpos: int = FC_CENTER,
+                   variant: int = HB_EO1, block: int = 65536) -> Tuple[int, np.ndarray]:
+    """Decimate -> pack -> encode every stream of iq (S, n, 2) with the oracle; returns (superframes, crc[S]) with
+    crc[s] = zlib.crc32 of stream s's datagram bytes in send order."""
+    a = np.ascontiguousarray(iq, dtype=np.int16)
+    s, n, _ = a.shape
+    L = lib()
+    L.sdro_rx_streams_crc.restype = C.c_longlong
+    L.sdro_rx_streams_crc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                      C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32), C.c_void_p]
+    crc = np.zeros(s, dtype=np.uint32)
+    dig = C.c_uint32(0)
+    fr = L.sdro_rx_streams_crc(log2_decim, fcpos, variant, n_fec, s, n_threads, a.ctypes.data, n, n, block, C.byref(dig),
+                               crc.ctypes.data)
+    return int(fr), crc
+
+
+def decode_frames(superblocks: np.ndarray, n_blocks, n_threads: int = 1):
+    """(n_frames, pitch, 512) received datagrams -> (payload (n, 127, 508), block0 (n, 508), status (n,)), threaded."""
+    sb = np.ascontiguousarray(superblocks, dtype=np.uint8)
+    nf, pitch, _ = sb.shape
+    nb = np.ascontiguousarray(np.broadcast_to(np.asarray(n_blocks, dtype=np.int32), (nf,)))
+    pay = np.zeros((nf, 127, BLOCK_BYTES), np.uint8)
+    b0 = np.zeros((nf, BLOCK_BYTES), np.uint8)
+    st = np.zeros(nf, np.int32)
+    L = lib()
+    L.sdro_decode_frames.restype = None
+    L.sdro_decode_frames.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sdro_decode_frames(sb.ctypes.data, pitch, nb.ctypes.data, nf, n_threads, pay.ctypes.data, b0.ctypes.data, st.ctypes.data)
+    return pay, b0, st

@@ -363,23 +363,28 @@ int sdro_cm256_decode(sdro_cm256_params p, sdro_cm256_block* blocks)
 }
 
 /* boost::crc_32_type: reflected 0xEDB88320, init and final xor 0xFFFFFFFF (UDPSinkFEC.cpp:106-109) */
-uint32_t sdro_crc32(const void* data, size_t n)
+static uint32_t crc_table[256];
+static void crc_init(void)
 {
-    static uint32_t table[256];
-    static int ready = 0;
-    if (!ready) {
-        for (uint32_t i = 0; i < 256; i++) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
-            table[i] = c;
-        }
-        ready = 1;
+    static volatile int ready = 0;
+    if (ready) return;
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+        crc_table[i] = c;
     }
-    uint32_t c = 0xFFFFFFFFu;
+    ready = 1;
+}
+/* running form (zlib convention: start from 0, feed the previous result back in) */
+uint32_t sdro_crc32_update(uint32_t crc, const void* data, size_t n)
+{
+    crc_init();
+    uint32_t c = crc ^ 0xFFFFFFFFu;
     const uint8_t* p = (const uint8_t*)data;
-    for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    for (size_t i = 0; i < n; i++) c = crc_table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
     return c ^ 0xFFFFFFFFu;
 }
+uint32_t sdro_crc32(const void* data, size_t n) { return sdro_crc32_update(0u, data, n); }
 
 /* ======================================================================= sink ======== */
 
@@ -614,6 +619,17 @@ int sdro_decode_frame(const uint8_t* superblocks, int n_blocks, uint8_t* payload
 }
 
 /* ======================================================================= bench leg ==== */
+typedef struct {
+    const uint8_t* sb;
+    size_t pitch;
+    const int* n_blocks;
+    int n_frames;
+    uint8_t *payload, *block0;
+    int* status;
+    volatile int* next;
+} dec_job;
+static void* dec_worker(void* arg);
+
 /* Whole Rx hot path (decimate -> pack -> encode) for n_streams streams on n_threads POSIX threads:
  * the "port" CPU baseline of bench.py when the reference build (oracle/_ref) is not available. */
 #include <pthread.h>
@@ -625,9 +641,10 @@ typedef struct {
     volatile int* next;
     long long frames;
     uint32_t digest;
+    uint32_t* stream_crc; /* optional: CRC-32 of every stream's datagram bytes, in send order */
 } rx_job;
 
-typedef struct { long long frames; uint32_t digest; } rx_acc;
+typedef struct { long long frames; uint32_t digest; uint32_t crc; int want_crc; } rx_acc;
 static void rx_cb(void* user, const uint8_t* dg, int n_blocks, uint16_t fi)
 {
     (void)fi;
@@ -637,6 +654,7 @@ static void rx_cb(void* user, const uint8_t* dg, int n_blocks, uint16_t fi)
     for (int i = 0; i < n_blocks * 128; i++) d ^= w[i];
     a->frames++;
     a->digest ^= d;
+    if (a->want_crc) a->crc = sdro_crc32_update(a->crc, dg, (size_t)n_blocks * SDRO_UDPSIZE);
 }
 
 static void* rx_worker(void* arg)
@@ -647,7 +665,7 @@ static void* rx_worker(void* arg)
         int s = __sync_fetch_and_add(j->next, 1);
         if (s >= j->n_streams) break;
         sdro_dec* d = sdro_dec_create(j->log2_decim, j->fcpos, j->variant);
-        rx_acc acc = {0, 0};
+        rx_acc acc = {0, 0, 0, j->stream_crc != NULL};
         sdro_sink* k = sdro_sink_create(rx_cb, &acc);
         sdro_sink_set_meta(k, 435000, 625000, 2, 16);
         sdro_sink_set_nb_fec(k, j->nb_fec);
@@ -665,6 +683,7 @@ static void* rx_worker(void* arg)
         sdro_dec_destroy(d);
         j->frames += acc.frames;
         j->digest ^= acc.digest;
+        if (j->stream_crc) j->stream_crc[s] = acc.crc;
     }
     free(out);
     return NULL;
@@ -674,14 +693,23 @@ long long sdro_rx_streams(int log2_decim, int fcpos, int variant, int nb_fec, in
                           const int16_t* iq_in, size_t n_in_per_stream, size_t in_stride, size_t block,
                           uint32_t* digest)
 {
+    return sdro_rx_streams_crc(log2_decim, fcpos, variant, nb_fec, n_streams, n_threads, iq_in, n_in_per_stream, in_stride,
+                               block, digest, NULL);
+}
+
+long long sdro_rx_streams_crc(int log2_decim, int fcpos, int variant, int nb_fec, int n_streams, int n_threads,
+                              const int16_t* iq_in, size_t n_in_per_stream, size_t in_stride, size_t block,
+                              uint32_t* digest, uint32_t* stream_crc)
+{
     gf_init();
+    crc_init();
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 256) n_threads = 256;
     pthread_t th[256];
     rx_job jobs[256];
     volatile int next = 0;
     for (int t = 0; t < n_threads; t++) {
-        rx_job j = {log2_decim, fcpos, variant, nb_fec, n_streams, iq_in, n_in_per_stream, in_stride, block, &next, 0, 0};
+        rx_job j = {log2_decim, fcpos, variant, nb_fec, n_streams, iq_in, n_in_per_stream, in_stride, block, &next, 0, 0, stream_crc};
         jobs[t] = j;
         pthread_create(&th[t], NULL, rx_worker, &jobs[t]);
     }
@@ -694,7 +722,37 @@ long long sdro_rx_streams(int log2_decim, int fcpos, int variant, int nb_fec, in
     }
     if (digest) *digest = dg;
     return frames;
-}/* ---------------------------------------------------------------- interpolator ---- */
+}
+static void* dec_worker(void* arg)
+{
+    dec_job* j = (dec_job*)arg;
+    for (;;) {
+        int f = __sync_fetch_and_add(j->next, 1);
+        if (f >= j->n_frames) break;
+        j->status[f] = sdro_decode_frame(j->sb + (size_t)f * j->pitch * SDRO_UDPSIZE, j->n_blocks[f],
+                                         j->payload + (size_t)f * 127 * SDRO_BLOCK_BYTES,
+                                         j->block0 ? j->block0 + (size_t)f * SDRO_BLOCK_BYTES : NULL);
+    }
+    return NULL;
+}
+
+/* sdro_decode_frame over a batch of frames (frame f: n_blocks[f] datagrams at sb + f * pitch * 512) on n_threads
+ * threads: the all-frames checker of BASELINE config 4 and its CPU baseline */
+void sdro_decode_frames(const uint8_t* sb, size_t pitch, const int* n_blocks, int n_frames, int n_threads, uint8_t* payload,
+                        uint8_t* block0, int* status)
+{
+    gf_init();
+    crc_init();
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    pthread_t th[256];
+    volatile int next = 0;
+    dec_job j = {sb, pitch, n_blocks, n_frames, payload, block0, status, &next};
+    for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, dec_worker, &j);
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+}
+
+/* ---------------------------------------------------------------- interpolator ---- */
 
 /* HBFIRFilterTraits<32>/<16>::hbCoeffs as integers (sdmnbase/HBFilterTraits.cpp:62-72 and :25-31,
  * (int32_t)(c * (1 << 14)) truncated toward zero; values printed by a probe against the reference). */

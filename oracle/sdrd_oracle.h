@@ -142,6 +142,16 @@ int sdro_decode_frame(const uint8_t* superblocks, int n_blocks, uint8_t* payload
 long long sdro_rx_streams(int log2_decim, int fcpos, int variant, int nb_fec, int n_streams, int n_threads,
                           const int16_t* iq_in, size_t n_in_per_stream, size_t in_stride, size_t block,
                           uint32_t* digest);
+/* the same with, optionally, stream_crc[s] = CRC-32 (zlib convention) of stream s's datagram bytes in send order:
+ * the every-stream checker of the full-size parity tests (BASELINE configs 3 and 5) */
+long long sdro_rx_streams_crc(int log2_decim, int fcpos, int variant, int nb_fec, int n_streams, int n_threads,
+                              const int16_t* iq_in, size_t n_in_per_stream, size_t in_stride, size_t block,
+                              uint32_t* digest, uint32_t* stream_crc);
+uint32_t sdro_crc32_update(uint32_t crc, const void* data, size_t n);
+/* sdro_decode_frame over n_frames frames on n_threads threads (frame f: n_blocks[f] datagrams at
+ * superblocks + f * pitch * 512): the every-frame checker and CPU baseline of BASELINE config 4 */
+void sdro_decode_frames(const uint8_t* superblocks, size_t pitch, const int* n_blocks, int n_frames, int n_threads,
+                        uint8_t* payload, uint8_t* block0, int* status);
 
 #ifdef __cplusplus
 }
