@@ -411,6 +411,89 @@ def run_interp(args):
                                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}}), flush=True)
 
 
+def small_block_leg(lib, capi, n_blocks=1500, blk=65536):
+    """The reference's call granularity: ONE stream fed in TestSource-sized blocks of 65536 samples
+    (include/TestSource.h:33) from pageable host memory, the way sdrdaemonrx's main loop feeds Downsampler::process +
+    UDPSinkFEC::write (sdrdaemonrx.cpp:579-663).  Three forms, same config as the headline:
+      sync    sdrd_rx_process once per block (copy in, kernels, copy out, synchronise -- every block)
+      queued  sdrd_rx_submit per block + sdrd_rx_collect: no synchronisation per block, blocks batched on the way
+      classes the C++ mirror classes (Downsampler::process then UDPSinkFEC::write, host vectors in between)"""
+    import ctypes as C
+
+    rng = np.random.default_rng(77)
+    src = [rng.integers(-32768, 32768, size=(blk, 2), dtype=np.int16) for _ in range(8)]  # pageable
+    ptrs = [a.ctypes.data for a in src]
+    bpf = 128 + N_FEC
+    out = np.zeros((64, bpf, 512), np.uint8)
+    res = {"block_samples": blk, "blocks": n_blocks, "memory": "pageable host vectors, one stream"}
+    # what any entry point that accepts pageable memory has to pay first: one host copy of the block into page-locked
+    # staging memory (measured with the same blocks and one thread; the queued form is bounded by it)
+    try:
+        import torch
+
+        stage = torch.empty((blk, 2), dtype=torch.int16).pin_memory()
+        sp = stage.data_ptr()
+        for warm in (True, False):
+            t0 = time.perf_counter()
+            for b in range(200 if warm else n_blocks):
+                C.memmove(sp, ptrs[b & 7], blk * 4)
+            dt = time.perf_counter() - t0
+        res["host_copy_ceiling"] = {"value": round(n_blocks * blk / dt / 1e6, 1), "unit": UNIT, "GB_per_s": round(n_blocks * blk * 4 / dt / 1e9, 2),
+                                    "what": "memmove of each block into page-locked memory, one thread"}
+    except Exception:
+        pass
+    rx = capi.Rx(M_LOG2, n_streams=1, max_in=32 * blk, n_fec=N_FEC)
+    nfr = C.c_size_t(0)
+    for warm in (True, False):
+        n = 50 if warm else n_blocks
+        t0 = time.perf_counter()
+        for b in range(n):
+            lib.check(lib.sdrd_rx_process(rx._h, ptrs[b & 7], blk, blk, out.ctypes.data, 64, C.byref(nfr), None))
+        dt = time.perf_counter() - t0
+    res["sync"] = {"value": round(n_blocks * blk / dt / 1e6, 1), "unit": UNIT, "us_per_block": round(dt / n_blocks * 1e6, 2),
+                   "api": "sdrd_rx_process per block"}
+    bp = C.c_int(0)
+    for key, min_chain in (("queued", 0), ("queued_batched", 16 * blk)):
+        rx.reset()
+        rx.set_min_chain(min_chain)
+        frames = 0
+        for warm in (True, False):
+            n = 64 if warm else n_blocks
+            c0 = rx.chains
+            t0 = time.perf_counter()
+            for b in range(n):
+                lib.check(lib.sdrd_rx_submit(rx._h, ptrs[b & 7], blk, blk, None))
+                lib.check(lib.sdrd_rx_collect(rx._h, out.ctypes.data, 64, C.byref(nfr), C.byref(bp), 0))
+                frames += nfr.value
+            while True:
+                lib.check(lib.sdrd_rx_collect(rx._h, out.ctypes.data, 64, C.byref(nfr), C.byref(bp), 1))
+                frames += nfr.value
+                if not nfr.value:
+                    break
+            dt = time.perf_counter() - t0
+            chains = rx.chains - c0
+        res[key] = {"value": round(n_blocks * blk / dt / 1e6, 1), "unit": UNIT, "us_per_block": round(dt / n_blocks * 1e6, 2),
+                    "blocks_per_chain": round(n_blocks / max(chains, 1), 2),
+                    "api": "sdrd_rx_submit + sdrd_rx_collect" + (f", sdrd_rx_set_min_chain({min_chain})" if min_chain else " (an idle device starts at once)")}
+    rx.close()
+    # the C++ mirror classes, through tests/host/host_pipeline.cpp (built here if a compiler is present)
+    try:
+        exe = os.path.join(ROOT, "tests", "host", "host_pipeline_gpu")
+        srcf = os.path.join(ROOT, "tests", "host", "host_pipeline.cpp")
+        libdir = os.path.join(ROOT, "sdrdaemon_b200")
+        if (not os.path.exists(exe)) or os.path.getmtime(exe) < max(os.path.getmtime(srcf), os.path.getmtime(os.path.join(libdir, "libsdrd_b200.so"))):
+            cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+            subprocess.run([cxx, "-std=c++17", "-O2", "-pthread", "-o", exe, srcf, f"-L{libdir}", "-lsdrd_b200", f"-Wl,-rpath,{libdir}"],
+                           check=True, capture_output=True)
+        r = subprocess.run([exe, "blocks", str(n_blocks), str(M_LOG2), str(N_FEC), str(blk), "50"], capture_output=True, text=True, timeout=300)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        res["classes"] = {"value": round(j["msamples_per_s"], 1), "unit": UNIT, "us_per_block": j["us_per_block"],
+                          "api": "Downsampler::process + UDPSinkFEC::write (sdrd_host.hpp)"}
+    except Exception as e:
+        res["classes"] = {"value": None, "note": f"not measured ({type(e).__name__})"}
+    return res
+
+
 class DevView:
     """Zero-copy torch view of a raw device pointer (CUDA array interface)."""
 
@@ -574,6 +657,8 @@ def main():
         e2e = {"value": round(world * S * n_in * args.e2e_steps / dt / 1e6, 1), "unit": UNIT,
                "h2d_bytes_per_step": S * n_in * 4, "d2h_bytes_per_step": S * int(nfr.value) * bpf * 512,
                "steps": args.e2e_steps, "api": "sdrd_rx_process (host pointers, pinned)"}
+        if world == 1 and args.config == 2:
+            e2e["small_block"] = small_block_leg(lib, capi)
 
     # the only exchange of the job: one 8-byte digest per stream (sdrdaemon_b200.multi)
     digests = None

@@ -243,6 +243,32 @@ int sdrd_rx_process(sdrd_rx* rx, const int16_t* iq_in, size_t n_in, size_t in_st
 /* Calls of at least min_call_bytes input bytes (all streams) go through in 8 slices so that the host -> device
  * copy of slice i + 1 overlaps the kernels and the copy-back of slice i (default 32 MiB; 0 restores it). */
 int sdrd_rx_set_slice_bytes(sdrd_rx* rx, size_t min_call_bytes);
+/* Queued form, for callers that feed one block after the other the way the reference's threads do
+ * (sdrdaemonrx.cpp:579-663: the source thread pushes blocks, the main thread decimates and writes, the sink's own
+ * thread encodes and sends).
+ *   sdrd_rx_submit   copies the block (n_in samples per stream, a multiple of 2^decim; any host memory) into the
+ *                    handle's page-locked accumulation buffer and returns without waiting for the device.  Whenever
+ *                    the device is idle, everything accumulated so far goes out as ONE chain of copy -> decimate ->
+ *                    frame + encode -> copy back: blocks are batched exactly as far as the device lags behind the
+ *                    producer, so a slow producer sees single-block latency and a fast one full batches.  It waits
+ *                    only when a block no longer fits behind what has accumulated (max_in samples per stream).
+ *                    sample_bits as for sdrd_rx_process; on return it holds the decimator's output sample size.
+ *   sdrd_rx_collect  hands over the frames completed so far, oldest first, layout as sdrd_rx_process (stream pitch
+ *                    frame_capacity frames); wait != 0 first waits for everything submitted before the call.
+ *                    Frames of different sizes (setNbBlocksFEC changed in between) come in separate calls;
+ *                    *blocks_per_frame tells which.  May be called from another thread than sdrd_rx_submit.
+ * The datagrams are bit-identical to those of sdrd_rx_process over the same sample stream. */
+int sdrd_rx_submit(sdrd_rx* rx, const int16_t* iq_in, size_t n_in, size_t in_stride, unsigned* sample_bits);
+int sdrd_rx_collect(sdrd_rx* rx, uint8_t* datagrams, size_t frame_capacity, size_t* n_frames, int* blocks_per_frame,
+                    int wait);
+/* chains sent to the device by sdrd_rx_submit / sdrd_rx_collect so far (blocks submitted / chains = batching achieved) */
+long long sdrd_rx_chains(const sdrd_rx* rx);
+/* Latency against throughput: by default (0) an idle device gets whatever has accumulated at once.  Starting a chain
+ * costs the submitting thread some tens of microseconds of driver calls whatever its size; a producer that is faster
+ * than that can ask for chains of at least min_samples samples per stream (sdrd_rx_collect with wait != 0 still sends
+ * what is there). */
+int sdrd_rx_set_min_chain(sdrd_rx* rx, size_t min_samples);
+
 /* Device-resident form: input at sdrd_dec_dev_input(sdrd_rx_dec(rx)), datagram images left at
  * sdrd_rx_dev_datagrams() (stream pitch *frame_pitch frames of (128 + nb_fec) x 512 bytes). */
 void* sdrd_rx_dev_datagrams(sdrd_rx* rx, size_t* frame_pitch);

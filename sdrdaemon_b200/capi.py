@@ -82,6 +82,10 @@ SYMBOLS = [
     ("sdrd_rx_sink", _P, [_P]),
     ("sdrd_rx_process", C.c_int, [_P, _P, _SZ, _SZ, _P, _SZ, _SZP, _UP]),
     ("sdrd_rx_set_slice_bytes", C.c_int, [_P, _SZ]),
+    ("sdrd_rx_submit", C.c_int, [_P, _P, _SZ, _SZ, _UP]),
+    ("sdrd_rx_collect", C.c_int, [_P, _P, _SZ, _SZP, C.POINTER(C.c_int), C.c_int]),
+    ("sdrd_rx_chains", C.c_longlong, [_P]),
+    ("sdrd_rx_set_min_chain", C.c_int, [_P, _SZ]),
     ("sdrd_rx_dev_datagrams", _P, [_P, _SZP]),
     ("sdrd_rx_process_dev", C.c_int, [_P, _SZ, _SZP, _UP, _P]),
     ("sdrd_rx_launches", C.c_longlong, [_P]),
@@ -487,6 +491,32 @@ class Rx:
         self.sample_bits_out = ss.value
         res = out[:, : nfr.value]
         return res[0] if single else res
+
+    def submit(self, iq: np.ndarray, sample_bits: int = 16) -> int:
+        """queued form: returns once the block is staged; the decimator's output sample size"""
+        a = _iq3(iq)
+        s, n, _ = a.shape
+        ss = C.c_uint(sample_bits)
+        self.lib.check(self.lib.sdrd_rx_submit(self._h, a.ctypes.data, n, n, C.byref(ss)))
+        return ss.value
+
+    def collect(self, frame_capacity: int = 64, wait: bool = False) -> np.ndarray:
+        """frames completed so far -> (S, n_frames, blocks_per_frame, 512)"""
+        out = np.zeros(self.n_streams * max(frame_capacity, 1) * 256 * UDPSIZE, dtype=np.uint8)
+        nfr = C.c_size_t(0)
+        bpf = C.c_int(0)
+        self.lib.check(self.lib.sdrd_rx_collect(self._h, out.ctypes.data, frame_capacity, C.byref(nfr), C.byref(bpf), 1 if wait else 0))
+        if nfr.value == 0:
+            return np.zeros((self.n_streams, 0, self.sink.blocks_per_frame, UDPSIZE), np.uint8)
+        used = self.n_streams * frame_capacity * bpf.value * UDPSIZE  # stream pitch = frame_capacity frames
+        return out[:used].reshape(self.n_streams, frame_capacity, bpf.value, UDPSIZE)[:, : nfr.value].copy()
+
+    @property
+    def chains(self) -> int:
+        return self.lib.sdrd_rx_chains(self._h)
+
+    def set_min_chain(self, min_samples: int) -> None:
+        self.lib.check(self.lib.sdrd_rx_set_min_chain(self._h, min_samples))
 
     def dev_input(self) -> Tuple[int, int]:
         st = C.c_size_t(0)

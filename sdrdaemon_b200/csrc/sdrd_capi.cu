@@ -17,6 +17,7 @@
 #include <sys/time.h>
 
 #include <algorithm>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <string>
@@ -64,6 +65,64 @@ struct DeviceGuard {
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 #define SDRD_ON_DEVICE_OF(h) DeviceGuard device_guard_((h)->device)
+
+/* Small transfers between PAGEABLE host memory and the device (the reference's callers hand over std::vectors of
+ * 65536 samples): the driver stages such copies itself and blocks while it does; going through the handle's own
+ * page-locked buffer -- one memcpy, then an asynchronous copy -- costs the calling thread less.  Large transfers
+ * and page-locked user buffers go directly. */
+struct HostStage {
+    static constexpr size_t MAX_BYTES = (size_t)4 << 20;
+    uint8_t* in = nullptr;
+    uint8_t* out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    /* a device -> host copy that still has to be unpacked into the user's buffer after the stream has been synchronised */
+    uint8_t* pend_dst = nullptr;
+    size_t pend_dpitch = 0, pend_w = 0, pend_h = 0;
+    ~HostStage()
+    {
+        rt::host_release(in);
+        rt::host_release(out);
+    }
+    static int grow(uint8_t** p, size_t* cap, size_t need)
+    {
+        if (need <= *cap) return 0;
+        rt::host_release(*p);
+        *p = nullptr;
+        *cap = 0;
+        const size_t n = std::max<size_t>(need, (size_t)1 << 20);
+        if (rt::host_alloc((void**)p, n) != 0) return -1;
+        *cap = n;
+        return 0;
+    }
+    int to_device(void* dst, size_t dpitch, const void* src, size_t spitch, size_t w, size_t h, rt::stream_t st)
+    {
+        if (!w || !h) return 0;
+        if (w * h <= MAX_BYTES && rt::host_is_pageable(src) && grow(&in, &in_cap, w * h) == 0) {
+            for (size_t i = 0; i < h; i++) memcpy(in + i * w, (const uint8_t*)src + i * spitch, w);
+            return rt::copy2d(dst, dpitch, in, w, w, h, rt::H2D, st);
+        }
+        return rt::copy2d(dst, dpitch, src, spitch, w, h, rt::H2D, st);
+    }
+    int to_host(void* dst, size_t dpitch, const void* src, size_t spitch, size_t w, size_t h, rt::stream_t st)
+    {
+        if (!w || !h) return 0;
+        if (!pend_dst && w * h <= MAX_BYTES && rt::host_is_pageable(dst) && grow(&out, &out_cap, w * h) == 0) {
+            pend_dst = (uint8_t*)dst;
+            pend_dpitch = dpitch;
+            pend_w = w;
+            pend_h = h;
+            return rt::copy2d(out, w, src, spitch, w, h, rt::D2H, st);
+        }
+        return rt::copy2d(dst, dpitch, src, spitch, w, h, rt::D2H, st);
+    }
+    /* after the stream has been synchronised */
+    void finish()
+    {
+        if (!pend_dst) return;
+        for (size_t i = 0; i < pend_h; i++) memcpy(pend_dst + i * pend_dpitch, out + i * pend_w, pend_w);
+        pend_dst = nullptr;
+    }
+};
 
 /* raw samples of input history kept per stream: two chunks of the /4-prologue cascade */
 constexpr size_t HISTW = 16384;
@@ -190,6 +249,8 @@ struct sdrd_dec {
     size_t max_in = 0;
     uint32_t* d_in = nullptr;    /* [S][in_pitch]: HISTW history words, then the new samples */
     uint32_t* d_hist = nullptr;  /* [S][HISTW] */
+    bool hist_in_front = false;  /* the history already sits in d_in[0 .. HISTW) (a call of >= HISTW samples moves its
+                                    tail there directly); otherwise it is in d_hist and is restored at the next call */
     uint32_t* d_out = nullptr;   /* [S][out_pitch] */
     size_t in_pitch = 0, out_pitch = 0;
     long long consumed = 0;      /* raw samples consumed since reset (saturating) */
@@ -205,6 +266,7 @@ struct sdrd_dec {
     long long launches = 0;
     int sms = 148;
     rt::stream_t stream = 0;
+    HostStage stage;
 };
 
 extern "C" const char* sdrd_last_error(void) { return g_err.c_str(); }
@@ -283,6 +345,7 @@ extern "C" int sdrd_dec_reset(sdrd_dec* d)
     SDRD_TRY(rt::fill(d->d_hist, 0, HISTW * 4 * (size_t)d->S, d->stream), "reset history");
     SDRD_TRY(rt::fill(d->d_state, 0, (size_t)hb::STATE_WORDS * 4 * (size_t)d->S, d->stream), "reset stage states");
     SDRD_TRY(rt::sync(d->stream), "reset history");
+    d->hist_in_front = false;
     d->consumed = 0;
     d->consistent = true;
     d->run = 0;
@@ -318,8 +381,8 @@ extern "C" int sdrd_dec_configure(sdrd_dec* d, int log2_decim, int fcpos)
             if (d->last_stream != d->stream) SDRD_TRY(rt::sync(d->last_stream), "configure");
             const long long n_raw = std::min<long long>(d->run, DEC_HEAD);
             hb::StateParams p{};
-            p.in = d->d_hist + (HISTW - (size_t)n_raw);
-            p.in_stride = (long long)HISTW;
+            p.in = (d->hist_in_front ? d->d_in : d->d_hist) + (HISTW - (size_t)n_raw);
+            p.in_stride = (long long)(d->hist_in_front ? d->in_pitch : HISTW);
             p.out = nullptr;
             p.state = d->d_state;
             p.n_casc = n_raw / (pro ? 4 : 1);
@@ -380,7 +443,7 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
     uint32_t* out0 = d->d_out + (in_off >> L);
 
     /* history of the previous calls in front of the new samples */
-    if (first)
+    if (first && !d->hist_in_front)
         SDRD_TRY(rt::copy2d(d->d_in, d->in_pitch * 4, d->d_hist, HISTW * 4, HISTW * 4, (size_t)d->S, rt::D2D, st),
                  "restore history");
 
@@ -477,7 +540,10 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
             long long want = resident * d->sms;
             if (want < 1) want = 1;
             long long ev_warp = (ev_total + want - 1) / want;
-            const long long ev_min = std::min<long long>(8 * warm_ev, ev_stream);
+            /* Small calls (the reference's 65536-sample blocks) do not fill one wave: there the length of a share is
+             * what the caller waits for (a warp walks its share step by step, ~2.5 us each), so shares shrink until a
+             * share is only as long as its own warm-up -- the redundant warm-up runs on SMs that would idle anyway. */
+            const long long ev_min = std::min<long long>(std::max<long long>(warm_ev, 1), ev_stream);
             if (ev_warp < ev_min) ev_warp = ev_min;
             const long long n_seg = (ev_total + ev_warp - 1) / ev_warp;
             p.ev_stream = ev_stream;
@@ -499,10 +565,18 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
     if (!SDRD_LAUNCH_OK()) return fail_cuda("kernel launch");
 
     /* the last HISTW consumed samples become the next call's history */
-    if (last)
-        SDRD_TRY(rt::copy2d(d->d_hist, HISTW * 4, d->d_in + in_off + consumed_now, d->in_pitch * 4, HISTW * 4, (size_t)d->S,
-                            rt::D2D, st),
+    if (last) {
+        /* [.. | HISTW + in_off + consumed_now) ends the consumed stream: its last HISTW samples are the history.  When
+         * they lie wholly behind the front region they move there in one copy; otherwise through d_hist (source and
+         * destination would overlap). */
+        const bool direct = in_off + consumed_now >= HISTW;
+        SDRD_TRY(rt::copy2d(direct ? d->d_in : d->d_hist, (direct ? d->in_pitch : HISTW) * 4, d->d_in + in_off + consumed_now,
+                            d->in_pitch * 4, HISTW * 4, (size_t)d->S, rt::D2D, st),
                  "save history");
+        d->hist_in_front = direct;
+    } else {
+        d->hist_in_front = true; /* the next slice of this call finds its history in place */
+    }
     d->consumed += (long long)consumed_now;
     if (d->consumed > (1LL << 50)) d->consumed = 1LL << 50;
     d->run += (long long)consumed_now;
@@ -532,13 +606,14 @@ extern "C" int sdrd_dec_process(sdrd_dec* d, const int16_t* iq_in, size_t n_in, 
     /* everything that can be refused is refused before the filter state moves */
     if (d->S > 1 && out_stride < dec_out_count(d, n_in)) return fail(SDRD_EINVAL, "out_stride smaller than the output length");
     if (sample_bits && (*sample_bits < 1 || *sample_bits > 16)) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
-    SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, rt::H2D, d->stream),
+    SDRD_TRY(d->stage.to_device(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, d->stream),
              "copy samples to device");
     size_t n_out = 0;
     if (int rc = dec_run(d, n_in, &n_out, sample_bits, d->stream)) return rc;
-    SDRD_TRY(rt::copy2d(iq_out, out_stride * 4, d->d_out, d->out_pitch * 4, n_out * 4, (size_t)d->S, rt::D2H, d->stream),
+    SDRD_TRY(d->stage.to_host(iq_out, out_stride * 4, d->d_out, d->out_pitch * 4, n_out * 4, (size_t)d->S, d->stream),
              "copy samples to host");
     SDRD_TRY(rt::sync(d->stream), "decimate");
+    d->stage.finish();
     if (n_out_p) *n_out_p = n_out;
     return 0;
 }
@@ -590,6 +665,7 @@ struct sdrd_int {
     rt::stream_t last_stream = 0;
     long long launches = 0;
     rt::stream_t stream = 0;
+    HostStage stage;
 };
 
 static int check_interp(int log2_interp)
@@ -808,14 +884,15 @@ extern "C" int sdrd_int_process(sdrd_int* u, const int16_t* iq_in, size_t n_in, 
     if ((!iq_in && n_in) || !iq_out) return fail(SDRD_EINVAL, "null sample pointer");
     if (n_in > u->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
     if (u->S > 1 && in_stride < n_in) return fail(SDRD_EINVAL, "in_stride smaller than n_in");
-    SDRD_TRY(rt::copy2d(u->d_in + hbi::HIST, u->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)u->S, rt::H2D, u->stream),
+    if (u->S > 1 && out_stride < (n_in << u->log2_interp)) return fail(SDRD_EINVAL, "out_stride smaller than the output length");
+    SDRD_TRY(u->stage.to_device(u->d_in + hbi::HIST, u->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)u->S, u->stream),
              "copy samples to device");
     size_t n_out = 0;
     if (int rc = int_run(u, n_in, &n_out, u->stream)) return rc;
-    if (u->S > 1 && out_stride < n_out) return fail(SDRD_EINVAL, "out_stride smaller than the output length");
-    SDRD_TRY(rt::copy2d(iq_out, out_stride * 4, u->d_out, u->out_pitch * 4, n_out * 4, (size_t)u->S, rt::D2H, u->stream),
+    SDRD_TRY(u->stage.to_host(iq_out, out_stride * 4, u->d_out, u->out_pitch * 4, n_out * 4, (size_t)u->S, u->stream),
              "copy samples to host");
     SDRD_TRY(rt::sync(u->stream), "interpolate");
+    u->stage.finish();
     if (n_out_p) *n_out_p = n_out;
     return 0;
 }
@@ -849,6 +926,7 @@ struct sdrd_sink {
     /* layout of the last completed call */
     size_t last_frames = 0;
     size_t last_dgram_stride = 0;
+    HostStage stage;
 };
 
 extern "C" int sdrd_sink_create(sdrd_sink** out, int n_streams, size_t max_samples)
@@ -1036,8 +1114,8 @@ static int sink_fetch(sdrd_sink* k, uint8_t* datagrams, size_t frame_capacity, s
     if (!datagrams) return fail(SDRD_EINVAL, "null datagram buffer");
     if (frame_capacity < n_frames) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of completed frames");
     const size_t frame_bytes = (size_t)(128 + k->nb_fec) * SDRD_UDPSIZE;
-    SDRD_TRY(rt::copy2d(datagrams, frame_capacity * frame_bytes, k->d_dgrams, k->last_dgram_stride * 4, n_frames * frame_bytes,
-                        (size_t)k->S, rt::D2H, st),
+    SDRD_TRY(k->stage.to_host(datagrams, frame_capacity * frame_bytes, k->d_dgrams, k->last_dgram_stride * 4, n_frames * frame_bytes,
+                              (size_t)k->S, st),
              "copy datagrams to host");
     return 0;
 }
@@ -1049,12 +1127,20 @@ extern "C" int sdrd_sink_write(sdrd_sink* k, const int16_t* iq, size_t n, size_t
     SDRD_ON_DEVICE_OF(k);
     if (!iq && n) return fail(SDRD_EINVAL, "null sample pointer");
     if (n > k->max_samples) return fail(SDRD_ERANGE, "n_samples exceeds the max_samples given at create time");
-    SDRD_TRY(rt::copy2d(k->d_samples, k->samples_pitch * 4, iq, stride * 4, n * 4, (size_t)k->S, rt::H2D, k->stream),
+    /* refused before the frame counter moves */
+    {
+        const size_t will_close = sdrd_sink_frames_for(k, n);
+        if (will_close > k->frame_cap) return fail(SDRD_ERANGE, "write completes more frames than the handle was sized for");
+        if (will_close && !datagrams) return fail(SDRD_EINVAL, "null datagram buffer");
+        if (will_close > frame_capacity) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of completed frames");
+    }
+    SDRD_TRY(k->stage.to_device(k->d_samples, k->samples_pitch * 4, iq, stride * 4, n * 4, (size_t)k->S, k->stream),
              "copy samples to device");
     size_t n_frames = 0;
     if (int rc = sink_run(k, k->d_samples, k->samples_pitch, n, &n_frames, k->stream)) return rc;
     if (int rc = sink_fetch(k, datagrams, frame_capacity, n_frames, k->stream)) return rc;
     SDRD_TRY(rt::sync(k->stream), "sink write");
+    k->stage.finish();
     if (n_frames_p) *n_frames_p = n_frames;
     return 0;
 }
@@ -1086,6 +1172,33 @@ struct sdrd_rx {
     rt::stream_t copy_stream = 0;   /* host -> device copies of sdrd_rx_process, ahead of the kernels */
     rt::event_t copied[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t slice_threshold = (size_t)32 << 20; /* calls of at least this many input bytes go through in 8 slices */
+
+    /* ---- queued form (sdrd_rx_submit / sdrd_rx_collect) ----
+     * submit copies the caller's block into a page-locked accumulation buffer and returns; whenever the device is
+     * idle everything accumulated so far goes out as ONE chain of copy -> decimate -> frame + encode -> copy back
+     * (no synchronisation in submit), so small blocks are batched exactly as far as the device lags behind the
+     * producer.  Completed frames wait in `ready` until collect hands them over. */
+    struct Batch {
+        int blocks_per_frame = 0;
+        size_t n_frames = 0, taken = 0; /* per stream; frames already handed over */
+        std::vector<uint8_t> data;      /* [S][n_frames][blocks_per_frame * 512] */
+    };
+    std::mutex q_mutex;
+    uint32_t* q_in[2] = {nullptr, nullptr}; /* page-locked [S][q_cap] */
+    uint8_t* q_out = nullptr;               /* page-locked [S][q_out_frames][blocks per frame * 512], grown on demand */
+    size_t q_cap = 0, q_out_frames = 0, q_out_bytes = 0;
+    size_t q_fill = 0;                      /* samples per stream accumulated in q_in[q_cur] */
+    size_t q_min_chain = 0;                 /* submit starts a chain only once this many samples per stream have accumulated */
+    int q_cur = 0;
+    unsigned q_ss = 16;                     /* sample bits of the accumulated samples */
+    bool q_inflight = false;
+    size_t q_inflight_frames = 0;
+    int q_inflight_bpf = 0;
+    rt::event_t q_done = 0;
+    rt::stream_t q_stream = 0;
+    std::deque<Batch> ready;
+    size_t ready_frames = 0;                /* per stream */
+    long long q_launches = 0;               /* chains sent so far (a measure of the batching achieved) */
 };
 
 extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int variant, int n_streams, size_t max_in)
@@ -1112,6 +1225,12 @@ extern "C" void sdrd_rx_destroy(sdrd_rx* r)
     if (!r) return;
     SDRD_ON_DEVICE_OF(r);
     if (r->copy_stream) rt::sync(r->copy_stream);
+    if (r->q_stream) rt::sync(r->q_stream);
+    rt::host_release(r->q_in[0]);
+    rt::host_release(r->q_in[1]);
+    rt::host_release(r->q_out);
+    rt::event_destroy(r->q_done);
+    rt::stream_destroy(r->q_stream);
     sdrd_dec_destroy(r->dec);
     sdrd_sink_destroy(r->sink);
     for (int i = 0; i < 8; i++) rt::event_destroy(r->copied[i]);
@@ -1122,6 +1241,14 @@ extern "C" int sdrd_rx_reset(sdrd_rx* r)
 {
     if (!r) return fail(SDRD_EINVAL, "null handle");
     SDRD_ON_DEVICE_OF(r);
+    {
+        std::lock_guard<std::mutex> lk(r->q_mutex);
+        if (r->q_inflight) rt::event_sync(r->q_done);
+        r->q_inflight = false;
+        r->q_fill = 0;
+        r->ready.clear();
+        r->ready_frames = 0;
+    }
     if (int rc = sdrd_dec_reset(r->dec)) return rc;
     return sdrd_sink_reset(r->sink);
 }
@@ -1142,6 +1269,8 @@ extern "C" void* sdrd_rx_dev_datagrams(sdrd_rx* r, size_t* frame_pitch)
     return r->sink->d_dgrams;
 }
 
+static int q_drain(sdrd_rx* r);
+
 /* sdrdaemonrx.cpp:618-643: the sink's sample size follows the decimator -- with decim = 0 it stays the source's
  * (rescale left-justifies the samples but the meta data keep get_sample_bits()), otherwise it is what process
  * returned; sample bytes = (bits - 1) / 8 + 1 */
@@ -1160,6 +1289,7 @@ extern "C" int sdrd_rx_process_dev(sdrd_rx* r, size_t n_in, size_t* n_frames, un
     const unsigned ss_in = sample_bits ? *sample_bits : 16u;
     if (ss_in < 1 || ss_in > 16) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
     if (n_in > r->dec->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    if (int rc = q_drain(r)) return rc;
     size_t n_out = 0;
     unsigned ss = ss_in;
     if (int rc = dec_run(r->dec, n_in, &n_out, &ss, st)) return rc;
@@ -1186,6 +1316,7 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
         if (will_close > r->sink->frame_cap) return fail(SDRD_ERANGE, "write completes more frames than the handle was sized for");
         if (will_close && !datagrams) return fail(SDRD_EINVAL, "null datagram buffer");
     }
+    if (int rc = q_drain(r)) return rc;
     rt::stream_t st = d->stream;
     /* Large calls go through in slices: the copy of slice i + 1 (copy stream) runs while slice i is being
      * decimated, framed, encoded and its datagrams copied back (compute stream), so the call costs little
@@ -1209,7 +1340,7 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
                      "copy samples to device");
             SDRD_TRY(rt::event_record(r->copied[i], r->copy_stream), "record copy event");
         } else {
-            SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, rt::H2D, st),
+            SDRD_TRY(d->stage.to_device(d->d_in + HISTW, d->in_pitch * 4, iq_in, in_stride * 4, n_in * 4, (size_t)d->S, st),
                      "copy samples to device");
         }
     }
@@ -1225,15 +1356,213 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
         if (int rc = sink_run(r->sink, d->d_out + (off >> L), d->out_pitch, n_out, &nf, st)) return rc;
         if (nf) {
             if (n_frames + nf > frame_capacity) return fail(SDRD_ERANGE, "frame_capacity smaller than the number of completed frames");
-            SDRD_TRY(rt::copy2d(datagrams + n_frames * frame_bytes, frame_capacity * frame_bytes, r->sink->d_dgrams,
-                                r->sink->last_dgram_stride * 4, nf * frame_bytes, (size_t)d->S, rt::D2H, st),
-                     "copy datagrams to host");
+            if (n_slices == 1)
+                SDRD_TRY(d->stage.to_host(datagrams + n_frames * frame_bytes, frame_capacity * frame_bytes, r->sink->d_dgrams,
+                                          r->sink->last_dgram_stride * 4, nf * frame_bytes, (size_t)d->S, st),
+                         "copy datagrams to host");
+            else
+                SDRD_TRY(rt::copy2d(datagrams + n_frames * frame_bytes, frame_capacity * frame_bytes, r->sink->d_dgrams,
+                                    r->sink->last_dgram_stride * 4, nf * frame_bytes, (size_t)d->S, rt::D2H, st),
+                         "copy datagrams to host");
         }
         n_frames += nf;
     }
     SDRD_TRY(rt::sync(st), "rx process");
+    d->stage.finish();
     if (n_frames_p) *n_frames_p = n_frames;
     if (sample_bits) *sample_bits = ss_out;
+    return 0;
+}
+
+/* ---- queued form ---- */
+
+namespace {
+/* under q_mutex: allocate the staging buffers on first use */
+int q_prepare(sdrd_rx* r)
+{
+    if (r->q_in[0]) return 0;
+    sdrd_dec* d = r->dec;
+    r->q_cap = d->max_in;
+    const size_t in_bytes = (size_t)d->S * r->q_cap * 4;
+    if (rt::host_alloc((void**)&r->q_in[0], in_bytes) != 0 || rt::host_alloc((void**)&r->q_in[1], in_bytes) != 0 ||
+        rt::event_create(&r->q_done) != 0 || rt::stream_create(&r->q_stream) != 0) {
+        rt::host_release(r->q_in[0]);
+        rt::host_release(r->q_in[1]);
+        r->q_in[0] = r->q_in[1] = nullptr;
+        return fail_cuda("allocating the page-locked staging buffers");
+    }
+    return 0;
+}
+
+/* under q_mutex: the chain in flight has completed -> its frames join `ready` */
+void q_harvest(sdrd_rx* r)
+{
+    if (!r->q_inflight) return;
+    r->q_inflight = false;
+    if (!r->q_inflight_frames) return;
+    sdrd_rx::Batch b;
+    b.blocks_per_frame = r->q_inflight_bpf;
+    b.n_frames = r->q_inflight_frames;
+    const size_t per_stream = b.n_frames * (size_t)b.blocks_per_frame * SDRD_UDPSIZE;
+    b.data.resize((size_t)r->dec->S * per_stream);
+    for (int s = 0; s < r->dec->S; s++)
+        memcpy(&b.data[(size_t)s * per_stream], r->q_out + (size_t)s * r->q_out_frames * (size_t)b.blocks_per_frame * SDRD_UDPSIZE, per_stream);
+    r->ready_frames += b.n_frames;
+    r->ready.push_back(std::move(b));
+}
+
+/* under q_mutex, nothing in flight: send everything accumulated as one chain, no synchronisation */
+int q_launch(sdrd_rx* r)
+{
+    sdrd_dec* d = r->dec;
+    const size_t n = r->q_fill;
+    if (!n) return 0;
+    rt::stream_t st = r->q_stream;
+    /* room for the frames this chain will complete (nothing is in flight: the buffer is free) */
+    {
+        const size_t will_close = sdrd_sink_frames_for(r->sink, dec_out_count(d, n));
+        const size_t need = (size_t)d->S * will_close * (size_t)(128 + r->sink->nb_fec) * SDRD_UDPSIZE;
+        if (need > r->q_out_bytes) {
+            rt::host_release(r->q_out);
+            r->q_out = nullptr;
+            r->q_out_bytes = 0;
+            if (rt::host_alloc((void**)&r->q_out, need) != 0) return fail_cuda("allocating the page-locked output buffer");
+            r->q_out_bytes = need;
+        }
+        r->q_out_frames = will_close;
+    }
+    SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, r->q_in[r->q_cur], r->q_cap * 4, n * 4, (size_t)d->S, rt::H2D, st),
+             "copy samples to device");
+    size_t n_out = 0, nf = 0;
+    unsigned ss = r->q_ss;
+    if (int rc = dec_run(d, n, &n_out, &ss, st)) return rc;
+    rx_set_sample_size(r, r->q_ss, ss);
+    if (int rc = sink_run(r->sink, d->d_out, d->out_pitch, n_out, &nf, st)) return rc;
+    const int bpf = 128 + r->sink->nb_fec;
+    if (nf) {
+        const size_t frame_bytes = (size_t)bpf * SDRD_UDPSIZE;
+        SDRD_TRY(rt::copy2d(r->q_out, r->q_out_frames * frame_bytes, r->sink->d_dgrams, r->sink->last_dgram_stride * 4, nf * frame_bytes,
+                            (size_t)d->S, rt::D2H, st),
+                 "copy datagrams to host");
+    }
+    SDRD_TRY(rt::event_record(r->q_done, st), "record completion");
+    r->q_inflight = true;
+    r->q_inflight_frames = nf;
+    r->q_inflight_bpf = bpf;
+    r->q_cur ^= 1;
+    r->q_fill = 0;
+    r->q_launches++;
+    return 0;
+}
+} /* namespace */
+
+/* the synchronous entry points on a handle that also has queued work: that work comes first */
+static int q_drain(sdrd_rx* r)
+{
+    std::unique_lock<std::mutex> lk(r->q_mutex);
+    if (!r->q_in[0]) return 0;
+    for (int round = 0; round < 2; round++) {
+        if (r->q_inflight) {
+            SDRD_TRY(rt::event_sync(r->q_done), "waiting for the chain in flight");
+            q_harvest(r);
+        }
+        if (r->q_fill)
+            if (int rc = q_launch(r)) return rc;
+    }
+    return 0;
+}
+
+extern "C" int sdrd_rx_submit(sdrd_rx* r, const int16_t* iq_in, size_t n_in, size_t in_stride, unsigned* sample_bits)
+{
+    if (!r) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(r);
+    sdrd_dec* d = r->dec;
+    if (!iq_in && n_in) return fail(SDRD_EINVAL, "null sample pointer");
+    if (n_in > d->max_in) return fail(SDRD_ERANGE, "n_in exceeds the max_in given at create time");
+    if (d->S > 1 && in_stride < n_in) return fail(SDRD_EINVAL, "in_stride smaller than n_in");
+    const unsigned ss_in = sample_bits ? *sample_bits : 16u;
+    if (ss_in < 1 || ss_in > 16) return fail(SDRD_EINVAL, "sample_bits must be 1..16");
+    /* blocks of one chain are decimated as one piece of stream: whole groups of 2^decim samples per block, as the
+     * reference's own loop bound assumes of every vector (Decimators.cpp:412) */
+    if (n_in & (((size_t)1 << d->log2_decim) - 1)) return fail(SDRD_EINVAL, "queued blocks must be a multiple of 2^decim samples");
+    std::unique_lock<std::mutex> lk(r->q_mutex);
+    if (int rc = q_prepare(r)) return rc;
+    if (r->ready_frames > 65536) return fail(SDRD_ERANGE, "too many completed frames waiting: call sdrd_rx_collect");
+    if (r->q_inflight && rt::event_done(r->q_done) != 0) q_harvest(r);
+    /* a block that does not fit behind what has accumulated, or that has another sample size, starts a new chain */
+    if (r->q_fill && (r->q_fill + n_in > r->q_cap || ss_in != r->q_ss)) {
+        if (r->q_inflight) {
+            SDRD_TRY(rt::event_sync(r->q_done), "waiting for the chain in flight");
+            q_harvest(r);
+        }
+        if (int rc = q_launch(r)) return rc;
+    }
+    r->q_ss = ss_in;
+    for (int s = 0; s < d->S; s++)
+        memcpy(r->q_in[r->q_cur] + (size_t)s * r->q_cap + r->q_fill, iq_in + 2 * (size_t)s * in_stride, n_in * 4);
+    r->q_fill += n_in;
+    if (!r->q_inflight && r->q_fill >= r->q_min_chain)
+        if (int rc = q_launch(r)) return rc;
+    if (sample_bits) { /* what the decimator makes of ss_in (Decimators.cpp:408-409,515): known without running it */
+        int norm, trunk;
+        unsigned ss_out = ss_in;
+        if (d->log2_decim > 0) shift_rule(ss_in, d->log2_decim, &norm, &trunk, &ss_out);
+        *sample_bits = ss_out;
+    }
+    return 0;
+}
+
+extern "C" int sdrd_rx_collect(sdrd_rx* r, uint8_t* datagrams, size_t frame_capacity, size_t* n_frames_p, int* blocks_per_frame,
+                               int wait)
+{
+    if (!r) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(r);
+    if (n_frames_p) *n_frames_p = 0;
+    std::unique_lock<std::mutex> lk(r->q_mutex);
+    if (wait) {
+        /* everything submitted so far: the chain in flight, then what has accumulated behind it */
+        for (int round = 0; round < 2; round++) {
+            if (r->q_inflight) {
+                SDRD_TRY(rt::event_sync(r->q_done), "waiting for the chain in flight");
+                q_harvest(r);
+            }
+            if (r->q_fill) {
+                if (int rc = q_launch(r)) return rc;
+            }
+        }
+    } else if (r->q_inflight && rt::event_done(r->q_done) != 0) {
+        q_harvest(r);
+        if (r->q_fill && r->q_fill >= r->q_min_chain)
+            if (int rc = q_launch(r)) return rc;
+    }
+    if (r->ready.empty()) return 0;
+    if (!datagrams && frame_capacity) return fail(SDRD_EINVAL, "null datagram buffer");
+    /* hand over completed frames, oldest first, while they share one frame size */
+    const int bpf = r->ready.front().blocks_per_frame;
+    const size_t frame_bytes = (size_t)bpf * SDRD_UDPSIZE;
+    size_t got = 0;
+    while (!r->ready.empty() && got < frame_capacity && r->ready.front().blocks_per_frame == bpf) {
+        sdrd_rx::Batch& b = r->ready.front();
+        const size_t take = std::min(frame_capacity - got, b.n_frames - b.taken);
+        for (int s = 0; s < r->dec->S; s++)
+            memcpy(datagrams + ((size_t)s * frame_capacity + got) * frame_bytes,
+                   &b.data[((size_t)s * b.n_frames + b.taken) * frame_bytes], take * frame_bytes);
+        b.taken += take;
+        got += take;
+        r->ready_frames -= take;
+        if (b.taken == b.n_frames) r->ready.pop_front();
+    }
+    if (n_frames_p) *n_frames_p = got;
+    if (blocks_per_frame) *blocks_per_frame = bpf;
+    return 0;
+}
+extern "C" long long sdrd_rx_chains(const sdrd_rx* r) { return r ? r->q_launches : 0; }
+extern "C" int sdrd_rx_set_min_chain(sdrd_rx* r, size_t min_samples)
+{
+    if (!r) return fail(SDRD_EINVAL, "null handle");
+    if (min_samples > r->dec->max_in) return fail(SDRD_ERANGE, "min_samples exceeds the max_in given at create time");
+    std::lock_guard<std::mutex> lk(r->q_mutex);
+    r->q_min_chain = min_samples;
     return 0;
 }
 

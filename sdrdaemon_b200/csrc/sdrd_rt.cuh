@@ -47,6 +47,11 @@ inline int event_create(event_t* e) { *e = nullptr; return 0; }
 inline void event_destroy(event_t) {}
 inline int event_record(event_t, stream_t) { return 0; }
 inline int stream_wait(stream_t, event_t) { return 0; }
+inline int event_done(event_t) { return 1; }
+inline int event_sync(event_t) { return 0; }
+inline int host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : -1; }
+inline void host_release(void* p) { free(p); }
+inline bool host_is_pageable(const void*) { return true; }
 inline const char* last_error() { return "emu"; }
 
 #define SDRD_LAUNCH(kernel, gx, gy, nthreads, smem, stream, params)                                            \
@@ -134,6 +139,8 @@ inline int copy(void* d, const void* s, size_t n, CopyKind k, stream_t st)
 inline int copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, CopyKind k, stream_t st)
 {
     if (!w || !h) return 0;
+    /* one row (one stream, the reference's case) or rows that abut: a plain copy costs the host less to enqueue */
+    if (h == 1 || (dp == w && sp == w)) return cudaMemcpyAsync(d, s, w * h, kind_of(k), st) == cudaSuccess ? 0 : -1;
     return cudaMemcpy2DAsync(d, dp, s, sp, w, h, kind_of(k), st) == cudaSuccess ? 0 : -1;
 }
 inline int sync(stream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
@@ -144,10 +151,38 @@ inline int event_create(event_t* e) { return cudaEventCreateWithFlags(e, cudaEve
 inline void event_destroy(event_t e) { if (e) cudaEventDestroy(e); }
 inline int event_record(event_t e, stream_t s) { return cudaEventRecord(e, s) == cudaSuccess ? 0 : -1; }
 inline int stream_wait(stream_t s, event_t e) { return cudaStreamWaitEvent(s, e, 0) == cudaSuccess ? 0 : -1; }
+/* 1: everything recorded before the event has completed, 0: not yet, -1: error */
+inline int event_done(event_t e)
+{
+    const cudaError_t r = cudaEventQuery(e);
+    return r == cudaSuccess ? 1 : (r == cudaErrorNotReady ? 0 : -1);
+}
+inline int event_sync(event_t e) { return cudaEventSynchronize(e) == cudaSuccess ? 0 : -1; }
+/* page-locked host memory (staging rings of the queued entry points) */
+inline int host_alloc(void** p, size_t n) { return cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault) == cudaSuccess ? 0 : -1; }
+inline void host_release(void* p) { if (p) cudaFreeHost(p); }
+/* true for ordinary (unregistered) host memory: copies from / to it are staged by the driver, synchronously */
+inline bool host_is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
 
+/* the opt-in for more than 48 KB of dynamic shared memory is per function and device: set it when a launch site
+ * first needs that much on a device, not on every launch (a microsecond each on the small-block path) */
 #define SDRD_LAUNCH(kernel, gx, gy, nthreads, smem, stream, params)                                       \
     do {                                                                                                  \
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));           \
+        static int smem_set_[64];                                                                         \
+        int dev_ = 0;                                                                                     \
+        cudaGetDevice(&dev_);                                                                             \
+        if ((int)(smem) > smem_set_[dev_ & 63]) {                                                         \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));       \
+            smem_set_[dev_ & 63] = (int)(smem);                                                           \
+        }                                                                                                 \
         kernel<<<dim3((unsigned)(gx), (unsigned)(gy), 1), dim3((unsigned)(nthreads), 1, 1), (smem), (stream)>>>(params); \
     } while (0)
 #define SDRD_LAUNCH_OK() (cudaPeekAtLastError() == cudaSuccess)

@@ -398,7 +398,10 @@ public:
         : UDPSink(address, port, SDRD_UDPSIZE), m_sink(nullptr), m_nbBlocksFEC(0) /* UDPSinkFEC.cpp:31 */, m_txDelay(0), m_running(true),
           m_tap(nullptr), m_tapUser(nullptr), m_puncture(-1)
     {
-        if (sdrd_sink_create(&m_sink, 1, max_block) != 0) m_error = sdrd_last_error();
+        if (sdrd_sink_create(&m_sink, 1, max_block + SDRD_FRAME_SAMPLES) != 0) m_error = sdrd_last_error(); /* a write plus what was collected before it */
+        /* one stamp per frame (UDPSinkFEC.cpp:89-95): the wall clock of the call that brings the frame's samples to the
+         * library, advanced by the sample clock within the call */
+        if (m_sink) sdrd_sink_set_time(m_sink, 2, 0, 0);
         std::string err;
         if (!m_tx.open(address, port, err)) m_error = err;
         m_txThread = std::thread(&UDPSinkFEC::transmitUDP, this);
@@ -415,35 +418,32 @@ public:
     }
     virtual void setNbBlocksFEC(int nbBlocksFEC) { m_nbBlocksFEC = nbBlocksFEC; }
     virtual void setTxDelay(int txDelay) { m_txDelay = txDelay; }
-    void setTimestamp(uint32_t tv_sec, uint32_t tv_usec) { if (m_sink) sdrd_sink_set_time(m_sink, 1, tv_sec, tv_usec); }
+    void setTimestamp(uint32_t tv_sec, uint32_t tv_usec) { if (m_sink) sdrd_sink_set_time(m_sink, 1, tv_sec, tv_usec); } /* tests: a fixed stamp */
     void setTap(datagram_tap tap, void* user) { m_tap = tap; m_tapUser = user; }
     void setPuncture(int block) { m_puncture = block; } /* SDRDAEMON_PUNCTURE, UDPSinkFEC.cpp:261-265 */
-    void reset() { if (m_sink) sdrd_sink_reset(m_sink); }
+    void setTxEnabled(bool on) { m_txEnabled = on; }    /* false: datagrams are built (and tapped) but not handed to sendto */
+    void reset()
+    {
+        m_pending.clear();
+        if (m_sink) sdrd_sink_reset(m_sink);
+    }
 
+    /* UDPSinkFEC::write.  Samples are collected on the host while they complete no frame (the reference's write()
+     * likewise only memcpy's them into the slot being filled, UDPSinkFEC.cpp:138-155) and go to the GPU -- framing +
+     * encode, sdrd_sink_write -- as soon as a frame completes; what was collected is pushed through first whenever a
+     * setter has changed a value since, so the library sees settings and samples in exactly the order of the calls. */
     virtual void write(const IQSampleVector& samples_in)
     {
         if (!m_sink) return;
-        sdrd_sink_set_meta(m_sink, m_centerFrequency, m_sampleRate, m_sampleBytes, m_sampleBits);
-        if (sdrd_sink_set_nb_fec(m_sink, m_nbBlocksFEC) != 0) { m_error = sdrd_last_error(); return; }
-        const int bpf = sdrd_sink_blocks_per_frame(m_sink);
-        const std::size_t cap = sdrd_sink_frames_for(m_sink, samples_in.size());
-        Batch b;
-        b.blocks_per_frame = bpf;
-        b.tx_delay = m_txDelay;
-        b.data.resize((cap ? cap : 1) * (std::size_t)bpf * SDRD_UDPSIZE);
-        std::size_t n_frames = 0;
-        if (sdrd_sink_write(m_sink, reinterpret_cast<const int16_t*>(samples_in.data()), samples_in.size(), samples_in.size(),
-                            b.data.data(), cap ? cap : 1, &n_frames) != 0) {
-            m_error = sdrd_last_error();
-            return;
+        const Settings now = {m_centerFrequency, m_sampleRate, m_sampleBytes, m_sampleBits, (int)m_nbBlocksFEC};
+        if (!(now == m_applied)) {
+            if (!push()) return; /* with the settings those samples were written under */
+            sdrd_sink_set_meta(m_sink, now.freq, now.rate, now.bytes, now.bits);
+            if (sdrd_sink_set_nb_fec(m_sink, now.nbFEC) != 0) { m_error = sdrd_last_error(); return; }
+            m_applied = now;
         }
-        if (!n_frames) return;
-        b.data.resize(n_frames * (std::size_t)bpf * SDRD_UDPSIZE);
-        {
-            std::unique_lock<std::mutex> lk(m_mutex);
-            m_queue.push_back(std::move(b));
-        }
-        m_cond.notify_all();
+        m_pending.insert(m_pending.end(), samples_in.begin(), samples_in.end());
+        if (sdrd_sink_frames_for(m_sink, m_pending.size()) > 0) push();
     }
     /* block until everything queued has been sent */
     void flush()
@@ -457,6 +457,39 @@ private:
         int blocks_per_frame, tx_delay;
         std::vector<uint8_t> data;
     };
+    struct Settings {
+        uint32_t freq, rate;
+        uint8_t bytes, bits;
+        int nbFEC;
+        bool operator==(const Settings& o) const { return freq == o.freq && rate == o.rate && bytes == o.bytes && bits == o.bits && nbFEC == o.nbFEC; }
+    };
+    /* hand the collected samples to the library; completed frames go to the Tx thread */
+    bool push()
+    {
+        if (m_pending.empty()) return true;
+        const int bpf = sdrd_sink_blocks_per_frame(m_sink);
+        const std::size_t cap = sdrd_sink_frames_for(m_sink, m_pending.size());
+        Batch b;
+        b.blocks_per_frame = bpf;
+        b.tx_delay = m_txDelay;
+        b.data.resize((cap ? cap : 1) * (std::size_t)bpf * SDRD_UDPSIZE);
+        std::size_t n_frames = 0;
+        const int rc = sdrd_sink_write(m_sink, reinterpret_cast<const int16_t*>(m_pending.data()), m_pending.size(), m_pending.size(),
+                                       b.data.data(), cap ? cap : 1, &n_frames);
+        m_pending.clear();
+        if (rc != 0) {
+            m_error = sdrd_last_error();
+            return false;
+        }
+        if (!n_frames) return true;
+        b.data.resize(n_frames * (std::size_t)bpf * SDRD_UDPSIZE);
+        {
+            std::unique_lock<std::mutex> lk(m_mutex);
+            m_queue.push_back(std::move(b));
+        }
+        m_cond.notify_all();
+        return true;
+    }
     void transmitUDP()
     {
         for (;;) {
@@ -475,7 +508,7 @@ private:
                 if (blk == m_puncture) continue;
                 const uint8_t* dg = b.data.data() + i * SDRD_UDPSIZE;
                 if (m_tap) m_tap(m_tapUser, dg, b.blocks_per_frame, blk);
-                m_tx.send(dg, SDRD_UDPSIZE);
+                if (m_txEnabled) m_tx.send(dg, SDRD_UDPSIZE);
                 if (b.tx_delay > 0) usleep(b.tx_delay);
             }
             {
@@ -486,9 +519,12 @@ private:
         }
     }
     sdrd_sink* m_sink;
+    IQSampleVector m_pending;           /* samples written since the last frame completed */
+    Settings m_applied = {0, 0, 0, 0, -1}; /* what the library was last told */
     std::atomic_int m_nbBlocksFEC, m_txDelay;
     bool m_running;
     bool m_sending = false;
+    bool m_txEnabled = true;
     datagram_tap m_tap;
     void* m_tapUser;
     int m_puncture;

@@ -450,3 +450,59 @@ def check_sink_frame_clock(lib, ob, splits, rate=48000, F=4, base=(1700000000, 9
     stamps = {(int.from_bytes(f[0, 16:20].tobytes(), "little"), int.from_bytes(f[0, 20:24].tobytes(), "little")) for f in got}
     assert len(stamps) > 1
     sk.close()
+
+
+def check_rx_queued(lib, ob, M, F, S, blk, n_blk, max_blocks=8, threaded=False, bits=16, seed=808):
+    """sdrd_rx_submit / sdrd_rx_collect: blocks of `blk` samples submitted one after the other (batched on the way as
+    far as the device lags), frames collected in between or from a second thread -- the datagram stream must be the
+    one UDPSinkFEC::write produces from the decimated stream (oracle), whatever the batching was."""
+    import threading
+
+    rng = np.random.default_rng(seed)
+    x = rand_iq(rng, (S, blk * n_blk), bits)
+    rx = capi.Rx(M, n_streams=S, max_in=blk * max_blocks, n_fec=F, lib=lib)
+    got = []
+    if threaded:
+        done = threading.Event()
+
+        def consumer():
+            while True:
+                last = done.is_set()
+                g = rx.collect(16, wait=last)
+                if g.shape[1]:
+                    got.append(g)
+                elif last:
+                    return
+
+        th = threading.Thread(target=consumer)
+        th.start()
+        for b in range(n_blk):
+            ss = rx.submit(x[:, b * blk:(b + 1) * blk], bits)
+        done.set()
+        th.join()
+        got.append(rx.collect(1 << 10, wait=True))
+    else:
+        for b in range(n_blk):
+            ss = rx.submit(x[:, b * blk:(b + 1) * blk], bits)
+            if b % 5 == 4:
+                g = rx.collect(3)          # a capacity smaller than what may be ready: the rest stays queued
+                if g.shape[1]:
+                    got.append(g)
+        while True:
+            g = rx.collect(7, wait=True)
+            if not g.shape[1]:
+                break
+            got.append(g)
+    g = np.concatenate(got, axis=1)
+    for s in range(S):
+        y, sso = ob.Decimator(M).process(x[s], bits)
+        mb = bits if M == 0 else sso
+        assert ss == sso
+        k = ob.Sink(n_fec=F, sample_bits=mb, sample_bytes=(mb - 1) // 8 + 1)
+        k.write(y)
+        want = np.stack(k.frames)
+        assert g[s].shape == want.shape, (g[s].shape, want.shape)
+        assert np.array_equal(g[s], want), f"queued path, stream {s}: datagrams differ from the oracle"
+    chains = rx.chains
+    rx.close()
+    return chains

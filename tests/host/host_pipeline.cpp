@@ -168,11 +168,65 @@ static int run_pipeline(int argc, char** argv)
     return 0;
 }
 
+/* host_pipeline blocks <n_blocks> <decim> <fecblk> <blklen> [warmup]
+ * The reference's call granularity, timed: one stream, TestSource-sized blocks in pageable std::vectors through
+ * Downsampler::process + UDPSinkFEC::write (sdrdaemonrx.cpp:636-660), datagrams built but not sent.  Prints one JSON
+ * line; bench.py's `small_block` leg runs this. */
+static int run_blocks(int argc, char** argv)
+{
+    if (argc < 6) return 2;
+    const int n_blocks = atoi(argv[2]), decim = atoi(argv[3]), fecblk = atoi(argv[4]), blklen = atoi(argv[5]);
+    const int warmup = argc > 6 ? atoi(argv[6]) : 8;
+    Downsampler dn((unsigned)decim, Downsampler::FC_POS_CENTER, SDRD_HB_EO1, (size_t)blklen);
+    if (!dn) { fprintf(stderr, "Downsampler: %s\n", dn.error().c_str()); return 1; }
+    UDPSinkFEC udp_output("127.0.0.1", 19399, (size_t)blklen);
+    if (!udp_output) { fprintf(stderr, "UDPSinkFEC: %s\n", udp_output.error().c_str()); return 1; }
+    udp_output.setTxEnabled(false);
+    udp_output.setNbBlocksFEC(fecblk);
+    udp_output.setSampleRate(10000000u >> decim);
+    udp_output.setCenterFrequency(435000000ull);
+    udp_output.setSampleBytes(2);
+    /* a few distinct source blocks (TestSource arithmetic), cycled */
+    const int n_src = 8;
+    std::vector<IQSampleVector> src(n_src);
+    float phase = 0;
+    std::vector<int16_t> buf(2 * (size_t)blklen);
+    for (int i = 0; i < n_src; i++) {
+        int got = 0;
+        TestSource::read_samples(buf.data(), 4 * blklen, got, phase, 10000000, 0.0628f, 0.5f, false);
+        src[i].resize(blklen);
+        memcpy((void*)src[i].data(), buf.data(), (size_t)blklen * 4);
+    }
+    IQSampleVector outsamples;
+    long long frames_bytes = 0;
+    struct timeval t0, t1;
+    for (int blk = -warmup; blk < n_blocks; blk++) {
+        if (blk == 0) {
+            udp_output.flush();
+            gettimeofday(&t0, 0);
+        }
+        unsigned int sampleSize = 16;
+        dn.process(sampleSize, src[(blk + warmup) % n_src], outsamples);
+        udp_output.setSampleBits((uint8_t)sampleSize);
+        udp_output.write(outsamples);
+        if (!dn || !udp_output) { fprintf(stderr, "error: %s %s\n", dn.error().c_str(), udp_output.error().c_str()); return 1; }
+    }
+    udp_output.flush();
+    gettimeofday(&t1, 0);
+    const double dt = (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_usec - t0.tv_usec);
+    (void)frames_bytes;
+    printf("{\"blocks\": %d, \"blklen\": %d, \"decim\": %d, \"fecblk\": %d, \"seconds\": %.6f, \"msamples_per_s\": %.3f, "
+           "\"us_per_block\": %.2f}\n",
+           n_blocks, blklen, decim, fecblk, dt, (double)n_blocks * blklen / dt * 1e-6, dt / n_blocks * 1e6);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 2 && std::string(argv[1]) == "blocks") return run_blocks(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "testsource") return run_testsource(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "upsample") return run_upsample(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "pipeline") return run_pipeline(argc, argv);
-    fprintf(stderr, "usage: host_pipeline testsource|upsample|pipeline ...\n");
+    fprintf(stderr, "usage: host_pipeline testsource|upsample|pipeline|blocks ...\n");
     return 2;
 }

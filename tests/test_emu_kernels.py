@@ -207,3 +207,9 @@ def test_rescale_keeps_filter_state(emu_lib, oracle):
 def test_sink_per_frame_time_stamps(emu_lib, oracle):
     F = cases.FRAME
     cases.check_sink_frame_clock(emu_lib, oracle, [0, 100, 100 + 3 * F, 100 + 3 * F + 50, 5 * F + 7, 6 * F + 7])
+
+
+def test_rx_queued(emu_lib, oracle):
+    cases.check_rx_queued(emu_lib, oracle, M=2, F=4, S=2, blk=4096, n_blk=24)
+    cases.check_rx_queued(emu_lib, oracle, M=4, F=8, S=1, blk=65536, n_blk=9, max_blocks=2, bits=12)
+    cases.check_rx_queued(emu_lib, oracle, M=1, F=0, S=1, blk=8192, n_blk=10, threaded=True)

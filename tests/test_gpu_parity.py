@@ -432,3 +432,14 @@ def test_full_size_config5_shard_every_stream(gpu_lib, oracle):
     """BASELINE config 5, one GPU's shard at full size: 256 streams x 2 superframes, decimate-by-64, 128 + 32 FEC
     (528 M input samples), every stream against the oracle."""
     _full_size_rx(gpu_lib, oracle, M=6, F=32, S=256, frames=2, seed=50000, batch=128)
+
+
+def test_rx_queued(gpu_lib, oracle):
+    """the queued form at the reference's block size: submit never waits for the device, blocks are batched on the way"""
+    n_blk = 64
+    chains = cases.check_rx_queued(gpu_lib, oracle, M=4, F=16, S=1, blk=65536, n_blk=n_blk, max_blocks=16)
+    assert 1 <= chains <= n_blk + 1
+    cases.check_rx_queued(gpu_lib, oracle, M=2, F=4, S=3, blk=4096, n_blk=100)
+    cases.check_rx_queued(gpu_lib, oracle, M=5, F=32, S=2, blk=65536, n_blk=20, max_blocks=3, bits=8)
+    cases.check_rx_queued(gpu_lib, oracle, M=4, F=16, S=1, blk=65536, n_blk=64, max_blocks=16, threaded=True)
+    cases.check_rx_queued(gpu_lib, oracle, M=0, F=8, S=1, blk=16384, n_blk=30, bits=12)
