@@ -411,7 +411,7 @@ def run_interp(args):
                                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}}), flush=True)
 
 
-def small_block_leg(lib, capi, n_blocks=1500, blk=65536):
+def small_block_leg(lib, capi, n_blocks=4000, blk=65536):
     """The reference's call granularity: ONE stream fed in TestSource-sized blocks of 65536 samples
     (include/TestSource.h:33) from pageable host memory, the way sdrdaemonrx's main loop feeds Downsampler::process +
     UDPSinkFEC::write (sdrdaemonrx.cpp:579-663).  Three forms, same config as the headline:
@@ -445,7 +445,7 @@ def small_block_leg(lib, capi, n_blocks=1500, blk=65536):
     rx = capi.Rx(M_LOG2, n_streams=1, max_in=32 * blk, n_fec=N_FEC)
     nfr = C.c_size_t(0)
     for warm in (True, False):
-        n = 50 if warm else n_blocks
+        n = 500 if warm else n_blocks
         t0 = time.perf_counter()
         for b in range(n):
             lib.check(lib.sdrd_rx_process(rx._h, ptrs[b & 7], blk, blk, out.ctypes.data, 64, C.byref(nfr), None))
@@ -458,7 +458,7 @@ def small_block_leg(lib, capi, n_blocks=1500, blk=65536):
         rx.set_min_chain(min_chain)
         frames = 0
         for warm in (True, False):
-            n = 64 if warm else n_blocks
+            n = 512 if warm else n_blocks
             c0 = rx.chains
             t0 = time.perf_counter()
             for b in range(n):
@@ -485,10 +485,18 @@ def small_block_leg(lib, capi, n_blocks=1500, blk=65536):
             cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
             subprocess.run([cxx, "-std=c++17", "-O2", "-pthread", "-o", exe, srcf, f"-L{libdir}", "-lsdrd_b200", f"-Wl,-rpath,{libdir}"],
                            check=True, capture_output=True)
-        r = subprocess.run([exe, "blocks", str(n_blocks), str(M_LOG2), str(N_FEC), str(blk), "50"], capture_output=True, text=True, timeout=300)
+        r = subprocess.run([exe, "blocks", str(n_blocks), str(M_LOG2), str(N_FEC), str(blk), "500"], capture_output=True, text=True, timeout=300)
         j = json.loads(r.stdout.strip().splitlines()[-1])
         res["classes"] = {"value": round(j["msamples_per_s"], 1), "unit": UNIT, "us_per_block": j["us_per_block"],
-                          "api": "Downsampler::process + UDPSinkFEC::write (sdrd_host.hpp)"}
+                          "api": "Downsampler::process + UDPSinkFEC::write (sdrd_host.hpp), native caller"}
+        # the queued entry points from a native caller (the ctypes legs above pay ~5 us of interpreter per call)
+        for key, mc in (("queued_native", 0), ("queued_batched_native", 16)):
+            r = subprocess.run([exe, "blocksq", str(4 * n_blocks), str(M_LOG2), str(N_FEC), str(blk), str(mc), "1000"], capture_output=True,
+                               text=True, timeout=300)
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            res[key] = {"value": round(j["msamples_per_s"], 1), "unit": UNIT, "us_per_block": j["us_per_block"],
+                        "blocks_per_chain": j["blocks_per_chain"],
+                        "api": "sdrd_rx_submit + sdrd_rx_collect from C++" + (f", sdrd_rx_set_min_chain({mc} blocks)" if mc else "")}
     except Exception as e:
         res["classes"] = {"value": None, "note": f"not measured ({type(e).__name__})"}
     return res

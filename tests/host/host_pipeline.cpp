@@ -221,8 +221,62 @@ static int run_blocks(int argc, char** argv)
     return 0;
 }
 
+/* host_pipeline blocksq <n_blocks> <decim> <fecblk> <blklen> <min_chain_blocks> [warmup]
+ * The same blocks through the queued C entry points (sdrd_rx_submit / sdrd_rx_collect) from a native caller: what a
+ * main loop gets that hands its blocks over instead of waiting for each (route C). */
+static int run_blocksq(int argc, char** argv)
+{
+    if (argc < 7) return 2;
+    const int n_blocks = atoi(argv[2]), decim = atoi(argv[3]), fecblk = atoi(argv[4]), blklen = atoi(argv[5]), min_chain = atoi(argv[6]);
+    const int warmup = argc > 7 ? atoi(argv[7]) : 64;
+    sdrd_rx* rx = nullptr;
+    if (sdrd_rx_create(&rx, decim, SDRD_FC_CENTER, SDRD_HB_EO1, 1, (size_t)blklen * 32) != 0) { fprintf(stderr, "%s\n", sdrd_last_error()); return 1; }
+    sdrd_sink_set_nb_fec(sdrd_rx_sink(rx), fecblk);
+    sdrd_sink_set_meta(sdrd_rx_sink(rx), 435000, 10000000u >> decim, 2, 16);
+    sdrd_rx_set_min_chain(rx, (size_t)min_chain * blklen);
+    const int n_src = 8;
+    std::vector<IQSampleVector> src(n_src);
+    float phase = 0;
+    std::vector<int16_t> buf(2 * (size_t)blklen);
+    for (int i = 0; i < n_src; i++) {
+        int got = 0;
+        TestSource::read_samples(buf.data(), 4 * blklen, got, phase, 10000000, 0.0628f, 0.5f, false);
+        src[i].resize(blklen);
+        memcpy((void*)src[i].data(), buf.data(), (size_t)blklen * 4);
+    }
+    std::vector<uint8_t> out((size_t)64 * (128 + fecblk) * SDRD_UDPSIZE);
+    size_t nfr = 0, frames = 0;
+    int bpf = 0;
+    long long chains0 = 0;
+    struct timeval t0, t1;
+    for (int blk = -warmup; blk < n_blocks; blk++) {
+        if (blk == 0) {
+            do { sdrd_rx_collect(rx, out.data(), 64, &nfr, &bpf, 1); } while (nfr);
+            chains0 = sdrd_rx_chains(rx);
+            gettimeofday(&t0, 0);
+        }
+        if (sdrd_rx_submit(rx, reinterpret_cast<const int16_t*>(src[(blk + warmup) % n_src].data()), (size_t)blklen, (size_t)blklen, nullptr) != 0 ||
+            sdrd_rx_collect(rx, out.data(), 64, &nfr, &bpf, 0) != 0) { fprintf(stderr, "%s\n", sdrd_last_error()); return 1; }
+        frames += nfr;
+    }
+    do {
+        if (sdrd_rx_collect(rx, out.data(), 64, &nfr, &bpf, 1) != 0) { fprintf(stderr, "%s\n", sdrd_last_error()); return 1; }
+        frames += nfr;
+    } while (nfr);
+    gettimeofday(&t1, 0);
+    const double dt = (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_usec - t0.tv_usec);
+    const long long chains = sdrd_rx_chains(rx) - chains0;
+    printf("{\"blocks\": %d, \"blklen\": %d, \"decim\": %d, \"fecblk\": %d, \"seconds\": %.6f, \"msamples_per_s\": %.3f, "
+           "\"us_per_block\": %.2f, \"blocks_per_chain\": %.2f, \"frames\": %zu}\n",
+           n_blocks, blklen, decim, fecblk, dt, (double)n_blocks * blklen / dt * 1e-6, dt / n_blocks * 1e6,
+           (double)n_blocks / (double)(chains > 0 ? chains : 1), frames);
+    sdrd_rx_destroy(rx);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 2 && std::string(argv[1]) == "blocksq") return run_blocksq(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "blocks") return run_blocks(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "testsource") return run_testsource(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "upsample") return run_upsample(argc, argv);
