@@ -381,6 +381,7 @@ struct DecParams {
      * order -- goes to recovered[(f * 128 + k) * 127 ..], for EVERY k: copying back only the last N descriptors is
      * SDRdaemonFECBuffer's doing (.cpp:208-213), not the library's. */
     uint32_t* recovered;
+    int n_frames;              /* decode_stream_kernel: frames of the batch (its CTAs are persistent) */
     int general_single;        /* 1: a lone recovery block is solved like any other (cm256 takes its XOR shortcut only
                                   when params.RecoveryCount == 1, not when one recovery block happens to be present) */
     Tables tab;
@@ -624,6 +625,335 @@ SDRD_KERNEL(NT, (DCAP <= 32 ? 2 : 1)) decode_kernel(DecParams p)
         }
     }
     if (tid == 0) p.status[f] = st;
+}
+
+
+/* ============================================================================ decode, streaming form ====
+ * K3 as of round 2.  The CTA-wide kernel above stages the whole frame (64 KB) in shared memory and walks it once
+ * per block of 16 output rows; with the 20 erasures of BASELINE config 4 that is two passes, the second with 4 of
+ * its 16 rows in use, a dozen CTA barriers per frame and two resident CTAs per SM.  Here every datagram word is read
+ * ONCE, straight from global memory into registers:
+ *   - a CTA is four warps = two halves of the datagram words x two groups of output rows; lanes hold 2 words (8-byte
+ *     loads, 256 B per warp) of every one of the 128 datagrams, fetched two column pairs ahead into registers that
+ *     are reloaded the moment their selectors are built;
+ *   - all N <= 32 output rows accumulate in registers in one pass (2 words x N/2 rows per warp, N rounded up to a
+ *     multiple of 4, the loop picked per frame from eight instantiations): a warp owns its words of its rows, so
+ *     there is nothing to merge and the recovered blocks leave from the accumulators (the price: the digit selectors
+ *     of a data word, 3 % of the work, are built by both row groups);
+ *   - received originals go out from the same registers (no shared-memory image, no second read);
+ *   - the coefficient matrix is held as full-word table offsets [row][datagram]: the entries of a column pair arrive
+ *     in one 8-byte load and go straight into the address of the table loads (packed 16-bit entries cost two ALU
+ *     instructions per row to pull apart, and the ALU pipe is what bounds this kernel);
+ *   - 28 KB of shared memory per CTA (tables, coefficient matrix, lists), four CTAs per SM.
+ * Classification and the closed-form decode matrix are those of the kernel above (which stays for frames with more
+ * than 32 recovery blocks). */
+#ifndef SDRD_K3_CTAS_PER_SM
+#define SDRD_K3_CTAS_PER_SM 4 /* resident 128-thread CTAs per SM the register budget is set for (4: 128 registers) */
+#endif
+constexpr int DS_NT = 128;
+constexpr int DS_CAP = 32;   /* rows the streaming form holds */
+constexpr size_t ds_smem_bytes() { return 256 * TAB_ENTRY + 128 * DS_CAP * 4 + 512 + 256 + 3072; }
+
+struct DsOut {
+    uint32_t* pay;        /* payload of the frame (blocks 1..127) or null */
+    uint32_t* b0;         /* block 0 or null */
+    uint32_t* recovered;  /* bare cm256 form: recovered + (f * 128 + c) * 127, or null */
+    const uint32_t* hdr;
+    const int* origRow;
+    const uint8_t* erased;
+    const uint8_t* recRowOf;
+    int N;
+};
+
+/* NR = rows per warp: warp (half, rg) holds rows rg * NR .. rg * NR + NR - 1 for the word half `half` */
+template <int NR>
+SDRD_DEVICE void ds_pass(const uint32_t* SDRD_RESTRICT frame, int half, int rg, int lane, const uint32_t* SDRD_RESTRICT coef_all,
+                         const unsigned char* SDRD_RESTRICT tab, const DsOut& o)
+{
+    const int m = 32 * half + lane;           /* this lane's word pair: words 2m, 2m + 1 of every datagram */
+    const uint2* src = reinterpret_cast<const uint2*>(frame) + m;
+    const bool pass_through = o.recovered == nullptr && rg == 0; /* one row group sends the received originals on */
+    const uint32_t* coef = coef_all + rg * NR * 128;
+    uint32_t acc[NR][2];
+#pragma unroll
+    for (int r = 0; r < NR; r++) acc[r][0] = acc[r][1] = 0u;
+    /* two column pairs in flight (A, B): a pair's words are dead once its selectors are built, so its registers are
+     * reloaded with the pair two ahead right there -- no register moves, the loads have a whole row loop to arrive */
+    uint2 xa0 = src[0], xa1 = src[ROW_WORDS / 2];
+    uint2 xb0 = src[2 * (ROW_WORDS / 2)], xb1 = src[3 * (ROW_WORDS / 2)];
+    auto column_pair = [&](int jj, uint2& c0, uint2& c1) {
+        if (pass_through) { /* a received original leaves as it is: payload word k of the datagram is word k + 1 */
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int i = jj + c;
+                const int z = (int)((o.hdr[i] >> 16) & 0xFFu);
+                if (z < 128 && o.origRow[z] == i) {
+                    uint32_t* d = z == 0 ? o.b0 : o.pay + (z - 1) * 127;
+                    if (d) {
+                        const uint2 v = c ? c1 : c0;
+                        if (m > 0) d[2 * m - 1] = v.x;
+                        d[2 * m] = v.y;
+                    }
+                }
+            }
+        }
+        uint32_t s0[2][2], s1[2][2], s2[2][2];
+        selectors(c0.x, s0[0][0], s1[0][0], s2[0][0]);
+        selectors(c0.y, s0[0][1], s1[0][1], s2[0][1]);
+        selectors(c1.x, s0[1][0], s1[1][0], s2[1][0]);
+        selectors(c1.y, s0[1][1], s1[1][1], s2[1][1]);
+        if (jj + 4 < 128) {
+            c0 = src[(size_t)(jj + 4) * (ROW_WORDS / 2)];
+            c1 = src[(size_t)(jj + 5) * (ROW_WORDS / 2)];
+        }
+        const uint2* co = reinterpret_cast<const uint2*>(coef + jj);
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const uint2 cc = co[r * (128 / 2)];
+            const unsigned char* e0 = tab + cc.x;
+            const unsigned char* e1 = tab + cc.y;
+            const uint4 a0 = *reinterpret_cast<const uint4*>(e0);
+            const uint32_t q0 = *reinterpret_cast<const uint32_t*>(e0 + 16);
+            const uint4 a1 = *reinterpret_cast<const uint4*>(e1);
+            const uint32_t q1 = *reinterpret_cast<const uint32_t*>(e1 + 16);
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                uint32_t v = acc[r][w];
+                v = v ^ prmt(a0.x, a0.y, s0[0][w]) ^ prmt(a0.z, a0.w, s1[0][w]);
+                v = v ^ prmt(q0, q0, s2[0][w]) ^ prmt(a1.x, a1.y, s0[1][w]);
+                v = v ^ prmt(a1.z, a1.w, s1[1][w]) ^ prmt(q1, q1, s2[1][w]);
+                acc[r][w] = v;
+            }
+        }
+    };
+#pragma unroll 1
+    for (int jj = 0; jj < 128; jj += 4) {
+        column_pair(jj, xa0, xa1);
+        column_pair(jj + 2, xb0, xb1);
+    }
+    /* row c = the original solved into recovery descriptor c = erased original c: straight from the accumulators */
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const int c = rg * NR + r;
+        if (c < o.N) {
+            uint32_t* d;
+            bool copied = true;
+            if (o.recovered) {
+                d = o.recovered + c * 127;
+            } else {
+                const int b = o.erased[c];
+                /* the reference copies back only the LAST N descriptors (.cpp:208-213): a recovery block that arrived
+                 * before an original keeps its result to itself and the erased block stays zero */
+                copied = (int)o.recRowOf[c] >= 128 - o.N;
+                d = b == 0 ? o.b0 : o.pay + (b - 1) * 127;
+            }
+            if (d) {
+                if (m > 0) d[2 * m - 1] = copied ? acc[r][0] : 0u;
+                d[2 * m] = copied ? acc[r][1] : 0u;
+            }
+        }
+    }
+}
+
+SDRD_KERNEL(DS_NT, SDRD_K3_CTAS_PER_SM) decode_stream_kernel(DecParams p)
+{
+    const int n_frames = p.n_frames;
+    SDRD_DYN_SMEM(smem_raw);
+    const int tid = (int)threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    unsigned char* tab = smem_raw;                                                   /* [256][32] */
+    uint32_t* coef = reinterpret_cast<uint32_t*>(tab + 256 * TAB_ENTRY);             /* [DS_CAP][128] */
+    uint8_t* gfexp = reinterpret_cast<uint8_t*>(coef + DS_CAP * 128);                /* [512] */
+    uint8_t* gflog = gfexp + 512;                                                    /* [256] */
+    int* lists = reinterpret_cast<int*>(gflog + 256);                                /* 3072 bytes */
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(lists);   /* [128] header word of datagram i */
+    int* origRow = lists + 128;                           /* [128] datagram holding original b, or -1 */
+    int* origCnt = lists + 256;                           /* [128] */
+    unsigned* recMask = reinterpret_cast<unsigned*>(lists + 384);  /* [4] */
+    unsigned* missMask = recMask + 4;                              /* [4] */
+    int* flags = lists + 392;                                      /* [2] */
+    unsigned* recSeen = reinterpret_cast<unsigned*>(lists + 394);  /* [4] */
+    uint8_t* recRowOf = reinterpret_cast<uint8_t*>(lists + 400);   /* [128] */
+    uint8_t* recIdxOf = recRowOf + 128;
+    uint8_t* erased = recIdxOf + 128;
+    uint8_t* lbase = erased + 128;
+    uint8_t* lp = lbase + 128;                                     /* [DS_CAP] */
+
+    for (int i = tid; i < 256; i += DS_NT) {
+        *reinterpret_cast<uint4*>(tab + i * TAB_ENTRY) = p.tab.tabA[i];
+        *reinterpret_cast<uint32_t*>(tab + i * TAB_ENTRY + 16) = p.tab.tabB[i];
+    }
+    for (int i = tid; i < 512; i += DS_NT) gfexp[i] = p.tab.gfexp[i];
+    for (int i = tid; i < 256; i += DS_NT) gflog[i] = p.tab.gflog[i];
+
+    for (int f = (int)blockIdx.x; f < n_frames; f += (int)gridDim.x) {
+        __syncthreads(); /* the lists of the previous frame are no longer read */
+        int nb = p.n_blocks[f];
+        if (nb > 128) nb = 128; /* blocks beyond the first 128 received are dropped (.cpp:143) */
+        if (nb > p.blocks_pitch) nb = (int)p.blocks_pitch;
+        if (nb < 0) nb = 0;
+        const long long first = p.frame_start ? p.frame_start[f] : (long long)f * p.blocks_pitch;
+        const uint32_t* frame = p.sb + first * ROW_WORDS;
+        for (int i = tid; i < 128; i += DS_NT) {
+            hdr[i] = i < nb ? frame[(size_t)i * ROW_WORDS] : 0u;
+            origRow[i] = -1;
+            origCnt[i] = 0;
+        }
+        if (tid < 8) recMask[tid] = 0u;
+        if (tid < 6) flags[tid] = 0;
+        __syncthreads();
+
+        /* classify the received datagrams by header.blockIndex (.cpp:143-166) */
+        for (int i = tid; i < nb; i += DS_NT) {
+            const int idx = (int)((hdr[i] >> 16) & 0xFFu);
+            if (idx < 128) {
+                atomicMax(&origRow[idx], i); /* a repeated original overwrites the earlier copy */
+                atomicAdd(&origCnt[idx], 1);
+            } else {
+                atomicOr(&recMask[i >> 5], 1u << (i & 31));
+                if (atomicOr(&recSeen[(idx - 128) >> 5], 1u << (idx & 31)) & (1u << (idx & 31))) flags[1] = 1;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 128; i += DS_NT) {
+            if (origRow[i] < 0) atomicOr(&missMask[i >> 5], 1u << (i & 31));
+            if (origCnt[i] > 1) flags[0] = 1;
+        }
+        __syncthreads();
+        const int N = __popc(recMask[0]) + __popc(recMask[1]) + __popc(recMask[2]) + __popc(recMask[3]);
+        const int n_missing = __popc(missMask[0]) + __popc(missMask[1]) + __popc(missMask[2]) + __popc(missMask[3]);
+        for (int i = tid; i < 128; i += DS_NT) {
+            const int wq = i >> 5;
+            const unsigned below = (1u << (i & 31)) - 1u;
+            int rr = 0, rm = 0;
+            for (int q = 0; q < wq; q++) {
+                rr += __popc(recMask[q]);
+                rm += __popc(missMask[q]);
+            }
+            if (recMask[wq] & (1u << (i & 31))) {
+                const int k = rr + __popc(recMask[wq] & below);
+                recRowOf[k] = (uint8_t)i;
+                recIdxOf[k] = (uint8_t)((hdr[i] >> 16) & 0xFFu);
+            }
+            if (missMask[wq] & (1u << (i & 31))) erased[rm + __popc(missMask[wq] & below)] = (uint8_t)i;
+        }
+        __syncthreads();
+
+        int st;
+        bool do_decode = false;
+        if (nb < 128) st = ST_INCOMPLETE;
+        else if (N == 0) st = ST_COMPLETE;
+        else if (flags[0] || n_missing < N) st = ST_FAILED; /* repeated original: cm256_decode refuses */
+        else if (flags[1] && N > 1) st = ST_FAILED;         /* repeated recovery row: no solution */
+        else if (N > DS_CAP) st = ST_NEEDS_BIG;
+        else {
+            st = ST_RECOVERED;
+            do_decode = true;
+        }
+        if (tid == 0) p.status[f] = st;
+        if (st == ST_NEEDS_BIG) continue; /* left to decode_kernel<128>, which writes everything of this frame */
+        const int NR = (N + 3) & ~3;
+
+        if (do_decode) {
+            /* the decode matrix D [NR][128 datagrams], see decode_kernel for the closed form */
+            const bool shortcut = N == 1 && !p.general_single;
+            if (!shortcut) {
+                for (int i = tid; i < 128; i += DS_NT) {
+                    const int z = (int)((hdr[i] >> 16) & 0xFFu);
+                    const bool used = z >= 128 || origRow[z] == i;
+                    int me = -1;
+                    if (z >= 128) {
+                        const int wq = i >> 5;
+                        me = __popc(recMask[wq] & ((1u << (i & 31)) - 1u));
+                        for (int q = 0; q < wq; q++) me += __popc(recMask[q]);
+                    }
+                    int a = 0;
+                    if (used) {
+                        if (z < 128) a = gflog[z ^ 128];
+                        for (int j = 0; j < N; j++) {
+                            a += gflog[z ^ erased[j]];
+                            if (j != me) a += 255 - gflog[z ^ recIdxOf[j]];
+                        }
+                    }
+                    lbase[i] = (uint8_t)(a % 255);
+                }
+                if (tid < N) {
+                    const int v = erased[tid];
+                    int b = 255 - gflog[v ^ 128];
+                    for (int j = 0; j < N; j++) {
+                        b += gflog[v ^ recIdxOf[j]];
+                        if (j != tid) b += 255 - gflog[v ^ erased[j]];
+                    }
+                    lp[tid] = (uint8_t)(b % 255);
+                }
+                __syncthreads();
+            }
+            for (int i = tid; i < 128; i += DS_NT) {
+                const int z = (int)((hdr[i] >> 16) & 0xFFu);
+                const bool used = z >= 128 || origRow[z] == i;
+                const int lb = shortcut ? 0 : lbase[i];
+                for (int c = 0; c < NR; c++) {
+                    uint32_t v = 0u;
+                    if (shortcut) {
+                        v = c == 0 ? 1u : 0u; /* cm256's single-recovery shortcut: XOR of everything received */
+                    } else if (c < N && used) {
+                        int t = lp[c] + lb;
+                        if (t >= 255) t -= 255;
+                        v = gfexp[t + 255 - gflog[z ^ erased[c]]];
+                    }
+                    coef[c * 128 + i] = (uint32_t)TAB_ENTRY * v;
+                }
+            }
+            __syncthreads();
+        }
+
+        DsOut o;
+        o.pay = p.payload ? p.payload + (long long)f * 127 * 127 : nullptr;
+        o.b0 = p.block0 ? p.block0 + (long long)f * 127 : nullptr;
+        o.recovered = p.recovered ? p.recovered + (long long)f * 128 * 127 : nullptr;
+        o.hdr = hdr;
+        o.origRow = origRow;
+        o.erased = erased;
+        o.recRowOf = recRowOf;
+        o.N = N;
+        const bool raw = p.recovered != nullptr;
+
+        if (do_decode) {
+            const int half = warp & 1, rg = warp >> 1;
+            switch (NR) { /* two row groups of NR / 2 rows */
+                case 4: ds_pass<2>(frame, half, rg, lane, coef, tab, o); break;
+                case 8: ds_pass<4>(frame, half, rg, lane, coef, tab, o); break;
+                case 12: ds_pass<6>(frame, half, rg, lane, coef, tab, o); break;
+                case 16: ds_pass<8>(frame, half, rg, lane, coef, tab, o); break;
+                case 20: ds_pass<10>(frame, half, rg, lane, coef, tab, o); break;
+                case 24: ds_pass<12>(frame, half, rg, lane, coef, tab, o); break;
+                case 28: ds_pass<14>(frame, half, rg, lane, coef, tab, o); break;
+                default: ds_pass<16>(frame, half, rg, lane, coef, tab, o); break;
+            }
+            /* erased originals beyond the N recovered ones stay zero */
+            if (!raw)
+                for (int c = N + warp; c < n_missing; c += DS_NT / 32) {
+                    const int b = erased[c];
+                    uint32_t* dstb = b == 0 ? o.b0 : o.pay + (b - 1) * 127;
+                    if (!dstb) continue;
+                    for (int k = lane; k < 127; k += 32) dstb[k] = 0u;
+                }
+        } else if (!raw) {
+            /* nothing to solve: originals that arrived go out as they are, blocks that did not read as zero (.cpp:109) */
+            for (int b = warp; b < 128; b += DS_NT / 32) {
+                const int row = origRow[b];
+                uint32_t* dstb = b == 0 ? o.b0 : o.pay + (b - 1) * 127;
+                if (!dstb) continue;
+                const uint32_t* srcb = frame + (size_t)(row < 0 ? 0 : row) * ROW_WORDS + 1;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int k = lane + 32 * q;
+                    if (k < 127) dstb[k] = row >= 0 ? srcb[k] : 0u;
+                }
+            }
+        }
+    }
 }
 
 } /* namespace fec */

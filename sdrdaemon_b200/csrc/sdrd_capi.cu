@@ -222,6 +222,16 @@ int enc_grid(long long items)
     return (int)((items + per - 1) / per);
 }
 
+/* persistent decode grid: SDRD_K3_CTAS_PER_SM two-warp CTAs per SM, each walking frames blockIdx.x, + gridDim.x, .. */
+#ifndef SDRD_K3_GRID_WAVES
+#define SDRD_K3_GRID_WAVES 1000 /* CTAs launched per resident slot: 1 = persistent (measured slower: the static shares leave a tail), large = one CTA per frame */
+#endif
+int dec_grid(long long n_frames)
+{
+    const long long slots = (long long)rt::sm_count() * SDRD_K3_CTAS_PER_SM;
+    return (int)(n_frames < slots * SDRD_K3_GRID_WAVES ? n_frames : slots * SDRD_K3_GRID_WAVES);
+}
+
 template <int M, int PRO>
 void launch_decimate_warp2(const hb::Params& p, int n_seg, rt::stream_t st)
 {
@@ -1708,7 +1718,8 @@ extern "C" int sdrd_fec_decode_dev(const uint8_t* superblocks, size_t blocks_pit
     p.status = status;
     rt::stream_t st = (rt::stream_t)cuda_stream;
     p.pass = 0;
-    SDRD_LAUNCH(fec::decode_kernel<32>, n_frames, 1, fec::NT, fec::dec_smem_bytes<32>(), st, p);
+    p.n_frames = n_frames;
+    SDRD_LAUNCH(fec::decode_stream_kernel, dec_grid(n_frames), 1, fec::DS_NT, fec::ds_smem_bytes(), st, p);
     /* frames with more than 32 recovery blocks (flagged by the first pass) take the large-matrix build */
     p.pass = 1;
     SDRD_LAUNCH(fec::decode_kernel<128>, n_frames, 1, fec::NT, fec::dec_smem_bytes<128>(), st, p);
@@ -1860,7 +1871,8 @@ extern "C" int sdrd_cm256_decode_blocks(sdrd_cm256_params p, sdrd_cm256_block* b
     kp.recovered = reinterpret_cast<uint32_t*>(g_scr_b.p);
     kp.general_single = p.RecoveryCount != 1;
     kp.pass = 0;
-    SDRD_LAUNCH(fec::decode_kernel<32>, 1, 1, fec::NT, fec::dec_smem_bytes<32>(), 0, kp);
+    kp.n_frames = 1;
+    SDRD_LAUNCH(fec::decode_stream_kernel, 1, 1, fec::DS_NT, fec::ds_smem_bytes(), 0, kp);
     if (n_rec > 32) {
         kp.pass = 1;
         SDRD_LAUNCH(fec::decode_kernel<128>, 1, 1, fec::NT, fec::dec_smem_bytes<128>(), 0, kp);
@@ -2044,7 +2056,8 @@ extern "C" int sdrd_src_feed(sdrd_src* k, const uint8_t* dg, size_t n, uint8_t* 
         p.block0 = reinterpret_cast<uint32_t*>(k->d_block0);
         p.status = k->d_status;
         p.pass = 0;
-        SDRD_LAUNCH(fec::decode_kernel<32>, (int)nf, 1, fec::NT, fec::dec_smem_bytes<32>(), st, p);
+        p.n_frames = (int)nf;
+        SDRD_LAUNCH(fec::decode_stream_kernel, dec_grid((long long)nf), 1, fec::DS_NT, fec::ds_smem_bytes(), st, p);
         p.pass = 1;
         SDRD_LAUNCH(fec::decode_kernel<128>, (int)nf, 1, fec::NT, fec::dec_smem_bytes<128>(), st, p);
         k->launches += 2;
