@@ -3,12 +3,15 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (BASELINE.json configs[1]): TestSource-shaped 10 Msps int16 I/Q, decimate-by-16 (4 half-band
-stages, centred), 128 data + 16 FEC blocks per superframe, one stream per GPU.  A step is one pass of
-the hot path over one batch of FRAMES superframes (FRAMES * 258064 input samples, ~611 MB: larger than
-the 126 MB L2, so no flush is needed between steps).  Under torchrun every rank runs the same
-per-GPU workload on its own stream (weak scaling, no data-path collective; NCCL only for the barrier
-and the digest gather).
+Workload at N = 1 (BASELINE.json configs[1]): TestSource-shaped 10 Msps int16 I/Q, decimate-by-16 (4 half-band
+stages, centred), 128 data + 16 FEC blocks per superframe, one stream.  A step is one pass of the hot path over
+one batch of FRAMES superframes (FRAMES * 258064 input samples, ~611 MB: larger than the 126 MB L2, so no flush
+is needed between steps).
+Workload at N > 1 (BASELINE.json configs[4], the configuration its scaling claim is stated on): 2048 streams
+@ 61.44 Msps, decimate-by-64, 128 + 32 FEC, 2 superframes per stream per step, the streams sharded in contiguous
+ranges over the N ranks -- STRONG scaling, no data-path collective; NCCL carries the barrier, the digest gather
+and, in the drop-in figure, the scatter of the streams from rank 0 (overlapped with the shards' processing).
+`--config 2|3|5` selects a workload explicitly (3 / 5 at N = 1: one GPU's shard of 256 streams).
 
 One JSON line on rank 0:
   value        input Msamples/s, whole job, inputs resident in HBM, CUDA events, max over ranks
@@ -194,7 +197,8 @@ def run_reference(args):
     base["value"] = round(v, 3)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(1e3 * statistics.mean(times), 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(1e3 * statistics.mean(times), 3), "higher_is_better": True,
+        "scaling": "strong" if getattr(args, "strong", False) else "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config]["name"] + " (reference CPU path, bounded sample per step)",
                    "log2_decim": M_LOG2, "n_fec": N_FEC},
@@ -411,6 +415,36 @@ def run_interp(args):
                                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}}), flush=True)
 
 
+def bind_near_gpu(local: int):
+    """Run this rank (and first-touch its page-locked buffers) on the CPUs next to its GPU: the CPUs the PCI device
+    reports as local, when the container shows them.  Returns what was done, for the JSON line."""
+    try:
+        import torch
+
+        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)], capture_output=True, text=True).stdout.strip()
+            bdf = out[4:] if out.startswith("0000") and len(out) > 12 else out
+        bdf = str(bdf).lower()
+        if len(bdf.split(":")) == 2:
+            bdf = "0000:" + bdf
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = open(base + "/numa_node").read().strip()
+        cpus = open(base + "/local_cpulist").read().strip()
+        want = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            want.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = sorted(want & allowed)
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            return {"numa_node": node, "cpus": cpus, "bound": True}
+        return {"numa_node": node, "cpus": cpus, "bound": False, "why": "the local CPUs are all the rank is allowed anyway" if use else "no local CPU in the allowed set"}
+    except Exception as e:
+        return {"bound": False, "why": f"{type(e).__name__}"}
+
+
 def small_block_leg(lib, capi, n_blocks=4000, blk=65536):
     """The reference's call granularity: ONE stream fed in TestSource-sized blocks of 65536 samples
     (include/TestSource.h:33) from pageable host memory, the way sdrdaemonrx's main loop feeds Downsampler::process +
@@ -515,14 +549,20 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5, 6],
-                    help="BASELINE.json config (2 = headline); 6 = the Tx interpolation cascade (SURVEY 8f-1)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5, 6],
+                    help="BASELINE.json config (default: 2, the headline, on one GPU; 5 as stated -- 2048 streams over all "
+                         "GPUs -- under torchrun); 6 = the Tx interpolation cascade (SURVEY 8f-1)")
     ap.add_argument("--frames", type=int, default=0, help="superframes per stream per step (default: per config)")
     ap.add_argument("--log2-decim", type=int, default=0, help="experiments: override the workload's log2 decimation")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    strong = False
+    if args.config == 0:
+        args.config = 2 if world_env == 1 else 5
+        strong = world_env > 1
     if args.config == 4:
         return run_decode(args)
     if args.config == 6:
@@ -530,8 +570,14 @@ def main():
     if args.log2_decim:
         WORKLOADS[args.config] = dict(WORKLOADS[args.config], M=args.log2_decim,
                                       name=WORKLOADS[args.config]["name"] + f" [log2_decim overridden to {args.log2_decim}]")
+    if strong:
+        if 2048 % world_env:
+            raise SystemExit("config 5 shards 2048 streams: the number of GPUs has to divide it")
+        WORKLOADS[5] = dict(WORKLOADS[5], S=2048 // world_env,
+                            name=f"config5: 2048 streams @ 61.44 Msps, decimate-by-64, 128+32 FEC, sharded {2048 // world_env} per GPU")
     work = select_workload(args.config, args.frames or None)
     args.frames = work["frames"]
+    args.strong = strong
     if args.impl == "reference":
         return run_reference(args)
 
@@ -550,6 +596,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = capi.load()
     lib.check(lib.sdrd_set_device(local))
+    numa = bind_near_gpu(local) if world > 1 else None
 
     S = N_STREAMS
     n_in = args.frames * FRAME_IN
@@ -640,7 +687,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_in = torch.empty((S, n_in, 2), dtype=torch.int16).pin_memory()
-        host_in.copy_(dev_in.reshape(S, n_in, 2).cpu())
+        for s0 in range(S):  # per stream: no second host copy of the whole shard
+            host_in[s0].copy_(dev_in[s0].reshape(n_in, 2))
+        torch.cuda.synchronize()
         bpf = 128 + N_FEC
         host_out = torch.empty((S, args.frames + 1, bpf, 512), dtype=torch.uint8).pin_memory()
         nfr = C.c_size_t(0)
@@ -665,6 +714,32 @@ def main():
         e2e = {"value": round(world * S * n_in * args.e2e_steps / dt / 1e6, 1), "unit": UNIT,
                "h2d_bytes_per_step": S * n_in * 4, "d2h_bytes_per_step": S * int(nfr.value) * bpf * 512,
                "steps": args.e2e_steps, "api": "sdrd_rx_process (host pointers, pinned)"}
+        # the ceiling of any end-to-end figure: a bare host -> device copy of the same page-locked bytes, every rank at
+        # once (one PCIe link per GPU, one host memory system for all of them)
+        flat_h = host_in.view(torch.uint8).reshape(-1)
+        flat_d = dev_all.view(torch.uint8)[: flat_h.numel()] if S == 1 else torch.empty(flat_h.numel(), dtype=torch.uint8, device="cuda")
+        cs = torch.cuda.Stream()
+        with torch.cuda.stream(cs):
+            flat_d.copy_(flat_h, non_blocking=True)
+            cs.synchronize()
+            if world > 1:
+                dist.barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(cs)
+            for _ in range(3):
+                flat_d.copy_(flat_h, non_blocking=True)
+            c1.record(cs)
+            cs.synchronize()
+        tc = torch.tensor([c0.elapsed_time(c1) / 3], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        ceil_v = world * S * n_in / (float(tc[0]) * 1e-3) / 1e6
+        e2e["host_link_ceiling"] = {"value": round(ceil_v, 1), "unit": UNIT, "GB_per_s_all_gpus": round(world * flat_h.numel() / float(tc[0]) / 1e6, 1),
+                                    "what": "bare cudaMemcpyAsync of the same page-locked input bytes, all ranks at once"}
+        e2e["frac_of_host_link_ceiling"] = round(e2e["value"] / ceil_v, 3)
+        if numa is not None:
+            e2e["numa"] = numa
+        del flat_d
         if world == 1 and args.config == 2:
             e2e["small_block"] = small_block_leg(lib, capi)
 
@@ -685,8 +760,14 @@ def main():
     # NVLink (one NCCL group of sends); reported next to the headline, not part of `value` (there each rank
     # generates its own streams on the device)
     scatter = None
+    dropin = None
     if world > 1:
         x_all = torch.zeros((world * S if rank == 0 else 0, n_in * 2), dtype=torch.int16, device="cuda")
+        if rank == 0:  # distinct streams: the first ones are this rank's own (already in its input buffer)
+            gg = torch.Generator(device="cuda")
+            gg.manual_seed(0x5D12DAE0)
+            for s0 in range(world * S):
+                x_all[s0].copy_(torch.randint(-32768, 32768, (n_in * 2,), dtype=torch.int16, device="cuda", generator=gg))
         multi.scatter_streams(x_all, world * S, world, rank)  # warm-up: NCCL P2P channels
         sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
@@ -700,8 +781,59 @@ def main():
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         sc_bytes = (world - 1) * S * n_in * 4
         scatter = {"ms": round(float(ts[0]), 3), "bytes_from_rank0": sc_bytes, "GB_per_s": round(sc_bytes / float(ts[0]) / 1e6, 1),
-                   "api": "sdrdaemon_b200.multi.scatter_streams (NCCL send/recv, device buffers)"}
-        del x_all, mine
+                   "api": "sdrdaemon_b200.multi.scatter_streams (NCCL send/recv, device buffers), alone"}
+        del mine
+        # ---- drop-in mode, the scatter INSIDE the timed region and overlapped with the work: rank 0 holds every
+        # stream and sends each rank's range in K pieces (piece 0 to everybody, then piece 1, ...); a rank decimates /
+        # frames / encodes piece k while piece k + 1 is on the wire.  One Rx handle per piece (S / K streams each).
+        K = 4 if S % 4 == 0 and S >= 4 else 1
+        rx.close()
+        Sk = S // K
+        rxk = [capi.Rx(M_LOG2, n_streams=Sk, max_in=n_in, n_fec=N_FEC, sample_rate=out_rate) for _ in range(K)]
+        views = []
+        for h in rxk:
+            ip, istr = h.dev_input()
+            va = torch.as_tensor(DevView(ip, ((Sk - 1) * istr + n_in) * 4), device="cuda").view(torch.int16)
+            views.append(torch.as_strided(va, (Sk, n_in * 2), (istr * 2, 1)))
+        cur = torch.cuda.current_stream()
+
+        def dropin_step():
+            pieces = multi.scatter_streams_sliced(x_all, world * S, world, rank, K)
+            for k, (works, t) in enumerate(pieces):
+                if rank != 0:
+                    for w in works:
+                        w.wait()  # this stream waits for piece k only
+                views[k].copy_(t, non_blocking=True)
+                rxk[k].process_dev(n_in, cur.cuda_stream)
+            if rank == 0:
+                for works, _ in pieces:
+                    for w in works:
+                        w.wait()
+
+        dropin_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        da, db = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        da.record()
+        n_it = 3
+        for _ in range(n_it):
+            dropin_step()
+        db.record()
+        torch.cuda.synchronize()
+        td = torch.tensor([da.elapsed_time(db) / n_it], device="cuda", dtype=torch.float64)
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        td = float(td[0])
+        dev_ms = ms / args.steps
+        dropin = {"value": round(world * S * n_in / (td * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(td, 3), "pieces": K,
+                  "scatter_bytes_from_rank0": sc_bytes, "scatter_GB_per_s_inside": round(sc_bytes / td / 1e6, 1),
+                  "device_resident_ms_per_step": round(dev_ms, 3), "scatter_alone_ms": scatter["ms"],
+                  "limiter": ("the scatter: rank 0 sends (N-1)/N of all samples over its own NVLink ports (900 GB/s per direction nominal), "
+                              "the shards' work hides behind it" if scatter["ms"] > dev_ms else "the shards' work: the scatter hides behind it"),
+                  "what": "rank 0 holds all streams in HBM; NCCL send/recv of every other rank's range in pieces, each rank works on "
+                          "piece k while piece k+1 arrives; timed with the scatter inside, max over ranks"}
+        for h in rxk:
+            h.close()
+        del x_all, views
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -721,10 +853,11 @@ def main():
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {
                 "workload": f"{work['name']}, {args.frames} superframes per stream "
-                            f"({S * n_in} samples, {S * n_in * 4 / 1e6:.0f} MB) per step per GPU",
+                            f"({S * n_in} samples, {S * n_in * 4 / 1e6:.0f} MB) per step per GPU"
+                            + (f"; {world * S} streams in all, the total fixed as GPUs are added" if args.strong else ""),
                 "log2_decim": M_LOG2, "n_fec": N_FEC, "streams_per_gpu": S, "frames_per_step": args.frames,
                 "l2": "inputs larger than L2 (no flush needed)", "parity": parity,
             },
@@ -735,6 +868,7 @@ def main():
             "stream_digests_fold": (hex(int(np.bitwise_xor.reduce(digests))) if digests is not None else None),
             "n_stream_digests": (int(len(digests)) if digests is not None else None),
             "scatter": scatter,
+            "dropin": dropin,
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": f"hb::decimate_warp_kernel<{M_LOG2}> (K1)", "achieved": round(achieved, 1), "peak": peak,

@@ -80,6 +80,44 @@ def scatter_streams(x_all, n_streams: int, world: int, rank: int, src: int = 0):
     return mine
 
 
+def slice_range(count: int, n_slices: int, k: int) -> Tuple[int, int]:
+    """(first, number) of slice k when `count` streams are cut into n_slices contiguous pieces"""
+    base, extra = divmod(count, n_slices)
+    first = k * base + min(k, extra)
+    return first, base + (1 if k < extra else 0)
+
+
+def scatter_streams_sliced(x_all, n_streams: int, world: int, rank: int, n_slices: int, src: int = 0):
+    """The scatter of scatter_streams cut into n_slices pieces per rank so that a receiver can work on piece k while
+    piece k + 1 is still on the wire: rank `src` sends piece 0 of every rank's range, then piece 1, ... (one group
+    of point-to-point operations per piece, executed in order).  Returns a list of n_slices (work, tensor) pairs:
+    `work.wait()` (None for data that is already local) makes the current stream wait for that piece; the tensor
+    holds this rank's streams of the piece."""
+    import torch
+    import torch.distributed as dist
+
+    first, count = stream_range(n_streams, world, rank)
+    out = []
+    if rank == src:
+        for k in range(n_slices):
+            ops = []
+            for r in range(world):
+                a, c = stream_range(n_streams, world, r)
+                f, n = slice_range(c, n_slices, k)
+                if r != src and n:
+                    ops.append(dist.P2POp(dist.isend, _wire(x_all[a + f:a + f + n]), r))
+            works = dist.batch_isend_irecv(ops) if ops else []
+            f, n = slice_range(count, n_slices, k)
+            out.append((works, x_all[first + f:first + f + n]))
+        return out
+    for k in range(n_slices):
+        f, n = slice_range(count, n_slices, k)
+        piece = torch.empty((n,) + tuple(x_all.shape[1:]), dtype=x_all.dtype, device=x_all.device)
+        works = dist.batch_isend_irecv([dist.P2POp(dist.irecv, _wire(piece), src)]) if n else []
+        out.append((works, piece))
+    return out
+
+
 def gather_datagrams(dg_local, n_streams: int, world: int, rank: int, dst: int = 0):
     """The reverse exchange: every rank's datagram images (count, frames, blocks, 512) to rank `dst`, which
     returns the (n_streams, frames, blocks, 512) tensor in stream order (the other ranks return None)."""

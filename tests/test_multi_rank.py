@@ -36,6 +36,14 @@ def _worker(rank, world, port, q):
     first, count = multi.stream_range(S, world, rank)
     assert x.shape == (count, N_IN, 2) and np.array_equal(x, _inputs()[first:first + count])
     dg = multi.rx_sharded(x, M, F, lib=lib)
+    # the sliced scatter (pieces processed while later ones are on the wire) delivers the same streams, piece by piece
+    pieces = multi.scatter_streams_sliced(x_all, S, world, rank, 2)
+    got = []
+    for works, t in pieces:
+        for w in works:
+            w.wait()
+        got.append(t.numpy())
+    assert np.array_equal(np.concatenate(got), x)
     dig = multi.gather_digests(multi.datagram_digest(dg), S, world, rank)
     all_dg = multi.gather_datagrams(torch.from_numpy(dg), S, world, rank)
     if rank == 0:
