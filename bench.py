@@ -159,10 +159,13 @@ def cpu_pass(x, frames: int, cores: int):
     dt = time.perf_counter() - t0
     assert fr == cores * frames, (fr, cores, frames)
     msps = x.shape[0] * x.shape[1] / dt / 1e6
+    fec = ("restated CM256 with the SSSE3 byte-shuffle block multiply (what cm256cc runs on x86)" if ob.simd() else
+           "restated CM256, scalar 256-entry tables (no SSSE3 on this host)")
     sample = (f"{cores} streams x {frames} superframes ({cores * frames * FRAME_IN} samples) of the workload, one stream per "
-              f"thread, 65536-sample blocks; decimator = reference Decimators.cpp (EO1/SSE4.1 build), FEC = restated "
-              f"CM256 scalar tables" if kind == "reference" else
-              f"{cores} streams x {frames} superframes of the workload; C restatement (oracle port)")
+              f"thread, 65536-sample blocks; decimator = reference Decimators.cpp (EO1/SSE4.1 build), FEC = {fec}; the GPU arm "
+              f"runs ONE stream of {WORKLOADS[2]['frames']} superframes where the workload is config 2: a single stream cannot use "
+              f"more than one host core, so the CPU arm is given one stream per core" if kind == "reference" else
+              f"{cores} streams x {frames} superframes of the workload; C restatement (oracle port), FEC = {fec}")
     return {"value": round(msps, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, dt
 
 
@@ -208,6 +211,27 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def decode_cpu_leg(sb, seconds):
+    """config 4 on the host, all cores: the reference's own SDRdaemonFECBuffer (oracle/_ref) when its build is present,
+    else the oracle port; bounded to about `seconds`."""
+    from oracle import bindings as ob
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    kind = "reference" if ob.ref_available(0) else "port"
+    run = (lambda a: ob.ref_decode_frames(a, 128, cores)) if kind == "reference" else (lambda a: ob.decode_frames(a, 128, cores))
+    run(sb[: min(len(sb), 4 * cores)])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        run(sb)
+        n += len(sb)
+    dt = time.perf_counter() - t0
+    fec = "SSSE3 byte-shuffle block multiply" if ob.simd() else "scalar tables"
+    return {"value": round(n / dt / 1e6, 6), "unit": "Msuperframes/s", "cores": cores, "kind": kind,
+            "sample": f"{n} superframes ({len(sb)} distinct) of the workload on {cores} threads: " +
+                      ("SDRdaemonFECBuffer.cpp of the reference (oracle/_ref)" if kind == "reference" else "SDRdaemonFECBuffer logic of the oracle") +
+                      f" + restated CM256 ({fec})"}
+
+
 def run_decode(args):
     """BASELINE config 4: 4096 superframes, 20 of 128 blocks erased (F = 32), recover on the GPU."""
     import ctypes as C
@@ -230,16 +254,13 @@ def run_decode(args):
             keep = np.ones(128, bool)
             keep[rng.permutation(128)[:20]] = False
             sbs.append(np.concatenate([frames[f, :128][keep], frames[f, 128:148]]))
-        t0 = time.perf_counter()
-        for sb in sbs:
-            ob.decode_frame(sb)
-        dt = time.perf_counter() - t0
-        v = nf / dt / 1e6
-        print(json.dumps({"impl": "reference", "metric": "Msuperframes/s recovered (20/128 erasures)", "value": round(v, 6),
+        base = decode_cpu_leg(np.stack(sbs), 10.0)
+        v = base["value"]
+        print(json.dumps({"impl": "reference", "metric": "Msuperframes/s recovered (20/128 erasures)", "value": v,
                           "unit": "Msuperframes/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "higher_is_better": True,
-                          "config": {"workload": "config4 (reference-shaped CPU decode, 1 thread, 64 frames)"},
-                          "cpu_baseline": {"value": round(v, 6), "unit": "Msuperframes/s", "cores": 1, "kind": "port",
-                                           "sample": "64 superframes, SDRdaemonFECBuffer logic + restated CM256"}}), flush=True)
+                          "config": {"workload": "config4: superframes with 20/128 random erasures, F=32 (CPU decode, bounded sample)"},
+                          "cpu_baseline": base,
+                          "e2e": {"value": v, "unit": "Msuperframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
     lib = capi.load()
     torch.cuda.set_device(0)
@@ -270,20 +291,23 @@ def run_decode(args):
     stream.synchronize()
     ok = bool((d_st == 2).all()) and bool((d_pay.cpu().numpy() == frames[:, 1:128, 4:]).all())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = min(args.steps, 200)
+    steps = min(args.steps, 1000)
+    sampler = ClockSampler(0)
+    sampler.start()
     e0.record(stream)
     for _ in range(steps):
         step()
     e1.record(stream)
     stream.synchronize()
+    clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / steps
     peak, peak_src = measured_peaks()
     alg = nf * (128 * 512 + 127 * 508)
-    k3_traffic = None
+    k3_traffic, k3_traffic_src = None, None
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json")))
         if t.get("frames_per_launch") == nf:
-            k3_traffic = t.get("dram_bytes_per_launch")
+            k3_traffic, k3_traffic_src = t.get("dram_bytes_per_launch"), t.get("source")
     except Exception:
         k3_traffic = None
     # end to end through the host-pointer C ABI (what UDPSourceFEC would call): pinned host buffers, H2D of the
@@ -312,24 +336,16 @@ def run_decode(args):
                "api": "sdrd_fec_decode (host pointers, pinned)", "parity": "ok" if e2e_ok else "MISMATCH"}
     cpu = None
     if not args.no_cpu:
-        from oracle import bindings as ob
-
-        t0 = time.perf_counter()
-        n_cpu = 0
-        while time.perf_counter() - t0 < 5.0:
-            ob.decode_frame(sb[n_cpu % nf])
-            n_cpu += 1
-        cpu = {"value": round(n_cpu / (time.perf_counter() - t0) / 1e6, 6), "unit": "Msuperframes/s", "cores": 1, "kind": "port",
-               "sample": f"{n_cpu} superframes of the workload, SDRdaemonFECBuffer logic + restated CM256 (oracle), one thread"}
+        cpu = decode_cpu_leg(sb[:512], 10.0)
     print(json.dumps({"metric": "Msuperframes/s recovered (20/128 erasures)", "value": round(nf / ms / 1e3, 3),
                       "unit": "Msuperframes/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
                       "higher_is_better": True, "dtype": "u8 (GF(2^8))", "data": "synthetic",
                       "config": {"workload": "config4: 4096 superframes, 20/128 random erasures, F=32, bit-exact recover",
                                  "parity": "all frames recovered == transmitted" if ok else "MISMATCH"},
-                      "gpu_launches": 2 * steps, "e2e": e2e, "cpu_baseline": cpu,
-                      "roofline": {"bound": "hbm", "kernel": "fec::decode_kernel<32> (K3)", "achieved": round(alg / ms / 1e6, 1),
+                      "gpu_launches": 2 * steps, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+                      "roofline": {"bound": "hbm", "kernel": "fec::decode_stream_kernel (K3)", "achieved": round(alg / ms / 1e6, 1),
                                    "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": k3_traffic,
-                                   "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                                   "traffic_source": k3_traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                                    "note": "K3 is ALU-pipe bound (PRMT/LOP3 table arithmetic), see DESIGN.md"}}), flush=True)
 
 
@@ -392,15 +408,50 @@ def run_interp(args):
     for _ in range(max(args.warmup, 3)):
         u.process_dev(n_in, stream.cuda_stream)
     stream.synchronize()
-    steps = min(args.steps, 300)
+    steps = min(args.steps, 1000)
     l0 = u.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    sampler.start()
     e0.record(stream)
     for _ in range(steps):
         u.process_dev(n_in, stream.cuda_stream)
     e1.record(stream)
     stream.synchronize()
+    clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / steps
+    # end to end through Upsampler's host entry point (page-locked buffers, H2D + kernel + D2H per step) and the
+    # reference's own Upsampler on one host core (the cascade is sequential per stream)
+    e2e, cpu = None, None
+    if not args.no_e2e:
+        n_e = 64 * FRAME_SAMPLES  # a bounded piece of the stream: the output is 2^M times larger
+        hi = torch.empty((n_e, 2), dtype=torch.int16).pin_memory()
+        hi.copy_(dev_in[: 2 * n_e].reshape(n_e, 2))
+        ho = torch.empty((n_e << M, 2), dtype=torch.int16).pin_memory()
+        ue = capi.Interpolator(M, 1, max_in=n_e)
+        no = C.c_size_t(0)
+        for warm in (True, False):
+            t0 = time.perf_counter()
+            for _ in range(2 if warm else args.e2e_steps):
+                lib.check(lib.sdrd_int_process(ue._h, hi.data_ptr(), n_e, n_e, ho.data_ptr(), n_e << M, C.byref(no)))
+            dt = (time.perf_counter() - t0) / (2 if warm else args.e2e_steps)
+        e2e = {"value": round((n_e << M) / dt / 1e6, 1), "unit": UNIT, "h2d_bytes_per_step": n_e * 4, "d2h_bytes_per_step": (n_e << M) * 4,
+               "steps": args.e2e_steps, "api": "sdrd_int_process (host pointers, pinned)"}
+        ue.close()
+    if not args.no_cpu:
+        try:
+            from oracle import bindings as ob
+
+            xs = dev_in[: 2 * 16 * FRAME_SAMPLES].cpu().numpy().reshape(-1, 2)
+            kind = "reference" if ob.ref_available(0) else "port"
+            uu = ob.RefUpsampler(M, 0) if kind == "reference" else ob.Interpolator(M)
+            t0 = time.perf_counter()
+            yy = uu.process(xs)
+            dtc = time.perf_counter() - t0
+            cpu = {"value": round(len(yy) / dtc / 1e6, 3), "unit": UNIT, "cores": 1, "kind": kind,
+                   "sample": f"{len(xs)} input samples through one Upsampler ({'reference Interpolators.cpp' if kind == 'reference' else 'oracle port'}), one thread"}
+        except Exception:
+            cpu = None
     n_out = n_in << M
     peak, peak_src = measured_peaks()
     alg = 4 * n_in + 4 * n_out
@@ -409,7 +460,7 @@ def run_interp(args):
                       "config": {"workload": f"tx (SURVEY 8f-1): {nfr} superframes ({n_in} samples) interpolated by {1 << M}, "
                                              f"{n_out * 4 / 1e6:.0f} MB out per step", "parity": parity,
                                  "l2": "outputs larger than L2 (no flush needed)"},
-                      "gpu_launches": int(u.launches - l0),
+                      "gpu_launches": int(u.launches - l0), "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
                       "roofline": {"bound": "hbm", "kernel": f"hbi::interpolate_warp_kernel<{min(M, 5)}> (K4)", "achieved": round(alg / ms / 1e6, 1),
                                    "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": None,
                                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}}), flush=True)
@@ -840,14 +891,14 @@ def main():
         k1_bytes = S * n_in * k1_bytes_per_sample(M_LOG2)
         achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
         step_bytes = S * n_in * algorithmic_bytes_per_sample(M_LOG2, N_FEC)
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tp):
             try:
                 t = json.load(open(tp))
                 # the capture is of one launch of a given shape: only quote it for that shape
                 if t.get("log2_decim", 4) == M_LOG2 and t.get("samples_per_launch", 592 * 16129 * 16) == S * n_in:
-                    traffic = t.get("dram_bytes_per_launch")
+                    traffic, traffic_src = t.get("dram_bytes_per_launch"), t.get("source")
             except Exception:
                 traffic = None
         line = {
@@ -872,7 +923,7 @@ def main():
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": f"hb::decimate_warp_kernel<{M_LOG2}> (K1)", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "k1_ms_per_launch": round(k1_ms, 4), "algorithmic_bytes_per_launch": int(k1_bytes),
                 "whole_step": {"algorithmic_bytes": int(step_bytes), "achieved": round(step_bytes / (ms / args.steps * 1e-3) / 1e9, 1),
                                "frac": round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak, 4)},

@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
         L.sdro_cm256_encode.argtypes = [_Params, C.POINTER(_Block), C.c_void_p]
         L.sdro_cm256_decode.restype = C.c_int
         L.sdro_cm256_decode.argtypes = [_Params, C.POINTER(_Block)]
+        L.sdro_set_simd.argtypes = [C.c_int]
+        L.sdro_simd.restype = C.c_int
         L.sdro_crc32.restype = C.c_uint32
         L.sdro_crc32.argtypes = [C.c_void_p, C.c_size_t]
         L.sdro_sink_create.restype = C.c_void_p
@@ -486,3 +488,26 @@ def decode_frames(superblocks: np.ndarray, n_blocks, n_threads: int = 1):
     L.sdro_decode_frames.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sdro_decode_frames(sb.ctypes.data, pitch, nb.ctypes.data, nf, n_threads, pay.ctypes.data, b0.ctypes.data, st.ctypes.data)
     return pay, b0, st
+
+
+def set_simd(on: bool) -> None:
+    """force the scalar (False) or allow the SSSE3 (True) block multiply of the restated CM256"""
+    lib().sdro_set_simd(1 if on else 0)
+
+
+def simd() -> bool:
+    return bool(lib().sdro_simd())
+
+
+def ref_decode_frames(superblocks: np.ndarray, n_blocks, n_threads: int = 1) -> np.ndarray:
+    """(n_frames, pitch, 512) received datagrams through the REFERENCE's SDRdaemonFECBuffer (oracle/_ref, restated
+    CM256 inside), n_threads buffers in parallel -> payload (n_frames, 127, 508)."""
+    sb = np.ascontiguousarray(superblocks, dtype=np.uint8)
+    nf, pitch, _ = sb.shape
+    nb = np.ascontiguousarray(np.broadcast_to(np.asarray(n_blocks, dtype=np.int32), (nf,)))
+    pay = np.zeros((nf, 127, BLOCK_BYTES), np.uint8)
+    L = ref(HB_EO1)
+    L.ref_fecbuf_decode_frames.restype = None
+    L.ref_fecbuf_decode_frames.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ref_fecbuf_decode_frames(sb.ctypes.data, pitch, nb.ctypes.data, nf, n_threads, pay.ctypes.data)
+    return pay

@@ -227,6 +227,42 @@ void ref_fecbuf_current_meta(void* h, uint8_t meta20[20])
     memcpy(meta20, &((SDRdaemonFECBuffer*)h)->getCurrentMeta(), 20);
 }
 
+/* BASELINE config 4 on the CPU, all cores: every frame's received datagrams go through the reference's own
+ * SDRdaemonFECBuffer::writeAndRead (store, cm256_decode, copy-back; sdmnbase/SDRdaemonFECBuffer.cpp:112-250), one
+ * buffer object per thread; a datagram of another frame index flushes the frame out (:133-139).
+ * payload: n_frames x 127 x 508 bytes.  The reference logs every decode to std::cerr: silenced for the call. */
+void ref_fecbuf_decode_frames(const uint8_t* sb, size_t pitch, const int* n_blocks, int n_frames, int n_threads, uint8_t* payload)
+{
+    std::ostringstream quiet;
+    std::streambuf* old = std::cerr.rdbuf(quiet.rdbuf());
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        SDRdaemonFECBuffer* buf = new SDRdaemonFECBuffer();
+        std::vector<uint8_t> data(128 * 512);
+        uint8_t dg[SDRDAEMONFEC_UDPSIZE];
+        for (;;) {
+            const int f = next.fetch_add(1);
+            if (f >= n_frames) break;
+            std::size_t len = 0;
+            for (int i = 0; i < n_blocks[f]; i++) {
+                memcpy(dg, sb + ((size_t)f * pitch + i) * 512, 512);
+                dg[0] = (uint8_t)(f & 0xFF); /* distinct frame indices per frame of the batch */
+                dg[1] = (uint8_t)((f >> 8) & 0x7F);
+                buf->writeAndRead(dg, data.data(), len);
+            }
+            memset(dg, 0, 512);
+            dg[0] = (uint8_t)((f + 1) & 0xFF);
+            dg[1] = (uint8_t)((((f + 1) >> 8) & 0x7F) | 0x80); /* never equal to a frame's own index */
+            if (buf->writeAndRead(dg, data.data(), len)) memcpy(payload + (size_t)f * 127 * 508, data.data(), 127 * 508);
+        }
+        delete buf;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < (n_threads < 1 ? 1 : n_threads); t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+    std::cerr.rdbuf(old);
+}
+
 /* ------------------------------------------------------------------ UDPSinkFEC ----- */
 
 /* Drives the reference sender over 127.0.0.1:port and captures the datagrams it emits.

@@ -232,10 +232,62 @@ uint8_t sdro_cm256_matrix_element(uint8_t x_i, uint8_t x_0, uint8_t y_j)
     return sdro_gf_div((uint8_t)(y_j ^ x_0), (uint8_t)(x_i ^ y_j));
 }
 
+/* cm256cc / gf256 multiply blocks with the SSSE3 byte shuffle, 16 bytes per instruction: two 16-entry tables per
+ * multiplier (its products with the low and with the high nibble), z ^= lo[x & 15] ^ hi[x >> 4].  Same arithmetic as
+ * the scalar table below -- used when the CPU has SSSE3 (as the library does), so that the CPU arm of bench.py is not
+ * slower than the real thing; sdro_set_simd(0) forces the scalar path (tests compare the two). */
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define SDRO_HAVE_SSSE3_PATH 1
+static int g_simd = -1; /* -1: not probed yet */
+__attribute__((target("ssse3"))) static void gf_muladd_mem_ssse3(uint8_t* z, uint8_t c, const uint8_t* x, int n)
+{
+    uint8_t lo[16], hi[16];
+    const unsigned lc = GF_LOG[c];
+    lo[0] = hi[0] = 0;
+    for (int v = 1; v < 16; v++) {
+        lo[v] = GF_EXP[GF_LOG[v] + lc];
+        hi[v] = GF_EXP[GF_LOG[v << 4] + lc];
+    }
+    const __m128i tlo = _mm_loadu_si128((const __m128i*)lo), thi = _mm_loadu_si128((const __m128i*)hi);
+    const __m128i mask = _mm_set1_epi8(0x0F);
+    int i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m128i v = _mm_loadu_si128((const __m128i*)(x + i));
+        const __m128i l = _mm_shuffle_epi8(tlo, _mm_and_si128(v, mask));
+        const __m128i h = _mm_shuffle_epi8(thi, _mm_and_si128(_mm_srli_epi64(v, 4), mask));
+        __m128i o = _mm_loadu_si128((const __m128i*)(z + i));
+        o = _mm_xor_si128(o, _mm_xor_si128(l, h));
+        _mm_storeu_si128((__m128i*)(z + i), o);
+    }
+    for (; i < n; i++) z[i] ^= (uint8_t)(lo[x[i] & 15] ^ hi[x[i] >> 4]);
+}
+#endif
+void sdro_set_simd(int on)
+{
+#ifdef SDRO_HAVE_SSSE3_PATH
+    g_simd = on && __builtin_cpu_supports("ssse3") ? 1 : 0;
+#else
+    (void)on;
+#endif
+}
+int sdro_simd(void)
+{
+#ifdef SDRO_HAVE_SSSE3_PATH
+    if (g_simd < 0) g_simd = __builtin_cpu_supports("ssse3") ? 1 : 0;
+    return g_simd;
+#else
+    return 0;
+#endif
+}
+
 static void gf_muladd_mem(uint8_t* z, uint8_t c, const uint8_t* x, int n)
 {
     if (c == 0) return;
     if (c == 1) { for (int i = 0; i < n; i++) z[i] ^= x[i]; return; }
+#ifdef SDRO_HAVE_SSSE3_PATH
+    if (sdro_simd()) { gf_muladd_mem_ssse3(z, c, x, n); return; }
+#endif
     uint8_t t[256];
     t[0] = 0;
     unsigned lc = GF_LOG[c];

@@ -74,6 +74,10 @@ uint8_t sdro_gf_div(uint8_t a, uint8_t b);
 uint8_t sdro_gf_exp(int i);              /* 2^i */
 uint8_t sdro_gf_log(uint8_t a);          /* a != 0 */
 uint8_t sdro_cm256_matrix_element(uint8_t x_i, uint8_t x_0, uint8_t y_j);
+/* block multiply-add: SSSE3 byte shuffle (16 bytes per instruction, what cm256cc uses on x86) when the CPU has it,
+ * else the scalar 256-entry table; sdro_set_simd(0) forces the scalar path, sdro_simd() tells which is active */
+void sdro_set_simd(int on);
+int sdro_simd(void);
 
 typedef struct {
     void*   Block;

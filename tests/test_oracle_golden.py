@@ -96,6 +96,25 @@ def test_cm256_mds_and_linearity(oracle):
             assert np.array_equal(out[128 - ne + k], o[er[k]])
 
 
+def test_cm256_ssse3_equals_scalar(oracle):
+    """the pshufb block multiply (what cm256cc uses on x86, and what bench.py's CPU arm runs) == the scalar table"""
+    rng = np.random.default_rng(12)
+    o = rng.integers(0, 256, size=(128, 508), dtype=np.uint8)
+    try:
+        oracle.set_simd(False)
+        a = oracle.cm256_encode(o, 40)
+        er = sorted(rng.choice(128, 20, replace=False).tolist())
+        blocks = np.concatenate([np.delete(o, er, axis=0), a[:20]])
+        idx = [i for i in range(128) if i not in er] + list(range(128, 148))
+        da = oracle.cm256_decode(blocks, idx, 128, 20)
+        oracle.set_simd(True)
+        b = oracle.cm256_encode(o, 40)
+        db = oracle.cm256_decode(blocks, idx, 128, 20)
+    finally:
+        oracle.set_simd(True)
+    assert np.array_equal(a, b) and da[0] == db[0] == 0 and np.array_equal(da[1], db[1]) and da[2] == db[2]
+
+
 needs_ref = pytest.mark.skipif("not __import__('oracle.bindings').bindings.ref_available(0)",
                                reason="reference build (oracle/_ref) not present")
 
