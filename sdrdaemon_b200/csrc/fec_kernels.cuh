@@ -185,11 +185,11 @@ struct EncParams {
 
 /* persistent form: two datagram images (the next superframe is gathered while this one is encoded) */
 constexpr int ENC_NT = 512;
-inline size_t enc_smem_bytes(int cstride) { return SMEM_FIXED + (size_t)IMG_WORDS * 4 + (size_t)128 * cstride * 2; }
+inline size_t enc_smem_bytes(int cstride) { return SMEM_FIXED + (size_t)IMG_WORDS * 4 + (size_t)128 * cstride * 4; }
 
 /* 16 warps: warp w takes columns 8w .. 8w+7 of a pass */
 template <bool FULL>
-SDRD_DEVICE void enc_matvec_pass_t(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride, int row0,
+SDRD_DEVICE void enc_matvec_pass_t(const uint32_t* SDRD_RESTRICT img, const uint32_t* SDRD_RESTRICT coef, int row0,
                                    int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
@@ -205,13 +205,15 @@ SDRD_DEVICE void enc_matvec_pass_t(const uint32_t* SDRD_RESTRICT img, const uint
         for (int c = 0; c < 2; c++)
 #pragma unroll
             for (int w = 0; w < 4; w++) selectors(img[(j + c) * ROW_WORDS + lane + 32 * w], s0[c][w], s1[c][w], s2[c][w]);
-        const uint16_t* co0 = coefT + j * cstride + row0;
-        const uint16_t* co1 = co0 + cstride;
+        /* coef[r][j] = 32 * M[r][j] as a full word: the two columns' entries arrive in one 8-byte load and go straight
+         * into the table addresses (16-bit entries cost two ALU instructions per row to pull apart) */
+        const uint2* co = reinterpret_cast<const uint2*>(coef + row0 * 128 + j);
 #pragma unroll
         for (int r = 0; r < RB; r++) {
             if (FULL || r < nrows) {
-                const unsigned char* e0 = tab + co0[r];
-                const unsigned char* e1 = tab + co1[r];
+                const uint2 cc = co[r * 64];
+                const unsigned char* e0 = tab + cc.x;
+                const unsigned char* e1 = tab + cc.y;
                 const uint4 a0 = *reinterpret_cast<const uint4*>(e0);
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(e0 + 16);
                 const uint4 a1 = *reinterpret_cast<const uint4*>(e1);
@@ -236,11 +238,11 @@ SDRD_DEVICE void enc_matvec_pass_t(const uint32_t* SDRD_RESTRICT img, const uint
     }
 }
 
-SDRD_DEVICE void enc_matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint16_t* SDRD_RESTRICT coefT, int cstride, int row0,
+SDRD_DEVICE void enc_matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint32_t* SDRD_RESTRICT coef, int row0,
                                  int nrows, const unsigned char* SDRD_RESTRICT tab, uint32_t* rec16, int tid)
 {
-    if (nrows == RB) enc_matvec_pass_t<true>(img, coefT, cstride, row0, nrows, tab, rec16, tid);
-    else enc_matvec_pass_t<false>(img, coefT, cstride, row0, nrows, tab, rec16, tid);
+    if (nrows == RB) enc_matvec_pass_t<true>(img, coef, row0, nrows, tab, rec16, tid);
+    else enc_matvec_pass_t<false>(img, coef, row0, nrows, tab, rec16, tid);
 }
 
 /* Persistent: CTA c encodes work items c, c + gridDim.x, ... (item = stream * n_frames + frame).  While
@@ -251,13 +253,14 @@ SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
 {
     SDRD_DYN_SMEM(smem_raw);
     const int tid = (int)threadIdx.x;
-    Smem sm = carve(smem_raw, p.cstride);
+    Smem sm = carve(smem_raw, 2 * p.cstride); /* the coefficient area holds full words here */
     uint32_t* const img2[2] = {sm.img, reinterpret_cast<uint32_t*>(sm.extra)};
+    uint32_t* const coef = reinterpret_cast<uint32_t*>(sm.coefT); /* [cstride rows][128 blocks] */
     load_tables(sm, p.tab, tid);
-    /* coefficient rows of the Cauchy matrix, transposed so that the 16 rows of a pass are adjacent */
+    /* the Cauchy rows 128 .. 128 + F - 1 as table offsets */
     for (int k = tid; k < 128 * p.cstride; k += ENC_NT) {
-        const int j = k / p.cstride, r = k - j * p.cstride;
-        sm.coefT[k] = (uint16_t)(TAB_ENTRY * (r < p.F ? p.tab.cauchy[r * 128 + j] : (uint8_t)0));
+        const int r = k >> 7;
+        coef[k] = (uint32_t)TAB_ENTRY * (r < p.F ? (uint32_t)p.tab.cauchy[k] : 0u);
     }
     const long long n_items = (long long)p.n_frames * p.n_streams;
 
@@ -337,7 +340,7 @@ SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
             const int nrows = p.F - row0 < RB ? p.F - row0 : RB;
             for (int k = tid; k < RB * ROW_WORDS; k += ENC_NT) sm.rec16[k] = 0u;
             __syncthreads();
-            enc_matvec_pass(img, sm.coefT, p.cstride, row0, nrows, sm.tab, sm.rec16, tid);
+            enc_matvec_pass(img, coef, row0, nrows, sm.tab, sm.rec16, tid);
             __syncthreads();
             if (p.mode == 0) {
                 /* recovery datagram = header {frameIndex, blockIndex = 128 + r, filler 0} + payload */
