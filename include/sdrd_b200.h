@@ -107,6 +107,22 @@ int sdrd_dec_process_dev(sdrd_dec* dec, size_t n_in, size_t* n_out, unsigned* sa
 /* Number of kernel launches issued by this handle so far (for bench accounting). */
 long long sdrd_dec_launches(const sdrd_dec* dec);
 
+/* Feeding a handle from ANOTHER process (drop-in mode: one process holds every stream, the GPUs of the box
+ * each run a range of them in a process of their own).  The owner exports its input buffer as a CUDA IPC handle
+ * (64 bytes); the feeding process opens it and writes the samples with the copy engines over NVLink --
+ * sdrd_ipc_copy_rows is a device-to-device cudaMemcpy2DAsync, it occupies no SM and therefore overlaps the kernels
+ * of both processes completely (an NCCL send / recv pair is a kernel on either side and has to wait for SMs the
+ * decimator's one-wave grid has filled).  *offset_bytes / *stride are where stream 0's next input sample goes inside
+ * the exported allocation and the stream pitch in samples (= sdrd_dec_dev_input). */
+#define SDRD_IPC_HANDLE_BYTES 64
+int sdrd_dec_ipc_export(sdrd_dec* dec, void* handle_out, size_t* offset_bytes, size_t* stride);
+int sdrd_ipc_open(const void* handle, void** dev_ptr);
+int sdrd_ipc_close(void* dev_ptr);
+/* n_rows rows of row_bytes each from src (pitch src_pitch bytes) to dst (pitch dst_pitch bytes), device to device,
+ * either pointer may belong to a peer device; asynchronous on cuda_stream */
+int sdrd_ipc_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t n_rows,
+                       void* cuda_stream);
+
 /* ------------------------------------------------------------------------------------------
  * Interpolator (Tx side): Upsampler + Interpolators + IntHalfbandFilter{EO1,DB}<64/32/16>
  *   replaces  Upsampler::Upsampler/configure/process (include/Upsampler.h:36-50,

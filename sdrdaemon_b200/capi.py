@@ -42,6 +42,10 @@ SYMBOLS = [
     ("sdrd_dec_dev_output", _P, [_P, _SZP]),
     ("sdrd_dec_process_dev", C.c_int, [_P, _SZ, _SZP, _UP, _P]),
     ("sdrd_dec_launches", C.c_longlong, [_P]),
+    ("sdrd_dec_ipc_export", C.c_int, [_P, _P, _SZP, _SZP]),
+    ("sdrd_ipc_open", C.c_int, [_P, C.POINTER(_P)]),
+    ("sdrd_ipc_close", C.c_int, [_P]),
+    ("sdrd_ipc_copy_rows", C.c_int, [_P, _SZ, _P, _SZ, _SZ, _SZ, _P]),
     ("sdrd_src_create", C.c_int, [C.POINTER(_P), _SZ]),
     ("sdrd_src_destroy", None, [_P]),
     ("sdrd_src_reset", C.c_int, [_P]),

@@ -427,6 +427,37 @@ extern "C" void* sdrd_dec_dev_output(sdrd_dec* d, size_t* stride)
     return d->d_out;
 }
 
+extern "C" int sdrd_dec_ipc_export(sdrd_dec* d, void* handle_out, size_t* offset_bytes, size_t* stride)
+{
+    if (!d) return fail(SDRD_EINVAL, "null handle");
+    SDRD_ON_DEVICE_OF(d);
+    if (!handle_out) return fail(SDRD_EINVAL, "null handle buffer");
+    SDRD_TRY(rt::ipc_export(d->d_in, handle_out), "cudaIpcGetMemHandle");
+    if (offset_bytes) *offset_bytes = HISTW * 4;
+    if (stride) *stride = d->in_pitch;
+    return 0;
+}
+extern "C" int sdrd_ipc_open(const void* handle, void** dev_ptr)
+{
+    if (!handle || !dev_ptr) return fail(SDRD_EINVAL, "null pointer");
+    SDRD_TRY(rt::ipc_open(handle, dev_ptr), "cudaIpcOpenMemHandle");
+    return 0;
+}
+extern "C" int sdrd_ipc_close(void* dev_ptr)
+{
+    if (!dev_ptr) return 0;
+    SDRD_TRY(rt::ipc_close(dev_ptr), "cudaIpcCloseMemHandle");
+    return 0;
+}
+extern "C" int sdrd_ipc_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t n_rows,
+                                  void* cuda_stream)
+{
+    if (!dst || !src) return fail(SDRD_EINVAL, "null pointer");
+    if (dst_pitch < row_bytes || src_pitch < row_bytes) return fail(SDRD_EINVAL, "pitch smaller than the row");
+    SDRD_TRY(rt::copy2d(dst, dst_pitch, src, src_pitch, row_bytes, n_rows, rt::D2D, (rt::stream_t)cuda_stream), "device-to-device copy");
+    return 0;
+}
+
 /* samples a process call of n_in samples per stream produces under the current configuration */
 static size_t dec_out_count(const sdrd_dec* d, size_t n_in)
 {

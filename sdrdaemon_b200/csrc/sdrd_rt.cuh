@@ -52,6 +52,10 @@ inline int event_sync(event_t) { return 0; }
 inline int host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : -1; }
 inline void host_release(void* p) { free(p); }
 inline bool host_is_pageable(const void*) { return true; }
+/* inter-process handles: within the emulation a "handle" is the pointer itself */
+inline int ipc_export(void* p, void* handle64) { memset(handle64, 0, 64); memcpy(handle64, &p, sizeof p); return 0; }
+inline int ipc_open(const void* handle64, void** p) { memcpy(p, handle64, sizeof *p); return 0; }
+inline int ipc_close(void*) { return 0; }
 inline const char* last_error() { return "emu"; }
 
 #define SDRD_LAUNCH(kernel, gx, gy, nthreads, smem, stream, params)                                            \
@@ -161,6 +165,18 @@ inline int event_sync(event_t e) { return cudaEventSynchronize(e) == cudaSuccess
 /* page-locked host memory (staging rings of the queued entry points) */
 inline int host_alloc(void** p, size_t n) { return cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault) == cudaSuccess ? 0 : -1; }
 inline void host_release(void* p) { if (p) cudaFreeHost(p); }
+inline int ipc_export(void* p, void* handle64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    return cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), p) == cudaSuccess ? 0 : -1;
+}
+inline int ipc_open(const void* handle64, void** p)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    return cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? 0 : -1;
+}
+inline int ipc_close(void* p) { return cudaIpcCloseMemHandle(p) == cudaSuccess ? 0 : -1; }
 /* true for ordinary (unregistered) host memory: copies from / to it are staged by the driver, synchronously */
 inline bool host_is_pageable(const void* p)
 {

@@ -213,3 +213,28 @@ def test_rx_queued(emu_lib, oracle):
     cases.check_rx_queued(emu_lib, oracle, M=2, F=4, S=2, blk=4096, n_blk=24)
     cases.check_rx_queued(emu_lib, oracle, M=4, F=8, S=1, blk=65536, n_blk=9, max_blocks=2, bits=12)
     cases.check_rx_queued(emu_lib, oracle, M=1, F=0, S=1, blk=8192, n_blk=10, threaded=True)
+
+
+def test_ipc_feed_entry_points(emu_lib, oracle):
+    """sdrd_dec_ipc_export / sdrd_ipc_open / sdrd_ipc_copy_rows: another owner of the samples writes them straight into the
+    handle's input buffer, then the device-resident form runs (in the emulation the 'peer' is this process)"""
+    import ctypes as C
+
+    from sdrdaemon_b200 import capi
+
+    rng = np.random.default_rng(909)
+    S, n, M = 3, 8192, 3
+    x = cases.rand_iq(rng, (S, n))
+    d = capi.Decimator(M, n_streams=S, max_in=n, lib=emu_lib)
+    handle = (C.c_ubyte * 64)()
+    off, stride = C.c_size_t(0), C.c_size_t(0)
+    emu_lib.check(emu_lib.sdrd_dec_ipc_export(d._h, handle, C.byref(off), C.byref(stride)))
+    peer = C.c_void_p()
+    emu_lib.check(emu_lib.sdrd_ipc_open(handle, C.byref(peer)))
+    emu_lib.check(emu_lib.sdrd_ipc_copy_rows(peer.value + off.value, stride.value * 4, x.ctypes.data, n * 4, n * 4, S, None))
+    n_out, ss = d.process_dev(n)
+    out_ptr, out_stride = d.dev_output()
+    y = np.ctypeslib.as_array(C.cast(out_ptr, C.POINTER(C.c_int16)), shape=(S, out_stride, 2))[:, :n_out]
+    for s in range(S):
+        assert np.array_equal(y[s], oracle.Decimator(M).process(x[s])[0])
+    emu_lib.check(emu_lib.sdrd_ipc_close(peer))
