@@ -231,10 +231,14 @@ void ref_fecbuf_current_meta(void* h, uint8_t meta20[20])
  * SDRdaemonFECBuffer::writeAndRead (store, cm256_decode, copy-back; sdmnbase/SDRdaemonFECBuffer.cpp:112-250), one
  * buffer object per thread; a datagram of another frame index flushes the frame out (:133-139).
  * payload: n_frames x 127 x 508 bytes.  The reference logs every decode to std::cerr: silenced for the call. */
+struct DiscardBuf : std::streambuf { /* stateless: safe to share between the threads that log into it */
+    int overflow(int c) override { return c; }
+    std::streamsize xsputn(const char*, std::streamsize n) override { return n; }
+};
 void ref_fecbuf_decode_frames(const uint8_t* sb, size_t pitch, const int* n_blocks, int n_frames, int n_threads, uint8_t* payload)
 {
-    std::ostringstream quiet;
-    std::streambuf* old = std::cerr.rdbuf(quiet.rdbuf());
+    static DiscardBuf quiet;
+    std::streambuf* old = std::cerr.rdbuf(&quiet);
     std::atomic<int> next(0);
     auto work = [&]() {
         SDRdaemonFECBuffer* buf = new SDRdaemonFECBuffer();
