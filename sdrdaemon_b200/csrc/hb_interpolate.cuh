@@ -340,12 +340,9 @@ SDRD_HD constexpr int w_off(int b)
     for (int t = 0; t < b; t++) o += w_len(t);
     return o;
 }
-#ifndef SDRD_K4_TMA_STORE
-#define SDRD_K4_TMA_STORE 0 /* 1: every lane sends its own row of 2 N samples with one TMA bulk store instead of the staging read-back + STG.  Measured, bit-exact and SLOWER (x16 0.262 vs 0.232 ms, x2 1.08 vs 0.47 ms): a bulk copy is a uniform-datapath instruction, 32 per-lane copies are issued one lane after the other.  The form that would pay is ONE tensor-map store per pass from a 128B-swizzled staging tile. */
-#endif
-SDRD_HD constexpr int w_stage_pitch(int S) { return 2 * w_nstep(S) + 4; } /* words between the rows of two lanes (TMA form) */
-SDRD_HD constexpr int w_stage_words(int S) { return SDRD_K4_TMA_STORE ? 32 * w_stage_pitch(S) : 64 * w_nstep(S); } /* one pass of the last stage: 32 lanes x 2 N samples */
-SDRD_HD constexpr size_t w_smem_bytes(int S) { return (size_t)w_off(S) * 8 + (size_t)w_stage_words(S) * 4; }
+SDRD_HD constexpr int w_stage_words(int S) { return 64 * w_nstep(S); } /* one pass of the last stage: 32 lanes x 2 N samples */
+/* the staging tile of the TMA tensor store has to sit on a 1024-byte boundary (128-byte swizzle): 1 KB of slack */
+SDRD_HD constexpr size_t w_smem_bytes(int S) { return (size_t)w_off(S) * 8 + (size_t)w_stage_words(S) * 4 + 1024; }
 
 template <int SW>
 SDRD_DEVICE int swz(int u) { return SW ? (u ^ ((u >> 3) & SW)) : u; }
@@ -438,12 +435,17 @@ struct WarpParams {
     long long n_in;       /* input samples per stream */
     int log2_interp;      /* 1..6; stages run S = min(log2_interp, 5) */
     int steps_per_warp;   /* steps of WC input samples per warp; warp blockIdx.x takes steps [x * spw, (x + 1) * spw) */
+    /* TMA tensor store of the last stage (16 steps per lane: x16, x32): the output buffer as rows of 32 words; a pass of
+     * the last stage is one 32 x 32-word tile = 1024 consecutive samples.  use_tma = 0: plain stores. */
+    int use_tma;
+    long long out_word0;  /* word index of out[0] inside the array the map describes */
+    TileMap tmap;
 };
 
 /* one stage of the step: reads buffer ST - 1, writes buffer ST (ST < S) or the output (ST == S) */
 template <int S, int ST>
 SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT stage, int lane, uint32_t* SDRD_RESTRICT out_step, int n_left,
-                            int wo, bool emit)
+                            int wo, bool emit, const TileMap* tmap, long long tile_row0)
 {
     constexpr int L = ring_len(ST);
     constexpr int N = w_nstep(ST);
@@ -478,28 +480,27 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
             constexpr int UL = N / 2; /* 16-byte units per lane */
             uint32_t wd[2 * N];
             fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { wd[2 * i] = pack16p(ev); wd[2 * i + 1] = pack16p(od); });
-#if SDRD_K4_TMA_STORE
-            /* the lane's 2 N samples are one contiguous run of the output (a row never straddles a group of 2^S when
-             * S >= 2; S = 1: two pairs, contiguous because wo = S): written to the lane's own padded row of the staging
-             * area (pitch 2 N + 4 words: conflict-free) and sent with one bulk store that bypasses the LSU data pipe */
-            (void)SWO;
-            uint32_t* row = stage + w_stage_pitch(S) * lane;
-            tma_store_wait_read(); /* the previous pass's store has read this row */
+            /* A whole pass of 16 steps per lane is one 32 x 32-word tile of consecutive output samples: written to the
+             * staging area in the 128-byte swizzle (which is the conflict-free layout the read-back form uses anyway) and
+             * sent with ONE TMA tensor store -- no read-back, no STG, nothing of it on the LSU data pipe. */
+            if (N == 16 && tmap != nullptr && wo == S && (64 * N) * (pass + 1) <= n_left) {
+                if (lane == 0) tma_store_wait_read(); /* the previous tile has been read out of the staging area */
+                SDRD_SYNCWARP();
+                uint4* sgt = reinterpret_cast<uint4*>(stage);
 #pragma unroll
-            for (int i = 0; i < UL; i++) reinterpret_cast<uint4*>(row)[i] = make_uint4(wd[4 * i], wd[4 * i + 1], wd[4 * i + 2], wd[4 * i + 3]);
-            fence_proxy_async_smem();
-            if (emit) {
-                const int n = (64 * N) * pass + 2 * N * lane; /* relative to the step's first sample */
-                uint32_t* dst = out_step + ((n >> S) << wo) + (n & ((1 << S) - 1));
-                if (n + 2 * N <= n_left) {
-                    tma_store_1d(dst, row, 8 * N);
+                for (int i = 0; i < UL; i++) sgt[swz<SWO>(UL * lane + i)] = make_uint4(wd[4 * i], wd[4 * i + 1], wd[4 * i + 2], wd[4 * i + 3]);
+                fence_proxy_async_smem();
+                SDRD_SYNCWARP();
+                if (lane == 0 && emit) {
+                    tma_store_tile32(tmap, stage, (int)(tile_row0 + 32 * pass));
                     tma_store_commit();
-                } else { /* the ragged end of the stream (S = 1 .. 3: a row covers several input samples) */
-                    for (int w = 0; w < 2 * N; w++)
-                        if (n + w < n_left) dst[w] = row[w];
                 }
+                continue;
             }
-#else
+            if (N == 16 && tmap != nullptr) { /* a ragged last pass after tensor stores: the staging area may still be read */
+                if (lane == 0) tma_store_wait_read();
+                SDRD_SYNCWARP();
+            }
             uint4* sg = reinterpret_cast<uint4*>(stage);
 #pragma unroll
             for (int i = 0; i < UL; i++) sg[swz<SWO>(UL * lane + i)] = make_uint4(wd[4 * i], wd[4 * i + 1], wd[4 * i + 2], wd[4 * i + 3]);
@@ -522,7 +523,6 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
                     }
                 }
             }
-#endif
         }
     }
 }
@@ -532,12 +532,16 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
 #endif
 
 template <int S>
-SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
+SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(SDRD_GRID_CONSTANT WarpParams p)
 {
     static_assert(S >= 1 && S <= 5, "1..5 stages");
     SDRD_DYN_SMEM(smem);
     int2* const buf = reinterpret_cast<int2*>(smem);
-    uint32_t* const stage = reinterpret_cast<uint32_t*>(smem + (size_t)w_off(S) * 8);
+    /* the staging tile on a 1024-byte boundary of the shared-memory address space (TMA's 128-byte swizzle is a function
+     * of the address) */
+    unsigned char* const stage_raw = smem + (size_t)w_off(S) * 8;
+    uint32_t* const stage = reinterpret_cast<uint32_t*>(stage_raw + ((1024u - (unsigned)(smem_addr(stage_raw) & 1023u)) & 1023u));
+    const TileMap* const tmap = (p.use_tma && w_nstep(S) == 16) ? &p.tmap : nullptr;
     const int lane = (int)threadIdx.x;
     const uint32_t* in = p.in + (long long)blockIdx.y * p.in_stride;
     uint32_t* out = p.out + (long long)blockIdx.y * p.out_stride;
@@ -573,11 +577,13 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
         uint32_t* const out_step = out + ((step * WC) << wo);
         const long long left = n_valid - ((step * WC) << S);
         const int n_left = left > (WC << S) ? (WC << S) : (int)left;
-        warp_stage<S, 1>(buf, stage, lane, out_step, n_left, wo, emit);
-        if (S >= 2) { SDRD_SYNCWARP(); warp_stage<S, S >= 2 ? 2 : 1>(buf, stage, lane, out_step, n_left, wo, emit); }
-        if (S >= 3) { SDRD_SYNCWARP(); warp_stage<S, S >= 3 ? 3 : 1>(buf, stage, lane, out_step, n_left, wo, emit); }
-        if (S >= 4) { SDRD_SYNCWARP(); warp_stage<S, S >= 4 ? 4 : 1>(buf, stage, lane, out_step, n_left, wo, emit); }
-        if (S >= 5) { SDRD_SYNCWARP(); warp_stage<S, S >= 5 ? 5 : 1>(buf, stage, lane, out_step, n_left, wo, emit); }
+        /* row (32 words) of the step's first output sample in the array the tensor map describes */
+        const long long tile_row0 = (p.out_word0 + (long long)blockIdx.y * p.out_stride + ((step * WC) << wo)) >> 5;
+        warp_stage<S, 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0);
+        if (S >= 2) { SDRD_SYNCWARP(); warp_stage<S, S >= 2 ? 2 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0); }
+        if (S >= 3) { SDRD_SYNCWARP(); warp_stage<S, S >= 3 ? 3 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0); }
+        if (S >= 4) { SDRD_SYNCWARP(); warp_stage<S, S >= 4 ? 4 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0); }
+        if (S >= 5) { SDRD_SYNCWARP(); warp_stage<S, S >= 5 ? 5 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0); }
         if (wo > S && emit) { /* interpolate64_cen: 32 zero samples after every 32 (Interpolators.cpp:370,413-603) */
             const int zq = ((1 << wo) - (1 << S)) / 4; /* zero uint4 per input sample */
             for (int i = lane; i < WC * zq; i += 32) {
@@ -620,7 +626,7 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(WarpParams p)
         }
         SDRD_SYNCWARP();
     }
-    if (SDRD_K4_TMA_STORE) tma_store_wait_read(); /* the staging rows stay allocated until the last bulk store has read them */
+    if (tmap != nullptr && lane == 0) tma_store_wait_read(); /* the staging tile stays allocated until the last store has read it */
 }
 
 } /* namespace hbi */

@@ -699,6 +699,8 @@ struct sdrd_int {
     uint32_t* d_hist = nullptr;  /* [S][hbi::HIST] */
     uint32_t* d_out = nullptr;   /* [S][out_pitch] */
     size_t in_pitch = 0, out_pitch = 0;
+    TileMap out_map;             /* d_out as rows of 32 words: what the TMA tensor store of K4's last stage goes through */
+    bool have_map = false;
     /* per-stage state across configure, as in sdrd_dec (Interpolators.h:52-58) */
     int* d_state = nullptr;      /* [S][hbi::ISTATE_WORDS] */
     bool consistent = true;
@@ -740,6 +742,8 @@ extern "C" int sdrd_int_create(sdrd_int** out, int log2_interp, int n_streams, s
         return rc;
     }
     rt::fill(u->d_in, 0, u->in_pitch * 4 * (size_t)n_streams, u->stream);
+    /* out_pitch is a multiple of 256 words, so every stream starts on a row of the map */
+    u->have_map = rt::make_tile_map(&u->out_map, u->d_out, (unsigned long long)(u->out_pitch * (size_t)n_streams / 32)) == 0;
     if (int rc = sdrd_int_reset(u)) {
         sdrd_int_destroy(u);
         return rc;
@@ -823,7 +827,7 @@ namespace {
 #define SDRD_K4_WARP 1 /* 1: warp-private kernel; 0: the CTA-wide tiled kernel (kept for A/B runs) */
 #endif
 template <int NS>
-void launch_interpolate(const hbi::Params& p, int S, rt::stream_t st)
+void launch_interpolate(const hbi::Params& p, int S, rt::stream_t st, const TileMap* map, long long out_word0)
 {
 #if SDRD_K4_WARP
     if (p.log2_interp > NS) { /* interp = 6 (32 samples + 32 zeros per input sample): the tiled kernel is 7 % faster there */
@@ -835,6 +839,11 @@ void launch_interpolate(const hbi::Params& p, int S, rt::stream_t st)
     hbi::WarpParams w{};
     w.in = p.in; w.in_stride = p.in_stride; w.out = p.out; w.out_stride = p.out_stride; w.n_in = p.n_in;
     w.log2_interp = p.log2_interp;
+    /* rows of the map are 32 words: the call's first output word has to start one (it does unless a reconfiguration
+     * head of odd length precedes it) */
+    w.use_tma = map != nullptr && (out_word0 & 31) == 0 && (p.out_stride & 31) == 0;
+    w.out_word0 = out_word0;
+    if (map) w.tmap = *map;
     const long long steps = (p.n_in + hbi::WC - 1) / hbi::WC;
     long long warps = ((long long)rt::sm_count() * SDRD_K4_WARPS_PER_SM + S - 1) / S; /* per stream */
     if (warps > steps) warps = steps;
@@ -886,11 +895,11 @@ static int int_run(sdrd_int* u, size_t n_in, size_t* n_out_p, rt::stream_t st)
                 p.n_in = (long long)(n_in - head);
                 p.log2_interp = L;
                 switch (L < 5 ? L : 5) {
-                    case 1: launch_interpolate<1>(p, u->S, st); break;
-                    case 2: launch_interpolate<2>(p, u->S, st); break;
-                    case 3: launch_interpolate<3>(p, u->S, st); break;
-                    case 4: launch_interpolate<4>(p, u->S, st); break;
-                    default: launch_interpolate<5>(p, u->S, st); break;
+                    case 1: launch_interpolate<1>(p, u->S, st, u->have_map ? &u->out_map : nullptr, (long long)(head << L)); break;
+                    case 2: launch_interpolate<2>(p, u->S, st, u->have_map ? &u->out_map : nullptr, (long long)(head << L)); break;
+                    case 3: launch_interpolate<3>(p, u->S, st, u->have_map ? &u->out_map : nullptr, (long long)(head << L)); break;
+                    case 4: launch_interpolate<4>(p, u->S, st, u->have_map ? &u->out_map : nullptr, (long long)(head << L)); break;
+                    default: launch_interpolate<5>(p, u->S, st, u->have_map ? &u->out_map : nullptr, (long long)(head << L)); break;
                 }
                 u->launches++;
             }

@@ -79,6 +79,7 @@ void launch(Dim3 grid, unsigned nthreads, size_t smem_bytes, Body body)
 #define blockDim (sdrd_emu::t_cta->blockDim)
 #define gridDim (sdrd_emu::t_cta->gridDim)
 #define SDRD_DYN_SMEM(name) unsigned char* name = sdrd_emu::t_cta->smem
+#define SDRD_GRID_CONSTANT const
 
 static inline void __syncthreads() { sdrd_emu::t_cta->bar->arrive_and_wait(); }
 /* kernels that use it run one warp per CTA, so the CTA barrier stands in for the warp barrier */
@@ -131,6 +132,19 @@ static inline void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t b
 static inline void tma_store_commit() {}
 static inline void tma_store_wait_read() {}
 static inline void fence_proxy_async_smem() {}
+/* TMA tensor store of one 32 x 32-word tile held in shared memory in the 128-byte swizzle (16-byte chunk c of row r sits
+ * at chunk c ^ (r & 7)) to rows row0 .. row0 + 31 of a global array of 32-word rows: in the emulation a plain copy that
+ * undoes the swizzle.  TileMap is the 128-byte descriptor (a CUtensorMap in the CUDA build, the base pointer here). */
+struct alignas(64) TileMap { unsigned char opaque[128]; };
+static inline void tma_store_tile32(const TileMap* map, const void* smem_tile, int row0)
+{
+    uint32_t* base;
+    memcpy(&base, map->opaque, sizeof base);
+    const unsigned char* t = (const unsigned char*)smem_tile;
+    for (int r = 0; r < 32; r++)
+        for (int c = 0; c < 8; c++) memcpy(base + ((size_t)(row0 + r) * 32 + 4 * c), t + (r * 8 + (c ^ (r & 7))) * 16, 16);
+}
+static inline uintptr_t smem_addr(const void* p) { return (uintptr_t)p; }
 } /* namespace sdrd */
 
 #else
@@ -145,6 +159,7 @@ static inline void fence_proxy_async_smem() {}
 #define SDRD_RESTRICT __restrict__
 #define SDRD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #define SDRD_SYNCWARP() __syncwarp()
+#define SDRD_GRID_CONSTANT const __grid_constant__ /* a kernel parameter whose address may be taken (the TMA descriptor) */
 
 namespace sdrd {
 typedef uint64_t mbar_t;
@@ -187,6 +202,18 @@ SDRD_DEVICE void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t byt
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
+/* TMA tensor store (cp.async.bulk.tensor.2d, SASS UTMASTG): one 32 x 32-word tile, held in shared memory in the
+ * 128-byte swizzle, to rows row0 .. row0 + 31 of the 2-D tensor the map describes (32 words per row).  Issued by ONE
+ * thread; the tile must be 1024-byte aligned.  Completion as for the bulk copy: commit, wait_group.read before the tile is
+ * overwritten. */
+struct alignas(64) TileMap { unsigned char opaque[128]; };
+SDRD_DEVICE void tma_store_tile32(const TileMap* map, const void* smem_tile, int row0)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(smem_tile)), "r"(0),
+                 "r"(row0)
+                 : "memory");
+}
+SDRD_DEVICE uint32_t smem_addr(const void* p) { return smem_u32(p); }
 SDRD_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 SDRD_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 SDRD_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -5,6 +5,9 @@
  */
 #pragma once
 #include "sdrd_platform.cuh"
+#if !defined(SDRD_EMU)
+#include <cuda.h> /* CUtensorMap and the enums of cuTensorMapEncodeTiled: types only, no libcuda symbol is linked */
+#endif
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -57,6 +60,13 @@ inline int ipc_export(void* p, void* handle64) { memset(handle64, 0, 64); memcpy
 inline int ipc_open(const void* handle64, void** p) { memcpy(p, handle64, sizeof *p); return 0; }
 inline int ipc_close(void*) { return 0; }
 inline const char* last_error() { return "emu"; }
+/* descriptor of a global array of 32-word rows for tma_store_tile32: in the emulation just the base pointer */
+inline int make_tile_map(TileMap* map, void* base, unsigned long long)
+{
+    memset(map->opaque, 0, sizeof map->opaque);
+    memcpy(map->opaque, &base, sizeof base);
+    return 0;
+}
 
 #define SDRD_LAUNCH(kernel, gx, gy, nthreads, smem, stream, params)                                            \
     sdrd_emu::launch(sdrd_emu::Dim3{(unsigned)(gx), (unsigned)(gy), 1u}, (unsigned)(nthreads), (size_t)(smem), \
@@ -186,6 +196,31 @@ inline bool host_is_pageable(const void* p)
         return true;
     }
     return a.type == cudaMemoryTypeUnregistered;
+}
+
+/* CUtensorMap over a global array of n_rows rows of 32 words (128 bytes), box 32 x 32, 128-byte swizzle: what
+ * tma_store_tile32 stores through.  cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime, so
+ * the library does not link libcuda. */
+inline int make_tile_map(TileMap* map, void* base, unsigned long long n_rows)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+        encode = (encode_fn)fn;
+    }
+    static_assert(sizeof(CUtensorMap) == sizeof(TileMap), "a CUtensorMap is 128 bytes");
+    const cuuint64_t dims[2] = {32, n_rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    return encode(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+               ? 0
+               : -1;
 }
 
 /* the opt-in for more than 48 KB of dynamic shared memory is per function and device: set it when a launch site
