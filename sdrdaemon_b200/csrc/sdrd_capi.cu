@@ -106,7 +106,8 @@ struct HostStage {
     int to_host(void* dst, size_t dpitch, const void* src, size_t spitch, size_t w, size_t h, rt::stream_t st)
     {
         if (!w || !h) return 0;
-        if (!pend_dst && w * h <= MAX_BYTES && rt::host_is_pageable(dst) && grow(&out, &out_cap, w * h) == 0) {
+        pend_dst = nullptr; /* one staged copy per call; a call that failed half-way must not leave its destination behind */
+        if (w * h <= MAX_BYTES && rt::host_is_pageable(dst) && grow(&out, &out_cap, w * h) == 0) {
             pend_dst = (uint8_t*)dst;
             pend_dpitch = dpitch;
             pend_w = w;
@@ -272,7 +273,6 @@ struct sdrd_dec {
     int* d_state = nullptr;      /* [S][hb::STATE_WORDS] */
     bool consistent = true;
     long long run = 0;           /* raw samples consumed under the current configuration (saturating) */
-    rt::stream_t last_stream = 0; /* stream of the last process call (configure waits for it) */
     long long launches = 0;
     int sms = 148;
     rt::stream_t stream = 0;
@@ -351,7 +351,7 @@ extern "C" int sdrd_dec_reset(sdrd_dec* d)
 {
     if (!d) return fail(SDRD_EINVAL, "null handle");
     SDRD_ON_DEVICE_OF(d);
-    if (d->last_stream != d->stream) SDRD_TRY(rt::sync(d->last_stream), "reset history");
+    SDRD_TRY(rt::sync_device(), "reset history"); /* whatever stream the caller's last process call used */
     SDRD_TRY(rt::fill(d->d_hist, 0, HISTW * 4 * (size_t)d->S, d->stream), "reset history");
     SDRD_TRY(rt::fill(d->d_state, 0, (size_t)hb::STATE_WORDS * 4 * (size_t)d->S, d->stream), "reset stage states");
     SDRD_TRY(rt::sync(d->stream), "reset history");
@@ -388,7 +388,7 @@ extern "C" int sdrd_dec_configure(sdrd_dec* d, int log2_decim, int fcpos)
         int M, pro;
         dec_shape(d->log2_decim, d->fcpos, &M, &pro);
         if (d->consistent && M > 0 && d->run > 0) {
-            if (d->last_stream != d->stream) SDRD_TRY(rt::sync(d->last_stream), "configure");
+            SDRD_TRY(rt::sync_device(), "configure"); /* the history of the last process call, whatever stream it used */
             const long long n_raw = std::min<long long>(d->run, DEC_HEAD);
             hb::StateParams p{};
             p.in = (d->hist_in_front ? d->d_in : d->d_hist) + (HISTW - (size_t)n_raw);
@@ -623,7 +623,6 @@ static int dec_run(sdrd_dec* d, size_t n_in, size_t* n_out_p, unsigned* sample_b
     d->run += (long long)consumed_now;
     if (d->run > (1LL << 50)) d->run = 1LL << 50;
     if (d->run >= DEC_HEAD) d->consistent = true;
-    d->last_stream = st;
     if (n_out_p) *n_out_p = n_out;
     if (sample_bits) *sample_bits = ss;
     return 0;
@@ -683,7 +682,6 @@ extern "C" int sdrd_dec_rescale(sdrd_dec* d, int16_t* iq, size_t n, size_t strid
     if (!SDRD_LAUNCH_OK()) return fail_cuda("kernel launch");
     SDRD_TRY(rt::copy2d(iq, stride * 4, d->d_out, d->out_pitch * 4, n * 4, (size_t)d->S, rt::D2H, st), "copy samples to host");
     SDRD_TRY(rt::sync(st), "rescale");
-    d->last_stream = st;
     return 0;
 }
 
@@ -705,7 +703,6 @@ struct sdrd_int {
     int* d_state = nullptr;      /* [S][hbi::ISTATE_WORDS] */
     bool consistent = true;
     long long consumed = 0, run = 0;
-    rt::stream_t last_stream = 0;
     long long launches = 0;
     rt::stream_t stream = 0;
     HostStage stage;
@@ -769,7 +766,7 @@ extern "C" int sdrd_int_reset(sdrd_int* u)
 {
     if (!u) return fail(SDRD_EINVAL, "null handle");
     SDRD_ON_DEVICE_OF(u);
-    if (u->last_stream != u->stream) SDRD_TRY(rt::sync(u->last_stream), "reset history");
+    SDRD_TRY(rt::sync_device(), "reset history");
     SDRD_TRY(rt::fill(u->d_hist, 0, hbi::HIST * 4 * (size_t)u->S, u->stream), "reset history");
     SDRD_TRY(rt::fill(u->d_state, 0, (size_t)hbi::ISTATE_WORDS * 4 * (size_t)u->S, u->stream), "reset stage states");
     SDRD_TRY(rt::sync(u->stream), "reset history");
@@ -787,7 +784,7 @@ extern "C" int sdrd_int_configure(sdrd_int* u, int log2_interp)
     if (u->consumed > 0) {
         /* leaving a configuration: make the state of the stages it ran explicit (see sdrd_dec_configure) */
         if (u->consistent && u->log2_interp > 0 && u->run > 0) {
-            if (u->last_stream != u->stream) SDRD_TRY(rt::sync(u->last_stream), "configure");
+            SDRD_TRY(rt::sync_device(), "configure");
             const long long n = std::min<long long>(u->run, (long long)hbi::HIST);
             hbi::IStateParams p{};
             p.in = u->d_hist + ((size_t)hbi::HIST - (size_t)n);
@@ -911,7 +908,6 @@ static int int_run(sdrd_int* u, size_t n_in, size_t* n_out_p, rt::stream_t st)
     u->run += (long long)n_in;
     if (u->run > (1LL << 50)) u->run = 1LL << 50;
     if (u->run >= INT_HEAD) u->consistent = true;
-    u->last_stream = st;
     /* the last HIST input samples become the next call's history */
     SDRD_TRY(rt::copy2d(u->d_hist, hbi::HIST * 4, u->d_in + n_in, u->in_pitch * 4, hbi::HIST * 4, (size_t)u->S, rt::D2D, st),
              "save history");

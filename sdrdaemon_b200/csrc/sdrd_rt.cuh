@@ -43,6 +43,7 @@ inline int copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t
     return 0;
 }
 inline int sync(stream_t) { return 0; }
+inline int sync_device() { return 0; }
 inline int stream_create(stream_t* s) { *s = nullptr; return 0; }
 inline void stream_destroy(stream_t) {}
 typedef void* event_t;
@@ -158,6 +159,7 @@ inline int copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t
     return cudaMemcpy2DAsync(d, dp, s, sp, w, h, kind_of(k), st) == cudaSuccess ? 0 : -1;
 }
 inline int sync(stream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
+inline int sync_device() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1; }
 inline int stream_create(stream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : -1; }
 inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
 typedef cudaEvent_t event_t;
