@@ -1422,7 +1422,41 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
 
 /* ---- queued form ---- */
 
+#if defined(__x86_64__) && !defined(SDRD_EMU)
+#include <emmintrin.h>
+#endif
 namespace {
+/* Copy into the page-locked accumulation buffer.  The destination is megabytes that the CPU never reads back (the copy
+ * engine does): ordinary stores would first fetch every line they overwrite; non-temporal stores do not, which roughly
+ * doubles the rate of this copy -- and it is what bounds the queued path. */
+void staging_copy(void* dst, const void* src, size_t n)
+{
+#if defined(__x86_64__) && !defined(SDRD_EMU)
+    unsigned char* d = (unsigned char*)dst;
+    const unsigned char* s = (const unsigned char*)src;
+    const size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    if (n < 256 || head > n) {
+        memcpy(d, s, n);
+        return;
+    }
+    memcpy(d, s, head);
+    d += head; s += head; n -= head;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(s + i)), b = _mm_loadu_si128((const __m128i*)(s + i + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(s + i + 32)), e = _mm_loadu_si128((const __m128i*)(s + i + 48));
+        _mm_stream_si128((__m128i*)(d + i), a);
+        _mm_stream_si128((__m128i*)(d + i + 16), b);
+        _mm_stream_si128((__m128i*)(d + i + 32), c);
+        _mm_stream_si128((__m128i*)(d + i + 48), e);
+    }
+    _mm_sfence(); /* visible to the copy engine before the transfer is enqueued */
+    memcpy(d + i, s + i, n - i);
+#else
+    memcpy(dst, src, n);
+#endif
+}
+
 /* under q_mutex: allocate the staging buffers on first use */
 int q_prepare(sdrd_rx* r)
 {
@@ -1534,7 +1568,10 @@ extern "C" int sdrd_rx_submit(sdrd_rx* r, const int16_t* iq_in, size_t n_in, siz
     std::unique_lock<std::mutex> lk(r->q_mutex);
     if (int rc = q_prepare(r)) return rc;
     if (r->ready_frames > 65536) return fail(SDRD_ERANGE, "too many completed frames waiting: call sdrd_rx_collect");
-    if (r->q_inflight && rt::event_done(r->q_done) != 0) q_harvest(r);
+    /* asking the driver whether the chain in flight has completed costs microseconds: only when the answer matters,
+     * i.e. when this block would let a new chain start (or would not fit behind what has accumulated) */
+    const bool may_start = r->q_fill + n_in >= r->q_min_chain || r->q_fill + n_in > r->q_cap;
+    if (r->q_inflight && may_start && rt::event_done(r->q_done) != 0) q_harvest(r);
     /* a block that does not fit behind what has accumulated, or that has another sample size, starts a new chain */
     if (r->q_fill && (r->q_fill + n_in > r->q_cap || ss_in != r->q_ss)) {
         if (r->q_inflight) {
@@ -1545,7 +1582,7 @@ extern "C" int sdrd_rx_submit(sdrd_rx* r, const int16_t* iq_in, size_t n_in, siz
     }
     r->q_ss = ss_in;
     for (int s = 0; s < d->S; s++)
-        memcpy(r->q_in[r->q_cur] + (size_t)s * r->q_cap + r->q_fill, iq_in + 2 * (size_t)s * in_stride, n_in * 4);
+        staging_copy(r->q_in[r->q_cur] + (size_t)s * r->q_cap + r->q_fill, iq_in + 2 * (size_t)s * in_stride, n_in * 4);
     r->q_fill += n_in;
     if (!r->q_inflight && r->q_fill >= r->q_min_chain)
         if (int rc = q_launch(r)) return rc;
@@ -1576,7 +1613,8 @@ extern "C" int sdrd_rx_collect(sdrd_rx* r, uint8_t* datagrams, size_t frame_capa
                 if (int rc = q_launch(r)) return rc;
             }
         }
-    } else if (r->q_inflight && rt::event_done(r->q_done) != 0) {
+    } else if (r->ready.empty() && r->q_inflight && rt::event_done(r->q_done) != 0) {
+        /* (frames already waiting are handed over without asking the driver about the chain in flight) */
         q_harvest(r);
         if (r->q_fill && r->q_fill >= r->q_min_chain)
             if (int rc = q_launch(r)) return rc;
