@@ -516,15 +516,15 @@ def small_block_leg(lib, capi, n_blocks=4000, blk=65536):
     try:
         import torch
 
-        stage = torch.empty((blk, 2), dtype=torch.int16).pin_memory()
+        stage = torch.empty((64, blk, 2), dtype=torch.int16).pin_memory()   # as large as the queue's two buffers
         sp = stage.data_ptr()
         for warm in (True, False):
             t0 = time.perf_counter()
             for b in range(200 if warm else n_blocks):
-                C.memmove(sp, ptrs[b & 7], blk * 4)
+                C.memmove(sp + (b & 63) * blk * 4, ptrs[b & 7], blk * 4)
             dt = time.perf_counter() - t0
         res["host_copy_ceiling"] = {"value": round(n_blocks * blk / dt / 1e6, 1), "unit": UNIT, "GB_per_s": round(n_blocks * blk * 4 / dt / 1e9, 2),
-                                    "what": "memmove of each block into page-locked memory, one thread"}
+                                    "what": "memmove of each block into 16 MB of page-locked memory (not cache resident), one thread"}
     except Exception:
         pass
     rx = capi.Rx(M_LOG2, n_streams=1, max_in=32 * blk, n_fec=N_FEC)
@@ -575,13 +575,17 @@ def small_block_leg(lib, capi, n_blocks=4000, blk=65536):
         res["classes"] = {"value": round(j["msamples_per_s"], 1), "unit": UNIT, "us_per_block": j["us_per_block"],
                           "api": "Downsampler::process + UDPSinkFEC::write (sdrd_host.hpp), native caller"}
         # the queued entry points from a native caller (the ctypes legs above pay ~5 us of interpreter per call)
-        for key, mc in (("queued_native", 0), ("queued_batched_native", 16)):
-            r = subprocess.run([exe, "blocksq", str(4 * n_blocks), str(M_LOG2), str(N_FEC), str(blk), str(mc), "1000"], capture_output=True,
-                               text=True, timeout=300)
+        # (`_staged`: sdrd_rx_set_staging_threads -- helper threads of the handle share the copy into page-locked memory,
+        # the way the reference spreads this work over its source / downsampler / sink threads)
+        for key, mc, helpers in (("queued_native", 0, 0), ("queued_batched_native", 16, 0), ("queued_native_staged", 0, 2),
+                                 ("queued_batched_native_staged", 16, 2)):
+            r = subprocess.run([exe, "blocksq", str(5 * n_blocks), str(M_LOG2), str(N_FEC), str(blk), str(mc), "2000", str(helpers)],
+                               capture_output=True, text=True, timeout=300)
             j = json.loads(r.stdout.strip().splitlines()[-1])
             res[key] = {"value": round(j["msamples_per_s"], 1), "unit": UNIT, "us_per_block": j["us_per_block"],
-                        "blocks_per_chain": j["blocks_per_chain"],
-                        "api": "sdrd_rx_submit + sdrd_rx_collect from C++" + (f", sdrd_rx_set_min_chain({mc} blocks)" if mc else "")}
+                        "blocks_per_chain": j["blocks_per_chain"], "staging_threads": helpers,
+                        "api": "sdrd_rx_submit + sdrd_rx_collect from C++" + (f", sdrd_rx_set_min_chain({mc} blocks)" if mc else "")
+                               + (f", sdrd_rx_set_staging_threads({helpers})" if helpers else "")}
     except Exception as e:
         res["classes"] = {"value": None, "note": f"not measured ({type(e).__name__})"}
     return res

@@ -284,6 +284,12 @@ long long sdrd_rx_chains(const sdrd_rx* rx);
  * than that can ask for chains of at least min_samples samples per stream (sdrd_rx_collect with wait != 0 still sends
  * what is there). */
 int sdrd_rx_set_min_chain(sdrd_rx* rx, size_t min_samples);
+/* sdrd_rx_submit is bounded by one host core copying the block into page-locked memory (15 - 20 GB/s against the
+ * 55 GB/s the copy engine takes).  n_helpers (0..15, default 0) threads owned by the handle share that copy with the
+ * caller: they spin for some tens of microseconds after a block (a streaming producer finds them awake), sleep
+ * otherwise, and end with sdrd_rx_destroy.  The reference spreads the same work over its four threads
+ * (sdrdaemonrx.cpp:579-663).  No effect on the results. */
+int sdrd_rx_set_staging_threads(sdrd_rx* rx, int n_helpers);
 
 /* Device-resident form: input at sdrd_dec_dev_input(sdrd_rx_dec(rx)), datagram images left at
  * sdrd_rx_dev_datagrams() (stream pitch *frame_pitch frames of (128 + nb_fec) x 512 bytes). */

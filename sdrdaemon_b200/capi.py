@@ -90,6 +90,7 @@ SYMBOLS = [
     ("sdrd_rx_collect", C.c_int, [_P, _P, _SZ, _SZP, C.POINTER(C.c_int), C.c_int]),
     ("sdrd_rx_chains", C.c_longlong, [_P]),
     ("sdrd_rx_set_min_chain", C.c_int, [_P, _SZ]),
+    ("sdrd_rx_set_staging_threads", C.c_int, [_P, C.c_int]),
     ("sdrd_rx_dev_datagrams", _P, [_P, _SZP]),
     ("sdrd_rx_process_dev", C.c_int, [_P, _SZ, _SZP, _UP, _P]),
     ("sdrd_rx_launches", C.c_longlong, [_P]),
@@ -521,6 +522,10 @@ class Rx:
 
     def set_min_chain(self, min_samples: int) -> None:
         self.lib.check(self.lib.sdrd_rx_set_min_chain(self._h, min_samples))
+
+    def set_staging_threads(self, n_helpers: int) -> None:
+        """Helper threads that share submit's copy into page-locked memory with the caller."""
+        self.lib.check(self.lib.sdrd_rx_set_staging_threads(self._h, n_helpers))
 
     def dev_input(self) -> Tuple[int, int]:
         st = C.c_size_t(0)

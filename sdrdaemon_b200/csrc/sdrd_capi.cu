@@ -17,8 +17,12 @@
 #include <sys/time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -1211,6 +1215,141 @@ extern "C" long long sdrd_sink_launches(const sdrd_sink* k) { return k ? k->laun
 /* fused rx pipeline                                                                           */
 /* ========================================================================================== */
 
+#if defined(__x86_64__) && !defined(SDRD_EMU)
+#include <emmintrin.h>
+#endif
+namespace {
+/* Copy into the page-locked accumulation buffer.  The destination is megabytes that the CPU never reads back (the copy
+ * engine does): ordinary stores would first fetch every line they overwrite; non-temporal stores do not, which roughly
+ * doubles the rate of this copy -- and it is what bounds the queued path. */
+void staging_copy(void* dst, const void* src, size_t n)
+{
+#if defined(__x86_64__) && !defined(SDRD_EMU)
+    unsigned char* d = (unsigned char*)dst;
+    const unsigned char* s = (const unsigned char*)src;
+    const size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    if (n < 256 || head > n) {
+        memcpy(d, s, n);
+        return;
+    }
+    memcpy(d, s, head);
+    d += head; s += head; n -= head;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(s + i)), b = _mm_loadu_si128((const __m128i*)(s + i + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(s + i + 32)), e = _mm_loadu_si128((const __m128i*)(s + i + 48));
+        _mm_stream_si128((__m128i*)(d + i), a);
+        _mm_stream_si128((__m128i*)(d + i + 16), b);
+        _mm_stream_si128((__m128i*)(d + i + 32), c);
+        _mm_stream_si128((__m128i*)(d + i + 48), e);
+    }
+    _mm_sfence(); /* visible to the copy engine before the transfer is enqueued */
+    memcpy(d + i, s + i, n - i);
+#else
+    memcpy(dst, src, n);
+#endif
+}
+
+inline void cpu_relax()
+{
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+}
+} /* namespace */
+
+/* Helper threads that share one staging copy with the thread that calls sdrd_rx_submit.  One core moves a block into
+ * memory it does not cache at 15 - 20 GB/s, which is what bounds the queued path; the copy engine takes 55 GB/s.  The
+ * helpers spin for a short while after a job (a producer that streams blocks finds them awake) and sleep otherwise. */
+struct CopyCrew {
+    explicit CopyCrew(int n_helpers)
+    {
+        try {
+            for (int i = 0; i < n_helpers; i++) th.emplace_back([this, i] { run(i + 1); });
+        } catch (...) {
+            dismiss();
+            throw;
+        }
+    }
+    ~CopyCrew() { dismiss(); }
+    CopyCrew(const CopyCrew&) = delete;
+    CopyCrew& operator=(const CopyCrew&) = delete;
+    int helpers() const { return (int)th.size(); }
+
+    /* the caller's share is part 0; returns when every part is in place */
+    void copy(void* dst_, const void* src_, size_t n_)
+    {
+        const int parts = (int)th.size() + 1;
+        if (n_ < (size_t)parts * 16384) { /* not worth a hand-over */
+            staging_copy(dst_, src_, n_);
+            return;
+        }
+        dst = (unsigned char*)dst_;
+        src = (const unsigned char*)src_;
+        n = n_;
+        pending.store((int)th.size(), std::memory_order_relaxed);
+        job.fetch_add(1); /* seq_cst: publishes dst / src / n, ordered against `sleepers` below */
+        if (sleepers.load() > 0) {
+            std::lock_guard<std::mutex> lk(m);
+            cv.notify_all();
+        }
+        part(0, parts);
+        while (pending.load(std::memory_order_acquire) != 0) cpu_relax();
+    }
+
+private:
+    void dismiss()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit.store(true);
+        }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+    void part(int i, int parts)
+    {
+        const size_t chunk = ((n / (size_t)parts) + 63) & ~(size_t)63;
+        const size_t b = std::min(n, chunk * (size_t)i), e = i + 1 == parts ? n : std::min(n, chunk * (size_t)(i + 1));
+        if (e > b) staging_copy(dst + b, src + b, e - b);
+    }
+    void run(int me)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            /* wait for the next job: spin first, then sleep */
+            bool got = false;
+            for (int spin = 0; spin < 20000; spin++) {
+                if (job.load(std::memory_order_acquire) != seen || quit.load(std::memory_order_relaxed)) {
+                    got = true;
+                    break;
+                }
+                cpu_relax();
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(m);
+                sleepers.fetch_add(1);
+                cv.wait(lk, [&] { return job.load() != seen || quit.load(); });
+                sleepers.fetch_sub(1);
+            }
+            if (quit.load()) return;
+            seen = job.load(std::memory_order_acquire);
+            part(me, (int)th.size() + 1);
+            pending.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::atomic<unsigned long long> job{0};
+    std::atomic<int> pending{0}, sleepers{0};
+    std::atomic<bool> quit{false};
+    unsigned char* dst = nullptr;
+    const unsigned char* src = nullptr;
+    size_t n = 0;
+};
+
 struct sdrd_rx {
     int device = -1;             /* the device the handle lives on */
     sdrd_dec* dec = nullptr;
@@ -1245,6 +1384,7 @@ struct sdrd_rx {
     std::deque<Batch> ready;
     size_t ready_frames = 0;                /* per stream */
     long long q_launches = 0;               /* chains sent so far (a measure of the batching achieved) */
+    CopyCrew* crew = nullptr;               /* helper threads that share submit's staging copy (sdrd_rx_set_staging_threads) */
 };
 
 extern "C" int sdrd_rx_create(sdrd_rx** out, int log2_decim, int fcpos, int variant, int n_streams, size_t max_in)
@@ -1272,6 +1412,7 @@ extern "C" void sdrd_rx_destroy(sdrd_rx* r)
     SDRD_ON_DEVICE_OF(r);
     if (r->copy_stream) rt::sync(r->copy_stream);
     if (r->q_stream) rt::sync(r->q_stream);
+    delete r->crew;
     rt::host_release(r->q_in[0]);
     rt::host_release(r->q_in[1]);
     rt::host_release(r->q_out);
@@ -1422,41 +1563,7 @@ extern "C" int sdrd_rx_process(sdrd_rx* r, const int16_t* iq_in, size_t n_in, si
 
 /* ---- queued form ---- */
 
-#if defined(__x86_64__) && !defined(SDRD_EMU)
-#include <emmintrin.h>
-#endif
 namespace {
-/* Copy into the page-locked accumulation buffer.  The destination is megabytes that the CPU never reads back (the copy
- * engine does): ordinary stores would first fetch every line they overwrite; non-temporal stores do not, which roughly
- * doubles the rate of this copy -- and it is what bounds the queued path. */
-void staging_copy(void* dst, const void* src, size_t n)
-{
-#if defined(__x86_64__) && !defined(SDRD_EMU)
-    unsigned char* d = (unsigned char*)dst;
-    const unsigned char* s = (const unsigned char*)src;
-    const size_t head = (16 - ((uintptr_t)d & 15)) & 15;
-    if (n < 256 || head > n) {
-        memcpy(d, s, n);
-        return;
-    }
-    memcpy(d, s, head);
-    d += head; s += head; n -= head;
-    size_t i = 0;
-    for (; i + 64 <= n; i += 64) {
-        const __m128i a = _mm_loadu_si128((const __m128i*)(s + i)), b = _mm_loadu_si128((const __m128i*)(s + i + 16));
-        const __m128i c = _mm_loadu_si128((const __m128i*)(s + i + 32)), e = _mm_loadu_si128((const __m128i*)(s + i + 48));
-        _mm_stream_si128((__m128i*)(d + i), a);
-        _mm_stream_si128((__m128i*)(d + i + 16), b);
-        _mm_stream_si128((__m128i*)(d + i + 32), c);
-        _mm_stream_si128((__m128i*)(d + i + 48), e);
-    }
-    _mm_sfence(); /* visible to the copy engine before the transfer is enqueued */
-    memcpy(d + i, s + i, n - i);
-#else
-    memcpy(dst, src, n);
-#endif
-}
-
 /* under q_mutex: allocate the staging buffers on first use */
 int q_prepare(sdrd_rx* r)
 {
@@ -1511,6 +1618,9 @@ int q_launch(sdrd_rx* r)
         }
         r->q_out_frames = will_close;
     }
+    /* (Slicing the chain so that the copy of one piece overlaps the kernels of the one before, as sdrd_rx_process does
+     * with large calls, was measured and gains nothing here: behind the copy a piece costs ~60 us of dependent
+     * launches whatever its size -- 4 pieces 9.1, 2 pieces 8.0, one piece 8.2 us per 65536-sample block.) */
     SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, r->q_in[r->q_cur], r->q_cap * 4, n * 4, (size_t)d->S, rt::H2D, st),
              "copy samples to device");
     size_t n_out = 0, nf = 0;
@@ -1581,8 +1691,12 @@ extern "C" int sdrd_rx_submit(sdrd_rx* r, const int16_t* iq_in, size_t n_in, siz
         if (int rc = q_launch(r)) return rc;
     }
     r->q_ss = ss_in;
-    for (int s = 0; s < d->S; s++)
-        staging_copy(r->q_in[r->q_cur] + (size_t)s * r->q_cap + r->q_fill, iq_in + 2 * (size_t)s * in_stride, n_in * 4);
+    for (int s = 0; s < d->S; s++) {
+        void* to = r->q_in[r->q_cur] + (size_t)s * r->q_cap + r->q_fill;
+        const void* from = iq_in + 2 * (size_t)s * in_stride;
+        if (r->crew) r->crew->copy(to, from, n_in * 4);
+        else staging_copy(to, from, n_in * 4);
+    }
     r->q_fill += n_in;
     if (!r->q_inflight && r->q_fill >= r->q_min_chain)
         if (int rc = q_launch(r)) return rc;
@@ -1647,6 +1761,23 @@ extern "C" int sdrd_rx_set_min_chain(sdrd_rx* r, size_t min_samples)
     if (min_samples > r->dec->max_in) return fail(SDRD_ERANGE, "min_samples exceeds the max_in given at create time");
     std::lock_guard<std::mutex> lk(r->q_mutex);
     r->q_min_chain = min_samples;
+    return 0;
+}
+extern "C" int sdrd_rx_set_staging_threads(sdrd_rx* r, int n_helpers)
+{
+    if (!r) return fail(SDRD_EINVAL, "null handle");
+    if (n_helpers < 0 || n_helpers > 15) return fail(SDRD_ERANGE, "0..15 helper threads");
+    std::lock_guard<std::mutex> lk(r->q_mutex);
+    if ((r->crew ? r->crew->helpers() : 0) == n_helpers) return 0;
+    delete r->crew;
+    r->crew = nullptr;
+    if (n_helpers) {
+        try {
+            r->crew = new CopyCrew(n_helpers);
+        } catch (...) {
+            return fail(SDRD_ENOMEM, "could not start the staging threads");
+        }
+    }
     return 0;
 }
 

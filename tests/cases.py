@@ -452,7 +452,7 @@ def check_sink_frame_clock(lib, ob, splits, rate=48000, F=4, base=(1700000000, 9
     sk.close()
 
 
-def check_rx_queued(lib, ob, M, F, S, blk, n_blk, max_blocks=8, threaded=False, bits=16, seed=808):
+def check_rx_queued(lib, ob, M, F, S, blk, n_blk, max_blocks=8, threaded=False, bits=16, seed=808, helpers=0):
     """sdrd_rx_submit / sdrd_rx_collect: blocks of `blk` samples submitted one after the other (batched on the way as
     far as the device lags), frames collected in between or from a second thread -- the datagram stream must be the
     one UDPSinkFEC::write produces from the decimated stream (oracle), whatever the batching was."""
@@ -461,6 +461,7 @@ def check_rx_queued(lib, ob, M, F, S, blk, n_blk, max_blocks=8, threaded=False, 
     rng = np.random.default_rng(seed)
     x = rand_iq(rng, (S, blk * n_blk), bits)
     rx = capi.Rx(M, n_streams=S, max_in=blk * max_blocks, n_fec=F, lib=lib)
+    rx.set_staging_threads(helpers)        # the staging copy shared with helper threads: same datagrams
     got = []
     if threaded:
         done = threading.Event()
@@ -483,6 +484,8 @@ def check_rx_queued(lib, ob, M, F, S, blk, n_blk, max_blocks=8, threaded=False, 
         got.append(rx.collect(1 << 10, wait=True))
     else:
         for b in range(n_blk):
+            if helpers and b == n_blk // 2:
+                rx.set_staging_threads(helpers + 1)   # the crew may change between blocks
             ss = rx.submit(x[:, b * blk:(b + 1) * blk], bits)
             if b % 5 == 4:
                 g = rx.collect(3)          # a capacity smaller than what may be ready: the rest stays queued

@@ -221,7 +221,7 @@ static int run_blocks(int argc, char** argv)
     return 0;
 }
 
-/* host_pipeline blocksq <n_blocks> <decim> <fecblk> <blklen> <min_chain_blocks> [warmup]
+/* host_pipeline blocksq <n_blocks> <decim> <fecblk> <blklen> <min_chain_blocks> [warmup] [staging_threads]
  * The same blocks through the queued C entry points (sdrd_rx_submit / sdrd_rx_collect) from a native caller: what a
  * main loop gets that hands its blocks over instead of waiting for each (route C). */
 static int run_blocksq(int argc, char** argv)
@@ -229,11 +229,13 @@ static int run_blocksq(int argc, char** argv)
     if (argc < 7) return 2;
     const int n_blocks = atoi(argv[2]), decim = atoi(argv[3]), fecblk = atoi(argv[4]), blklen = atoi(argv[5]), min_chain = atoi(argv[6]);
     const int warmup = argc > 7 ? atoi(argv[7]) : 64;
+    const int helpers = argc > 8 ? atoi(argv[8]) : 0;
     sdrd_rx* rx = nullptr;
     if (sdrd_rx_create(&rx, decim, SDRD_FC_CENTER, SDRD_HB_EO1, 1, (size_t)blklen * 32) != 0) { fprintf(stderr, "%s\n", sdrd_last_error()); return 1; }
     sdrd_sink_set_nb_fec(sdrd_rx_sink(rx), fecblk);
     sdrd_sink_set_meta(sdrd_rx_sink(rx), 435000, 10000000u >> decim, 2, 16);
     sdrd_rx_set_min_chain(rx, (size_t)min_chain * blklen);
+    if (sdrd_rx_set_staging_threads(rx, helpers) != 0) { fprintf(stderr, "%s\n", sdrd_last_error()); return 1; }
     const int n_src = 8;
     std::vector<IQSampleVector> src(n_src);
     float phase = 0;
@@ -267,15 +269,52 @@ static int run_blocksq(int argc, char** argv)
     const double dt = (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_usec - t0.tv_usec);
     const long long chains = sdrd_rx_chains(rx) - chains0;
     printf("{\"blocks\": %d, \"blklen\": %d, \"decim\": %d, \"fecblk\": %d, \"seconds\": %.6f, \"msamples_per_s\": %.3f, "
-           "\"us_per_block\": %.2f, \"blocks_per_chain\": %.2f, \"frames\": %zu}\n",
+           "\"us_per_block\": %.2f, \"blocks_per_chain\": %.2f, \"frames\": %zu, \"staging_threads\": %d}\n",
            n_blocks, blklen, decim, fecblk, dt, (double)n_blocks * blklen / dt * 1e-6, dt / n_blocks * 1e6,
-           (double)n_blocks / (double)(chains > 0 ? chains : 1), frames);
+           (double)n_blocks / (double)(chains > 0 ? chains : 1), frames, helpers);
+    sdrd_rx_destroy(rx);
+    return 0;
+}
+
+/* host_pipeline chain <decim> <fecblk> <blklen>: how long ONE chain of n blocks takes on the device (submit n blocks
+ * with the start held back, then time collect(wait): launch + copy in + kernels + copy back), n = 1 .. 32 */
+static int run_chain(int argc, char** argv)
+{
+    if (argc < 5) return 2;
+    const int decim = atoi(argv[2]), fecblk = atoi(argv[3]), blklen = atoi(argv[4]);
+    sdrd_rx* rx = nullptr;
+    if (sdrd_rx_create(&rx, decim, SDRD_FC_CENTER, SDRD_HB_EO1, 1, (size_t)blklen * 32) != 0) { fprintf(stderr, "%s\n", sdrd_last_error()); return 1; }
+    sdrd_sink_set_nb_fec(sdrd_rx_sink(rx), fecblk);
+    sdrd_sink_set_meta(sdrd_rx_sink(rx), 435000, 10000000u >> decim, 2, 16);
+    sdrd_rx_set_min_chain(rx, (size_t)32 * blklen);
+    std::vector<int16_t> buf(2 * (size_t)blklen);
+    float phase = 0;
+    int got = 0;
+    TestSource::read_samples(buf.data(), 4 * blklen, got, phase, 10000000, 0.0628f, 0.5f, false);
+    std::vector<uint8_t> out((size_t)64 * (128 + fecblk) * SDRD_UDPSIZE);
+    size_t nfr = 0;
+    int bpf = 0;
+    for (int n = 1; n <= 32; n *= 2) {
+        double best = 1e9;
+        for (int rep = 0; rep < 40; rep++) {
+            for (int b = 0; b < n - (n == 32); b++) sdrd_rx_submit(rx, buf.data(), (size_t)blklen, (size_t)blklen, nullptr);
+            struct timeval t0, t1;
+            gettimeofday(&t0, 0);
+            if (n == 32) sdrd_rx_submit(rx, buf.data(), (size_t)blklen, (size_t)blklen, nullptr); /* this one starts the chain */
+            do { sdrd_rx_collect(rx, out.data(), 64, &nfr, &bpf, 1); } while (nfr);
+            gettimeofday(&t1, 0);
+            const double dt = (t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_usec - t0.tv_usec);
+            if (rep >= 5 && dt < best) best = dt;
+        }
+        printf("{\"chain_blocks\": %d, \"us_per_chain\": %.1f, \"us_per_block\": %.2f}\n", n, best, best / n);
+    }
     sdrd_rx_destroy(rx);
     return 0;
 }
 
 int main(int argc, char** argv)
 {
+    if (argc >= 2 && std::string(argv[1]) == "chain") return run_chain(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "blocksq") return run_blocksq(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "blocks") return run_blocks(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "testsource") return run_testsource(argc, argv);

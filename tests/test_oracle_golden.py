@@ -75,6 +75,47 @@ def test_gf256_known_answers(oracle):
     assert oracle.crc32(b"123456789") == 0xCBF43926
 
 
+def test_gf256_against_third_party_polynomial_arithmetic(oracle):
+    """The oracle's GF(256) products, quotients, exp/log tables and Cauchy matrix elements against arithmetic that
+    this project did not write: sympy.polys.galoistools over GF(2), reduced modulo x^8+x^6+x^3+x^2+1 (0x14D, the
+    polynomial cm256's gf256 publishes as its default).  What this does NOT pin is the choice of polynomial and of the
+    matrix itself -- cm256cc is absent from the reference tree, see DESIGN.md section 2."""
+    gt = pytest.importorskip("sympy.polys.galoistools")
+    from sympy.polys.domains import ZZ
+
+    MOD = [ZZ(int(b)) for b in bin(0x14D)[2:]]              # dense, highest degree first
+    poly = lambda v: gt.gf_strip([ZZ(int(b)) for b in bin(v)[2:]]) if v else []
+    val = lambda p: int("".join(str(int(c)) for c in p), 2) if p else 0
+    L = oracle.lib()
+    assert gt.gf_irreducible_p(MOD, 2, ZZ)
+    mul = lambda a, b: val(gt.gf_rem(gt.gf_mul(poly(a), poly(b), 2, ZZ), MOD, 2, ZZ))
+    # the whole multiplication table through one generator: exp/log, then every product by table
+    exp = [1]
+    for i in range(1, 255):
+        exp.append(mul(exp[-1], 2))
+    assert sorted(exp) == list(range(1, 256))                # x generates the multiplicative group
+    assert [L.sdro_gf_exp(i) for i in range(255)] == exp
+    log = {v: i for i, v in enumerate(exp)}
+    assert all(L.sdro_gf_log(v) == log[v] for v in range(1, 256))
+    rng = np.random.default_rng(256)
+    for a, b in rng.integers(0, 256, size=(600, 2)).tolist() + [(0, 7), (9, 0), (255, 255), (1, 200)]:
+        want = mul(a, b)                                     # the polynomial product itself, not the tables above
+        assert L.sdro_gf_mul(a, b) == want
+        if b:
+            q = L.sdro_gf_div(a, b)
+            assert mul(q, b) == a
+    for a in range(256):                                     # full table against exp/log of the third-party field
+        for b in range(256):
+            want = exp[(log[a] + log[b]) % 255] if a and b else 0
+            assert L.sdro_gf_mul(a, b) == want
+    # cm256's matrix element (x_i, x_0 = 128, y_j) = (y_j + x_0) / (x_i + y_j) in that field
+    inv = lambda v: exp[(255 - log[v]) % 255]
+    for x in (128, 129, 130, 159, 200, 255):
+        for j in range(128):
+            want = mul(j ^ 128, inv(x ^ j))
+            assert L.sdro_cm256_matrix_element(x, 128, j) == want
+
+
 def test_cm256_mds_and_linearity(oracle):
     rng = np.random.default_rng(11)
     o = rng.integers(0, 256, size=(128, 508), dtype=np.uint8)
