@@ -20,7 +20,9 @@
  *     algorithm: GF(2^8) with polynomial 0x14D, generator 2, Cauchy element
  *     M[x_i][y_j] = (y_j ^ x_0) / (x_i ^ y_j), x_0 = OriginalCount.  It is anchored on the
  *     reference's call sites (sdmnbase/UDPSinkFEC.cpp:228-246, SDRdaemonFECBuffer.cpp:143-213)
- *     and on algebraic properties (MDS round trips, row-128 = XOR parity).
+ *     and on algebraic properties (MDS round trips, row-128 = XOR parity).  The field
+ *     arithmetic alone (products, quotients, exp/log, matrix elements given the polynomial
+ *     and the formula) is checked against sympy's GF(2)[x] routines in tests/.
  */
 #ifndef SDRD_ORACLE_H
 #define SDRD_ORACLE_H
