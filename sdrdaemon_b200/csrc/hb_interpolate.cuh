@@ -362,8 +362,34 @@ SDRD_DEVICE void st_unit(int2* SDRD_RESTRICT buf, int unit, int2 a, int2 b)
 #ifndef SDRD_K4_PACKED_X0
 #define SDRD_K4_PACKED_X0 1 /* buffer 0 keeps the raw {int16 I, int16 Q} words (half the window bytes of stage 1), sign-extended in registers */
 #endif
-template <int L, int N, bool PACKED = false, class Sink>
-SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, Sink&& sink)
+/* Pipe steering, as in K1 (hb_decimate.cuh, Steer): a step is T pre-adds + T multiply-accumulates per component; left
+ * alone ptxas writes 63 % of the pre-adds as IMAD.IADD, next to the IMADs on the FMA pipe (67 % busy, ALU 42 %).
+ * Tap t's pre-add is a three-source IADD3 (ALU only) unless t % SDRD_K4_FMA_ADD_MOD == 0, where it is an IMAD by a
+ * run-time 1 (FMA pipe); 0 = every pre-add on the ALU pipe, -1 = left to ptxas.
+ * Measured (x16, config 6, ms): -1: 0.2172, 2: 0.2162, 3: 0.2162, 0 / 4 / 5 / 6 / 8 / 16: 0.2069 / 0.2066 / 0.2058 /
+ * 0.2068 / 0.2062 / 0.2058.  Moving the >> 13 to the FMA pipe as well (high word of acc * 2^19, IMAD.HI) loses what
+ * the steering gains (0.217 - 0.227) and is not kept. */
+#ifndef SDRD_K4_FMA_ADD_MOD
+#define SDRD_K4_FMA_ADD_MOD 16
+#endif
+struct ISteer {
+    uint32_t zero, one;
+};
+SDRD_DEVICE uint32_t pre_add(uint32_t a, uint32_t b, int t, ISteer st)
+{
+    if (SDRD_K4_FMA_ADD_MOD < 0) return a + b;
+    if (SDRD_K4_FMA_ADD_MOD > 0 && t % (SDRD_K4_FMA_ADD_MOD > 0 ? SDRD_K4_FMA_ADD_MOD : 1) == 0) return mad_lo(a, st.one, b);
+    return add3(a, b, st.zero);
+}
+
+/* RAW8 (the last stage, whose samples only live on as int16): the taps are taken times 8 and the sums handed over
+ * unshifted -- bits 16..31 of the wrapping sum 8 * acc are bits 13..28 of acc, i.e. (int16)(acc >> 13), which the
+ * packing byte-permute picks up directly: no shift instruction for half of all the cascade's outputs. */
+#ifndef SDRD_K4_RAW8
+#define SDRD_K4_RAW8 1
+#endif
+template <int L, int N, bool PACKED = false, bool RAW8 = false, class Sink>
+SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, ISteer steer, Sink&& sink)
 {
     constexpr int SW = w_sw_of_n(N);
     constexpr int T = L / 2;
@@ -415,17 +441,18 @@ SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, Sink&& sink)
         uint32_t ia = 0, qa = 0;
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            const int c = L == 32 ? C64[t & 15] : L == 16 ? C32[t & 7] : C16[t & 3];
+            const int c = (L == 32 ? C64[t & 15] : L == 16 ? C32[t & 7] : C16[t & 3]) * (RAW8 ? 8 : 1);
             const int2 a = win[i + 1 + t], b = win[i + L - t]; /* x[k+i-L+1+t], x[k+i-t] */
-            ia += ((uint32_t)a.x + (uint32_t)b.x) * (uint32_t)c;
-            qa += ((uint32_t)a.y + (uint32_t)b.y) * (uint32_t)c;
+            ia += pre_add((uint32_t)a.x, (uint32_t)b.x, t, steer) * (uint32_t)c;
+            qa += pre_add((uint32_t)a.y, (uint32_t)b.y, t, steer) * (uint32_t)c;
         }
-        sink(i, win[i + L - L / 2], make_int2(asr32(ia, 13), asr32(qa, 13)));
+        sink(i, win[i + L - L / 2], RAW8 ? make_int2((int)ia, (int)qa) : make_int2(asr32(ia, 13), asr32(qa, 13)));
     }
 }
 
-/* {int16 I, int16 Q} in one byte-permute */
+/* {int16 I, int16 Q} in one byte-permute: the low halves, or the high halves of sums that were left unshifted (RAW8) */
 SDRD_DEVICE uint32_t pack16p(int2 v) { return prmt((uint32_t)v.x, (uint32_t)v.y, 0x5410u); }
+SDRD_DEVICE uint32_t pack16hi(int2 v) { return prmt((uint32_t)v.x, (uint32_t)v.y, 0x7632u); }
 
 struct WarpParams {
     const uint32_t* in;   /* stream s, sample k (k >= -HIST): in[s * in_stride + k] */
@@ -438,6 +465,7 @@ struct WarpParams {
     /* TMA tensor store of the last stage (16 steps per lane: x16, x32): the output buffer as rows of 32 words; a pass of
      * the last stage is one 32 x 32-word tile = 1024 consecutive samples.  use_tma = 0: plain stores. */
     int use_tma;
+    uint32_t steer_zero, steer_one; /* 0 and 1 the compiler cannot fold: see ISteer */
     long long out_word0;  /* word index of out[0] inside the array the map describes */
     TileMap tmap;
 };
@@ -445,7 +473,7 @@ struct WarpParams {
 /* one stage of the step: reads buffer ST - 1, writes buffer ST (ST < S) or the output (ST == S) */
 template <int S, int ST>
 SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT stage, int lane, uint32_t* SDRD_RESTRICT out_step, int n_left,
-                            int wo, bool emit, const TileMap* tmap, long long tile_row0)
+                            int wo, bool emit, const TileMap* tmap, long long tile_row0, ISteer steer)
 {
     constexpr int L = ring_len(ST);
     constexpr int N = w_nstep(ST);
@@ -462,24 +490,27 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
             if (SWD == 7 && N == 8) { /* one whole swizzle row */
                 const int row = ub >> 3;
                 const int b0 = (row << 3) | (row & 7);
-                fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
+                fir_steps<L, N, PK>(src, u0, steer, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
             } else if (N == 4 && SWD == 3) { /* one chunk of 4 units */
                 const int q = ub >> 2;
                 const int b0 = 4 * q + ((q >> 1) & 3);
-                fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
+                fir_steps<L, N, PK>(src, u0, steer, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
             } else if (N == 2 && SWD == 1) { /* one pair of units */
                 const int q = ub >> 1;
                 const int b0 = 2 * q + ((q >> 2) & 1);
-                fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
+                fir_steps<L, N, PK>(src, u0, steer, [&](int i, int2 ev, int2 od) { st_unit(dst, b0 ^ i, ev, od); });
             } else {
-                fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { st_unit(dst, swz<SWD>(ub + i), ev, od); });
+                fir_steps<L, N, PK>(src, u0, steer, [&](int i, int2 ev, int2 od) { st_unit(dst, swz<SWD>(ub + i), ev, od); });
             }
         } else {
             /* last stage: pack to int16 pairs (IQSample::setReal/setImag), through the staging area, whole rows out */
             constexpr int SWO = w_sw_of_n(N);
             constexpr int UL = N / 2; /* 16-byte units per lane */
             uint32_t wd[2 * N];
-            fir_steps<L, N, PK>(src, u0, [&](int i, int2 ev, int2 od) { wd[2 * i] = pack16p(ev); wd[2 * i + 1] = pack16p(od); });
+            fir_steps<L, N, PK, SDRD_K4_RAW8 != 0>(src, u0, steer, [&](int i, int2 ev, int2 od) {
+                wd[2 * i] = pack16p(ev);
+                wd[2 * i + 1] = SDRD_K4_RAW8 ? pack16hi(od) : pack16p(od);
+            });
             /* A whole pass of 16 steps per lane is one 32 x 32-word tile of consecutive output samples: written to the
              * staging area in the 128-byte swizzle (which is the conflict-free layout the read-back form uses anyway) and
              * sent with ONE TMA tensor store -- no read-back, no STG, nothing of it on the LSU data pipe. */
@@ -543,6 +574,7 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(SDRD_GRID_CONSTANT
     uint32_t* const stage = reinterpret_cast<uint32_t*>(stage_raw + ((1024u - (unsigned)(smem_addr(stage_raw) & 1023u)) & 1023u));
     const TileMap* const tmap = (p.use_tma && w_nstep(S) == 16) ? &p.tmap : nullptr;
     const int lane = (int)threadIdx.x;
+    const ISteer steer = {p.steer_zero, p.steer_one};
     const uint32_t* in = p.in + (long long)blockIdx.y * p.in_stride;
     uint32_t* out = p.out + (long long)blockIdx.y * p.out_stride;
     const int wo = p.log2_interp;
@@ -579,11 +611,11 @@ SDRD_KERNEL(32, SDRD_K4_WARPS_PER_SM) interpolate_warp_kernel(SDRD_GRID_CONSTANT
         const int n_left = left > (WC << S) ? (WC << S) : (int)left;
         /* row (32 words) of the step's first output sample in the array the tensor map describes */
         const long long tile_row0 = (p.out_word0 + (long long)blockIdx.y * p.out_stride + ((step * WC) << wo)) >> 5;
-        warp_stage<S, 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0);
-        if (S >= 2) { SDRD_SYNCWARP(); warp_stage<S, S >= 2 ? 2 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0); }
-        if (S >= 3) { SDRD_SYNCWARP(); warp_stage<S, S >= 3 ? 3 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0); }
-        if (S >= 4) { SDRD_SYNCWARP(); warp_stage<S, S >= 4 ? 4 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0); }
-        if (S >= 5) { SDRD_SYNCWARP(); warp_stage<S, S >= 5 ? 5 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0); }
+        warp_stage<S, 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0, steer);
+        if (S >= 2) { SDRD_SYNCWARP(); warp_stage<S, S >= 2 ? 2 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0, steer); }
+        if (S >= 3) { SDRD_SYNCWARP(); warp_stage<S, S >= 3 ? 3 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0, steer); }
+        if (S >= 4) { SDRD_SYNCWARP(); warp_stage<S, S >= 4 ? 4 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0, steer); }
+        if (S >= 5) { SDRD_SYNCWARP(); warp_stage<S, S >= 5 ? 5 : 1>(buf, stage, lane, out_step, n_left, wo, emit, tmap, tile_row0, steer); }
         if (wo > S && emit) { /* interpolate64_cen: 32 zero samples after every 32 (Interpolators.cpp:370,413-603) */
             const int zq = ((1 << wo) - (1 << S)) / 4; /* zero uint4 per input sample */
             for (int i = lane; i < WC * zq; i += 32) {

@@ -844,6 +844,7 @@ void launch_interpolate(const hbi::Params& p, int S, rt::stream_t st, const Tile
      * head of odd length precedes it) */
     w.use_tma = map != nullptr && (out_word0 & 31) == 0 && (p.out_stride & 31) == 0;
     w.out_word0 = out_word0;
+    w.steer_zero = 0; w.steer_one = 1;
     if (map) w.tmap = *map;
     const long long steps = (p.n_in + hbi::WC - 1) / hbi::WC;
     long long warps = ((long long)rt::sm_count() * SDRD_K4_WARPS_PER_SM + S - 1) / S; /* per stream */
