@@ -388,6 +388,9 @@ SDRD_DEVICE uint32_t pre_add(uint32_t a, uint32_t b, int t, ISteer st)
 #ifndef SDRD_K4_RAW8
 #define SDRD_K4_RAW8 1
 #endif
+#ifndef SDRD_K4_PACKED_Q_PLAIN
+#define SDRD_K4_PACKED_Q_PLAIN 1
+#endif
 template <int L, int N, bool PACKED = false, bool RAW8 = false, class Sink>
 SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, ISteer steer, Sink&& sink)
 {
@@ -444,7 +447,9 @@ SDRD_DEVICE void fir_steps(const int2* SDRD_RESTRICT buf, int u0, ISteer steer, 
             const int c = (L == 32 ? C64[t & 15] : L == 16 ? C32[t & 7] : C16[t & 3]) * (RAW8 ? 8 : 1);
             const int2 a = win[i + 1 + t], b = win[i + L - t]; /* x[k+i-L+1+t], x[k+i-t] */
             ia += pre_add((uint32_t)a.x, (uint32_t)b.x, t, steer) * (uint32_t)c;
-            qa += pre_add((uint32_t)a.y, (uint32_t)b.y, t, steer) * (uint32_t)c;
+            /* packed input: the Q of a raw word is its high half, and ptxas folds that shift into the pre-add
+             * (LEA.HI.SX32, an ALU instruction already) -- a third operand would only add an instruction */
+            qa += ((PACKED && SDRD_K4_PACKED_Q_PLAIN) ? (uint32_t)a.y + (uint32_t)b.y : pre_add((uint32_t)a.y, (uint32_t)b.y, t, steer)) * (uint32_t)c;
         }
         sink(i, win[i + L - L / 2], RAW8 ? make_int2((int)ia, (int)qa) : make_int2(asr32(ia, 13), asr32(qa, 13)));
     }
