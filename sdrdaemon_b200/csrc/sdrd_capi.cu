@@ -824,18 +824,9 @@ extern "C" void* sdrd_int_dev_output(sdrd_int* u, size_t* stride)
 }
 
 namespace {
-#ifndef SDRD_K4_WARP
-#define SDRD_K4_WARP 1 /* 1: warp-private kernel; 0: the CTA-wide tiled kernel (kept for A/B runs) */
-#endif
 template <int NS>
 void launch_interpolate(const hbi::Params& p, int S, rt::stream_t st, const TileMap* map, long long out_word0)
 {
-#if SDRD_K4_WARP
-    if (p.log2_interp > NS) { /* interp = 6 (32 samples + 32 zeros per input sample): the tiled kernel is 7 % faster there */
-        const int tiles = (int)((p.n_in + hbi::tile_in(NS) - 1) / hbi::tile_in(NS));
-        SDRD_LAUNCH((hbi::interpolate_kernel<NS>), tiles, S, hbi::NT, hbi::smem_bytes(NS), st, p);
-        return;
-    }
     /* one wave of resident warps over all streams, each a contiguous range of 64-sample steps of one stream */
     hbi::WarpParams w{};
     w.in = p.in; w.in_stride = p.in_stride; w.out = p.out; w.out_stride = p.out_stride; w.n_in = p.n_in;
@@ -847,16 +838,15 @@ void launch_interpolate(const hbi::Params& p, int S, rt::stream_t st, const Tile
     w.steer_zero = 0; w.steer_one = 1;
     if (map) w.tmap = *map;
     const long long steps = (p.n_in + hbi::WC - 1) / hbi::WC;
-    long long warps = ((long long)rt::sm_count() * SDRD_K4_WARPS_PER_SM + S - 1) / S; /* per stream */
+    /* warps that are resident at once: the launch bound, or what fits in shared memory (1 KB per CTA is the system's) */
+    long long resident = (long long)((227 * 1024) / (hbi::w_smem_bytes(NS) + 1024));
+    if (resident > SDRD_K4_WARPS_PER_SM) resident = SDRD_K4_WARPS_PER_SM;
+    long long warps = ((long long)rt::sm_count() * resident + S - 1) / S; /* per stream */
     if (warps > steps) warps = steps;
     if (warps < 1) warps = 1;
     w.steps_per_warp = (int)((steps + warps - 1) / warps);
     warps = (steps + w.steps_per_warp - 1) / w.steps_per_warp;
     SDRD_LAUNCH((hbi::interpolate_warp_kernel<NS>), (int)warps, S, 32, hbi::w_smem_bytes(NS), st, w);
-#else
-    const int tiles = (int)((p.n_in + hbi::tile_in(NS) - 1) / hbi::tile_in(NS));
-    SDRD_LAUNCH((hbi::interpolate_kernel<NS>), tiles, S, hbi::NT, hbi::smem_bytes(NS), st, p);
-#endif
 }
 } /* namespace */
 
