@@ -266,8 +266,13 @@ int sdrd_rx_set_slice_bytes(sdrd_rx* rx, size_t min_call_bytes);
  *                    handle's page-locked accumulation buffer and returns without waiting for the device.  Whenever
  *                    the device is idle, everything accumulated so far goes out as ONE chain of copy -> decimate ->
  *                    frame + encode -> copy back: blocks are batched exactly as far as the device lags behind the
- *                    producer, so a slow producer sees single-block latency and a fast one full batches.  It waits
- *                    only when a block no longer fits behind what has accumulated (max_in samples per stream).
+ *                    producer, so a slow producer sees single-block latency and a fast one full batches.  Up to two
+ *                    chains are in flight: the copy of one runs under the kernels of the one before (a second
+ *                    chain is sent only when it is at least half as long as the one in flight).  The call waits
+ *                    only when a block no longer fits behind what has accumulated (max_in samples per stream)
+ *                    while two chains are still in flight.  The queued path alternates the decimator between two
+ *                    device input buffers: pointers obtained from sdrd_dec_dev_input / sdrd_dec_ipc_export of this
+ *                    handle's decimator are not stable across sdrd_rx_submit.
  *                    sample_bits as for sdrd_rx_process; on return it holds the decimator's output sample size.
  *   sdrd_rx_collect  hands over the frames completed so far, oldest first, layout as sdrd_rx_process (stream pitch
  *                    frame_capacity frames); wait != 0 first waits for everything submitted before the call.

@@ -263,6 +263,8 @@ struct sdrd_dec {
     int device = -1;             /* the device the handle lives on */
     size_t max_in = 0;
     uint32_t* d_in = nullptr;    /* [S][in_pitch]: HISTW history words, then the new samples */
+    uint32_t* d_in_alt = nullptr; /* a second buffer of the same shape, allocated by the queued Rx path: a chain's samples are
+                                     copied into it while the chain before still reads d_in, then the two swap roles */
     uint32_t* d_hist = nullptr;  /* [S][HISTW] */
     bool hist_in_front = false;  /* the history already sits in d_in[0 .. HISTW) (a call of >= HISTW samples moves its
                                     tail there directly); otherwise it is in d_hist and is restored at the next call */
@@ -344,6 +346,7 @@ extern "C" void sdrd_dec_destroy(sdrd_dec* d)
     SDRD_ON_DEVICE_OF(d);
     rt::sync(d->stream);
     rt::release(d->d_in);
+    rt::release(d->d_in_alt);
     rt::release(d->d_hist);
     rt::release(d->d_out);
     rt::release(d->d_state);
@@ -1359,18 +1362,24 @@ struct sdrd_rx {
         size_t n_frames = 0, taken = 0; /* per stream; frames already handed over */
         std::vector<uint8_t> data;      /* [S][n_frames][blocks_per_frame * 512] */
     };
+    struct Flight {                          /* a chain on the device */
+        int slot = 0;                        /* which q_out / q_done it owns */
+        size_t samples = 0;                  /* per stream */
+        size_t frames = 0, out_frames = 0;   /* frames completed per stream; frame pitch of q_out[slot] */
+        int bpf = 0;
+    };
     std::mutex q_mutex;
-    uint32_t* q_in[2] = {nullptr, nullptr}; /* page-locked [S][q_cap] */
-    uint8_t* q_out = nullptr;               /* page-locked [S][q_out_frames][blocks per frame * 512], grown on demand */
-    size_t q_cap = 0, q_out_frames = 0, q_out_bytes = 0;
+    uint32_t* q_in[3] = {nullptr, nullptr, nullptr}; /* page-locked [S][q_cap]: two chains in flight + the one being filled */
+    uint8_t* q_out[2] = {nullptr, nullptr};  /* page-locked [S][out_frames][blocks per frame * 512] per slot, grown on demand */
+    size_t q_out_bytes[2] = {0, 0};
+    size_t q_cap = 0;
     size_t q_fill = 0;                      /* samples per stream accumulated in q_in[q_cur] */
     size_t q_min_chain = 0;                 /* submit starts a chain only once this many samples per stream have accumulated */
     int q_cur = 0;
     unsigned q_ss = 16;                     /* sample bits of the accumulated samples */
-    bool q_inflight = false;
-    size_t q_inflight_frames = 0;
-    int q_inflight_bpf = 0;
-    rt::event_t q_done = 0;
+    std::deque<Flight> q_fly;               /* at most two, oldest first */
+    rt::event_t q_done[2] = {0, 0};
+    rt::event_t q_copied = 0;
     rt::stream_t q_stream = 0;
     std::deque<Batch> ready;
     size_t ready_frames = 0;                /* per stream */
@@ -1404,10 +1413,12 @@ extern "C" void sdrd_rx_destroy(sdrd_rx* r)
     if (r->copy_stream) rt::sync(r->copy_stream);
     if (r->q_stream) rt::sync(r->q_stream);
     delete r->crew;
-    rt::host_release(r->q_in[0]);
-    rt::host_release(r->q_in[1]);
-    rt::host_release(r->q_out);
-    rt::event_destroy(r->q_done);
+    for (int i = 0; i < 3; i++) rt::host_release(r->q_in[i]);
+    for (int i = 0; i < 2; i++) {
+        rt::host_release(r->q_out[i]);
+        rt::event_destroy(r->q_done[i]);
+    }
+    rt::event_destroy(r->q_copied);
     rt::stream_destroy(r->q_stream);
     sdrd_dec_destroy(r->dec);
     sdrd_sink_destroy(r->sink);
@@ -1421,8 +1432,8 @@ extern "C" int sdrd_rx_reset(sdrd_rx* r)
     SDRD_ON_DEVICE_OF(r);
     {
         std::lock_guard<std::mutex> lk(r->q_mutex);
-        if (r->q_inflight) rt::event_sync(r->q_done);
-        r->q_inflight = false;
+        for (const sdrd_rx::Flight& f : r->q_fly) rt::event_sync(r->q_done[f.slot]);
+        r->q_fly.clear();
         r->q_fill = 0;
         r->ready.clear();
         r->ready_frames = 0;
@@ -1562,77 +1573,138 @@ int q_prepare(sdrd_rx* r)
     sdrd_dec* d = r->dec;
     r->q_cap = d->max_in;
     const size_t in_bytes = (size_t)d->S * r->q_cap * 4;
-    if (rt::host_alloc((void**)&r->q_in[0], in_bytes) != 0 || rt::host_alloc((void**)&r->q_in[1], in_bytes) != 0 ||
-        rt::event_create(&r->q_done) != 0 || rt::stream_create(&r->q_stream) != 0) {
-        rt::host_release(r->q_in[0]);
-        rt::host_release(r->q_in[1]);
-        r->q_in[0] = r->q_in[1] = nullptr;
-        return fail_cuda("allocating the page-locked staging buffers");
+    bool ok = rt::alloc((void**)&d->d_in_alt, d->in_pitch * 4 * (size_t)d->S) == 0;
+    for (int i = 0; i < 3 && ok; i++) ok = rt::host_alloc((void**)&r->q_in[i], in_bytes) == 0;
+    for (int i = 0; i < 2 && ok; i++) ok = rt::event_create(&r->q_done[i]) == 0;
+    ok = ok && rt::event_create(&r->q_copied) == 0 && rt::stream_create(&r->q_stream) == 0;
+    /* (bytes past the valid samples are read by a launch's last chunk, results discarded: keep them defined) */
+    ok = ok && rt::fill(d->d_in_alt, 0, d->in_pitch * 4 * (size_t)d->S, r->q_stream) == 0 && rt::sync(r->q_stream) == 0;
+    if (!ok) {
+        for (int i = 0; i < 3; i++) {
+            rt::host_release(r->q_in[i]);
+            r->q_in[i] = nullptr;
+        }
+        rt::release(d->d_in_alt);
+        d->d_in_alt = nullptr;
+        return fail_cuda("allocating the buffers of the queued path");
     }
     return 0;
 }
 
-/* under q_mutex: the chain in flight has completed -> its frames join `ready` */
+/* under q_mutex: the oldest chain in flight has completed -> its frames join `ready` */
 void q_harvest(sdrd_rx* r)
 {
-    if (!r->q_inflight) return;
-    r->q_inflight = false;
-    if (!r->q_inflight_frames) return;
+    if (r->q_fly.empty()) return;
+    const sdrd_rx::Flight f = r->q_fly.front();
+    r->q_fly.pop_front();
+    if (!f.frames) return;
     sdrd_rx::Batch b;
-    b.blocks_per_frame = r->q_inflight_bpf;
-    b.n_frames = r->q_inflight_frames;
+    b.blocks_per_frame = f.bpf;
+    b.n_frames = f.frames;
     const size_t per_stream = b.n_frames * (size_t)b.blocks_per_frame * SDRD_UDPSIZE;
     b.data.resize((size_t)r->dec->S * per_stream);
     for (int s = 0; s < r->dec->S; s++)
-        memcpy(&b.data[(size_t)s * per_stream], r->q_out + (size_t)s * r->q_out_frames * (size_t)b.blocks_per_frame * SDRD_UDPSIZE, per_stream);
+        memcpy(&b.data[(size_t)s * per_stream], r->q_out[f.slot] + (size_t)s * f.out_frames * (size_t)b.blocks_per_frame * SDRD_UDPSIZE,
+               per_stream);
     r->ready_frames += b.n_frames;
     r->ready.push_back(std::move(b));
 }
+/* under q_mutex: harvest every chain that has completed (asks the driver once per chain in flight) */
+void q_poll(sdrd_rx* r)
+{
+    while (!r->q_fly.empty() && rt::event_done(r->q_done[r->q_fly.front().slot]) != 0) q_harvest(r);
+}
+/* under q_mutex: wait for the oldest chain in flight */
+int q_wait_oldest(sdrd_rx* r)
+{
+    if (r->q_fly.empty()) return 0;
+    SDRD_TRY(rt::event_sync(r->q_done[r->q_fly.front().slot]), "waiting for the chain in flight");
+    q_harvest(r);
+    return 0;
+}
 
-/* under q_mutex, nothing in flight: send everything accumulated as one chain, no synchronisation */
+/* under q_mutex, at most one chain in flight: send everything accumulated as one chain, no synchronisation.
+ *
+ * Two chains overlap on the device: the samples of chain k go into the decimator's ALTERNATE input buffer on the copy
+ * stream while chain k - 1 (copy done, kernels running on q_stream) still reads the current one; then, in q_stream order,
+ * the history chain k - 1 left at the front of its buffer is carried over and the two buffers swap roles.  Chain k - 2,
+ * the last user of the alternate buffer, has completed before chain k is sent (at most two in flight).  Everything
+ * behind the copy -- decimator state, the sink's pending samples, the datagram images -- is single and ordered by
+ * q_stream.  (Cutting ONE chain into pieces instead was measured and gains nothing: behind its copy a piece costs
+ * ~60 us of dependent launches whatever its size.) */
 int q_launch(sdrd_rx* r)
 {
     sdrd_dec* d = r->dec;
     const size_t n = r->q_fill;
     if (!n) return 0;
+    if (r->q_fly.size() >= 2) return fail(SDRD_ECUDA, "internal: two chains already in flight");
     rt::stream_t st = r->q_stream;
-    /* room for the frames this chain will complete (nothing is in flight: the buffer is free) */
+    sdrd_rx::Flight f;
+    f.slot = r->q_fly.empty() ? 0 : 1 - r->q_fly.back().slot;
+    f.samples = n;
+    /* room for the frames this chain will complete.  (will_close counts from the sink's state, which already includes
+     * the chain in flight: sink_run advances it at launch time.) */
     {
         const size_t will_close = sdrd_sink_frames_for(r->sink, dec_out_count(d, n));
         const size_t need = (size_t)d->S * will_close * (size_t)(128 + r->sink->nb_fec) * SDRD_UDPSIZE;
-        if (need > r->q_out_bytes) {
-            rt::host_release(r->q_out);
-            r->q_out = nullptr;
-            r->q_out_bytes = 0;
-            if (rt::host_alloc((void**)&r->q_out, need) != 0) return fail_cuda("allocating the page-locked output buffer");
-            r->q_out_bytes = need;
+        if (need > r->q_out_bytes[f.slot]) {
+            rt::host_release(r->q_out[f.slot]);
+            r->q_out[f.slot] = nullptr;
+            r->q_out_bytes[f.slot] = 0;
+            if (rt::host_alloc((void**)&r->q_out[f.slot], need) != 0) return fail_cuda("allocating the page-locked output buffer");
+            r->q_out_bytes[f.slot] = need;
         }
-        r->q_out_frames = will_close;
+        f.out_frames = will_close;
     }
-    /* (Slicing the chain so that the copy of one piece overlaps the kernels of the one before, as sdrd_rx_process does
-     * with large calls, was measured and gains nothing here: behind the copy a piece costs ~60 us of dependent
-     * launches whatever its size -- 4 pieces 9.1, 2 pieces 8.0, one piece 8.2 us per 65536-sample block.) */
-    SDRD_TRY(rt::copy2d(d->d_in + HISTW, d->in_pitch * 4, r->q_in[r->q_cur], r->q_cap * 4, n * 4, (size_t)d->S, rt::H2D, st),
+    SDRD_TRY(rt::copy2d(d->d_in_alt + HISTW, d->in_pitch * 4, r->q_in[r->q_cur], r->q_cap * 4, n * 4, (size_t)d->S, rt::H2D, r->copy_stream),
              "copy samples to device");
+    SDRD_TRY(rt::event_record(r->q_copied, r->copy_stream), "record copy event");
+    SDRD_TRY(rt::stream_wait(st, r->q_copied), "wait for copy");
+    if (d->hist_in_front)
+        SDRD_TRY(rt::copy2d(d->d_in_alt, d->in_pitch * 4, d->d_in, d->in_pitch * 4, HISTW * 4, (size_t)d->S, rt::D2D, st), "carry the history over");
+    std::swap(d->d_in, d->d_in_alt);
     size_t n_out = 0, nf = 0;
     unsigned ss = r->q_ss;
     if (int rc = dec_run(d, n, &n_out, &ss, st)) return rc;
     rx_set_sample_size(r, r->q_ss, ss);
     if (int rc = sink_run(r->sink, d->d_out, d->out_pitch, n_out, &nf, st)) return rc;
-    const int bpf = 128 + r->sink->nb_fec;
+    f.bpf = 128 + r->sink->nb_fec;
     if (nf) {
-        const size_t frame_bytes = (size_t)bpf * SDRD_UDPSIZE;
-        SDRD_TRY(rt::copy2d(r->q_out, r->q_out_frames * frame_bytes, r->sink->d_dgrams, r->sink->last_dgram_stride * 4, nf * frame_bytes,
+        const size_t frame_bytes = (size_t)f.bpf * SDRD_UDPSIZE;
+        SDRD_TRY(rt::copy2d(r->q_out[f.slot], f.out_frames * frame_bytes, r->sink->d_dgrams, r->sink->last_dgram_stride * 4, nf * frame_bytes,
                             (size_t)d->S, rt::D2H, st),
                  "copy datagrams to host");
     }
-    SDRD_TRY(rt::event_record(r->q_done, st), "record completion");
-    r->q_inflight = true;
-    r->q_inflight_frames = nf;
-    r->q_inflight_bpf = bpf;
-    r->q_cur ^= 1;
+    SDRD_TRY(rt::event_record(r->q_done[f.slot], st), "record completion");
+    f.frames = nf;
+    r->q_fly.push_back(f);
+    r->q_cur = (r->q_cur + 1) % 3;
     r->q_fill = 0;
     r->q_launches++;
+    return 0;
+}
+
+/* under q_mutex: may what has accumulated go now?  An idle device takes it at once (latency).  Sending a chain costs
+ * the submitting thread ~25 us of driver calls whatever its length, so next to a chain in flight a second one goes
+ * only when that cost is small against its copy -- at least 1 MB of samples -- and when it is at least as long as the
+ * one in flight: a device that lags gets longer chains, not more of them (measured with the greedy rule "whenever
+ * fewer than two are in flight": 1.3 blocks per chain and 27 us per 65536-sample block from a single thread). */
+bool q_may_launch(const sdrd_rx* r, size_t fill)
+{
+    if (!fill || fill < r->q_min_chain || r->q_fly.size() >= 2) return false;
+    if (r->q_fly.empty()) return true;
+    return fill >= r->q_fly.back().samples && (size_t)r->dec->S * fill * 4 >= ((size_t)1 << 20);
+}
+/* under q_mutex: everything submitted so far through the device and into `ready` */
+int q_flush(sdrd_rx* r)
+{
+    while (!r->q_fly.empty() || r->q_fill) {
+        if (r->q_fill && r->q_fly.size() < 2) {
+            if (int rc = q_launch(r)) return rc;
+        } else if (int rc = q_wait_oldest(r)) {
+            return rc;
+        }
+    }
     return 0;
 }
 } /* namespace */
@@ -1642,15 +1714,7 @@ static int q_drain(sdrd_rx* r)
 {
     std::unique_lock<std::mutex> lk(r->q_mutex);
     if (!r->q_in[0]) return 0;
-    for (int round = 0; round < 2; round++) {
-        if (r->q_inflight) {
-            SDRD_TRY(rt::event_sync(r->q_done), "waiting for the chain in flight");
-            q_harvest(r);
-        }
-        if (r->q_fill)
-            if (int rc = q_launch(r)) return rc;
-    }
-    return 0;
+    return q_flush(r);
 }
 
 extern "C" int sdrd_rx_submit(sdrd_rx* r, const int16_t* iq_in, size_t n_in, size_t in_stride, unsigned* sample_bits)
@@ -1669,16 +1733,10 @@ extern "C" int sdrd_rx_submit(sdrd_rx* r, const int16_t* iq_in, size_t n_in, siz
     std::unique_lock<std::mutex> lk(r->q_mutex);
     if (int rc = q_prepare(r)) return rc;
     if (r->ready_frames > 65536) return fail(SDRD_ERANGE, "too many completed frames waiting: call sdrd_rx_collect");
-    /* asking the driver whether the chain in flight has completed costs microseconds: only when the answer matters,
-     * i.e. when this block would let a new chain start (or would not fit behind what has accumulated) */
-    const bool may_start = r->q_fill + n_in >= r->q_min_chain || r->q_fill + n_in > r->q_cap;
-    if (r->q_inflight && may_start && rt::event_done(r->q_done) != 0) q_harvest(r);
     /* a block that does not fit behind what has accumulated, or that has another sample size, starts a new chain */
     if (r->q_fill && (r->q_fill + n_in > r->q_cap || ss_in != r->q_ss)) {
-        if (r->q_inflight) {
-            SDRD_TRY(rt::event_sync(r->q_done), "waiting for the chain in flight");
-            q_harvest(r);
-        }
+        if (r->q_fly.size() >= 2)
+            if (int rc = q_wait_oldest(r)) return rc;
         if (int rc = q_launch(r)) return rc;
     }
     r->q_ss = ss_in;
@@ -1689,7 +1747,10 @@ extern "C" int sdrd_rx_submit(sdrd_rx* r, const int16_t* iq_in, size_t n_in, siz
         else staging_copy(to, from, n_in * 4);
     }
     r->q_fill += n_in;
-    if (!r->q_inflight && r->q_fill >= r->q_min_chain)
+    /* asking the driver whether a chain has completed costs microseconds: only when the answer matters, i.e. when
+     * what has accumulated is long enough to go but the chains in flight, as last seen, stand in its way */
+    if (r->q_fill >= r->q_min_chain && !r->q_fly.empty() && !q_may_launch(r, r->q_fill)) q_poll(r);
+    if (q_may_launch(r, r->q_fill))
         if (int rc = q_launch(r)) return rc;
     if (sample_bits) { /* what the decimator makes of ss_in (Decimators.cpp:408-409,515): known without running it */
         int norm, trunk;
@@ -1708,20 +1769,12 @@ extern "C" int sdrd_rx_collect(sdrd_rx* r, uint8_t* datagrams, size_t frame_capa
     if (n_frames_p) *n_frames_p = 0;
     std::unique_lock<std::mutex> lk(r->q_mutex);
     if (wait) {
-        /* everything submitted so far: the chain in flight, then what has accumulated behind it */
-        for (int round = 0; round < 2; round++) {
-            if (r->q_inflight) {
-                SDRD_TRY(rt::event_sync(r->q_done), "waiting for the chain in flight");
-                q_harvest(r);
-            }
-            if (r->q_fill) {
-                if (int rc = q_launch(r)) return rc;
-            }
-        }
-    } else if (r->ready.empty() && r->q_inflight && rt::event_done(r->q_done) != 0) {
-        /* (frames already waiting are handed over without asking the driver about the chain in flight) */
-        q_harvest(r);
-        if (r->q_fill && r->q_fill >= r->q_min_chain)
+        /* everything submitted so far: the chains in flight, then what has accumulated behind them */
+        if (int rc = q_flush(r)) return rc;
+    } else if (r->ready.empty() && !r->q_fly.empty()) {
+        /* (frames already waiting are handed over without asking the driver about the chains in flight) */
+        q_poll(r);
+        if (q_may_launch(r, r->q_fill))
             if (int rc = q_launch(r)) return rc;
     }
     if (r->ready.empty()) return 0;

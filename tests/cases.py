@@ -452,6 +452,48 @@ def check_sink_frame_clock(lib, ob, splits, rate=48000, F=4, base=(1700000000, 9
     sk.close()
 
 
+def check_rx_queued_mixed(lib, ob, M=3, F=8, S=2, blk=16384, seed=909):
+    """The queued and the synchronous entry points taking turns on one handle (the queued path moves the decimator
+    between two input buffers and keeps up to two chains in flight; the synchronous calls drain it first): the datagram
+    stream, in order, must be the oracle's for the whole sample stream."""
+    rng = np.random.default_rng(seed)
+    plan = [("q", 5), ("s", 3), ("q", 1), ("q", 7), ("s", 1), ("s", 2), ("q", 9), ("s", 4), ("q", 3)]
+    total = sum(n for _, n in plan) * blk
+    x = rand_iq(rng, (S, total), 16)
+    rx = capi.Rx(M, n_streams=S, max_in=blk * 4, n_fec=F, lib=lib)
+    got = []
+
+    def drain():
+        while True:
+            g = rx.collect(5, wait=True)
+            if not g.shape[1]:
+                return
+            got.append(g)
+
+    pos = 0
+    for kind, n in plan:
+        if kind == "q":
+            for b in range(n):
+                rx.submit(x[:, pos:pos + blk])
+                pos += blk
+        else:
+            drain()                                  # keep the order: queued frames first
+            g = rx.process(x[:, pos:pos + n * blk])
+            pos += n * blk
+            if g.shape[1]:
+                got.append(g)
+    drain()
+    g = np.concatenate(got, axis=1)
+    for s in range(S):
+        y, sso = ob.Decimator(M).process(x[s], 16)
+        k = ob.Sink(n_fec=F, sample_bits=sso, sample_bytes=(sso - 1) // 8 + 1)
+        k.write(y)
+        want = np.stack(k.frames)
+        assert g[s].shape == want.shape, (g[s].shape, want.shape)
+        assert np.array_equal(g[s], want), f"queued + synchronous calls, stream {s}: datagrams differ from the oracle"
+    rx.close()
+
+
 def check_rx_queued(lib, ob, M, F, S, blk, n_blk, max_blocks=8, threaded=False, bits=16, seed=808, helpers=0):
     """sdrd_rx_submit / sdrd_rx_collect: blocks of `blk` samples submitted one after the other (batched on the way as
     far as the device lags), frames collected in between or from a second thread -- the datagram stream must be the
