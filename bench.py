@@ -455,6 +455,13 @@ def run_interp(args):
     n_out = n_in << M
     peak, peak_src = measured_peaks()
     alg = 4 * n_in + 4 * n_out
+    k4_traffic, k4_traffic_src = None, None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "k4_traffic.json")))
+        if t.get("log2_interp") == M and t.get("samples_in_per_launch") == n_in:
+            k4_traffic, k4_traffic_src = t.get("dram_bytes_per_launch"), t.get("source")
+    except Exception:
+        k4_traffic = None
     print(json.dumps({"metric": metric, "value": round(n_out / ms / 1e3, 1), "unit": UNIT, "n_gpus": 1, "steps": steps,
                       "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "dtype": "int32", "data": "synthetic",
                       "config": {"workload": f"tx (SURVEY 8f-1): {nfr} superframes ({n_in} samples) interpolated by {1 << M}, "
@@ -462,8 +469,8 @@ def run_interp(args):
                                  "l2": "outputs larger than L2 (no flush needed)"},
                       "gpu_launches": int(u.launches - l0), "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
                       "roofline": {"bound": "hbm", "kernel": f"hbi::interpolate_warp_kernel<{min(M, 5)}> (K4)", "achieved": round(alg / ms / 1e6, 1),
-                                   "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": None,
-                                   "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}}), flush=True)
+                                   "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4), "traffic": k4_traffic,
+                                   "traffic_source": k4_traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}}), flush=True)
 
 
 def bind_near_gpu(local: int):
