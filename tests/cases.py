@@ -494,6 +494,47 @@ def check_rx_queued_mixed(lib, ob, M=3, F=8, S=2, blk=16384, seed=909):
     rx.close()
 
 
+def check_rx_queued_reconfigure(lib, ob, F=4, S=2, blk=8192, seed=911):
+    """Downsampler::configure between queued blocks (the decimation changes while the sender keeps framing): the queued
+    path alternates the decimator between two input buffers, and configure derives the stage states from the raw
+    history wherever the last chain left it.  plan = [(log2_decim, blocks)]; the chain is drained before each change."""
+    rng = np.random.default_rng(seed)
+    plan = [(2, 6), (4, 5), (1, 3), (5, 8), (3, 1), (3, 4), (6, 8)]
+    total = sum(n for _, n in plan) * blk
+    x = rand_iq(rng, (S, total), 16)
+    rx = capi.Rx(plan[0][0], n_streams=S, max_in=blk * 4, n_fec=F, lib=lib)
+    refs = [ob.Decimator(plan[0][0]) for _ in range(S)]
+    sinks = [ob.Sink(n_fec=F, sample_bits=16, sample_bytes=2) for _ in range(S)]
+    got = []
+    pos = 0
+    for M, n in plan:
+        while True:                                   # everything submitted so far, then change the decimation
+            g = rx.collect(6, wait=True)
+            if not g.shape[1]:
+                break
+            got.append(g)
+        lib.check(lib.sdrd_dec_configure(rx.dec_handle, M, capi.FC_CENTER))
+        for s in range(S):
+            refs[s].configure(M)
+        for b in range(n):
+            rx.submit(x[:, pos:pos + blk])
+            for s in range(S):
+                y, _ = refs[s].process(x[s, pos:pos + blk], 16)
+                sinks[s].write(y)
+            pos += blk
+    while True:
+        g = rx.collect(6, wait=True)
+        if not g.shape[1]:
+            break
+        got.append(g)
+    g = np.concatenate(got, axis=1)
+    for s in range(S):
+        want = np.stack(sinks[s].frames)
+        assert g[s].shape == want.shape, (g[s].shape, want.shape)
+        assert np.array_equal(g[s], want), f"queued path across configure, stream {s}: datagrams differ from the oracle"
+    rx.close()
+
+
 def check_rx_queued(lib, ob, M, F, S, blk, n_blk, max_blocks=8, threaded=False, bits=16, seed=808, helpers=0):
     """sdrd_rx_submit / sdrd_rx_collect: blocks of `blk` samples submitted one after the other (batched on the way as
     far as the device lags), frames collected in between or from a second thread -- the datagram stream must be the

@@ -215,6 +215,7 @@ def test_rx_queued(emu_lib, oracle):
     cases.check_rx_queued(emu_lib, oracle, M=1, F=0, S=1, blk=8192, n_blk=10, threaded=True)
     cases.check_rx_queued(emu_lib, oracle, M=3, F=8, S=2, blk=65536, n_blk=12, max_blocks=4, helpers=2)
     cases.check_rx_queued_mixed(emu_lib, oracle)
+    cases.check_rx_queued_reconfigure(emu_lib, oracle)
 
 
 def test_ipc_feed_entry_points(emu_lib, oracle):

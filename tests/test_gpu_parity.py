@@ -446,4 +446,5 @@ def test_rx_queued(gpu_lib, oracle):
     cases.check_rx_queued(gpu_lib, oracle, M=4, F=16, S=1, blk=65536, n_blk=96, max_blocks=16, helpers=2)
     cases.check_rx_queued(gpu_lib, oracle, M=3, F=8, S=2, blk=65536, n_blk=24, max_blocks=4, helpers=3, threaded=True)
     cases.check_rx_queued_mixed(gpu_lib, oracle)
+    cases.check_rx_queued_reconfigure(gpu_lib, oracle)
     cases.check_rx_queued_mixed(gpu_lib, oracle, M=4, F=16, S=1, blk=65536, seed=910)
