@@ -249,6 +249,9 @@ SDRD_DEVICE void enc_matvec_pass(const uint32_t* SDRD_RESTRICT img, const uint32
  * item i is being encoded out of one image buffer, the samples of item i + gridDim.x arrive in the other
  * through cp.async (4-byte LDGSTS: the 127-sample blocks are neither 16-byte aligned nor a multiple of 16
  * bytes long, which rules the bulk copy out). */
+#ifndef SDRD_K2_BULK_ORIGINALS
+#define SDRD_K2_BULK_ORIGINALS 1
+#endif
 SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
 {
     SDRD_DYN_SMEM(smem_raw);
@@ -322,6 +325,10 @@ SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
     if (it < n_items) gather(it, img2[0]);
     for (; it < n_items; it += gridDim.x, cur ^= 1) {
         cp_async_wait_all();
+#if SDRD_K2_BULK_ORIGINALS
+        fence_proxy_async_smem();                 /* this thread's share of image `cur`, visible to the bulk copy below */
+        if (tid == 0) tma_store_wait_read();      /* the bulk copy out of image `cur ^ 1` (previous item) has read it */
+#endif
         __syncthreads(); /* image `cur` complete; everybody is done with image `cur ^ 1` */
         if (it + gridDim.x < n_items) gather(it + gridDim.x, img2[cur ^ 1]);
         const uint32_t* img = img2[cur];
@@ -331,10 +338,19 @@ SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
         uint32_t* out = nullptr;
         if (p.mode == 0) {
             out = p.dgrams + (long long)s * p.dgram_stride + (long long)f * (128 + p.F) * ROW_WORDS;
-            /* the 128 original datagrams leave as they are */
+            /* the 128 original datagrams leave as they are: 64 KB, contiguous on both sides */
+#if SDRD_K2_BULK_ORIGINALS
+            /* ... as bulk copies by the async engine (UBLKCP shared -> global), under the products below */
+            if (tid == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) tma_store_1d(out + q * (IMG_WORDS / 4), img + q * (IMG_WORDS / 4), IMG_WORDS);
+                tma_store_commit();
+            }
+#else
             const uint4* src4 = reinterpret_cast<const uint4*>(img);
             uint4* dst4 = reinterpret_cast<uint4*>(out);
             for (int k = tid; k < IMG_WORDS / 4; k += ENC_NT) dst4[k] = src4[k];
+#endif
         }
         for (int row0 = 0; row0 < p.F; row0 += RB) {
             const int nrows = p.F - row0 < RB ? p.F - row0 : RB;
@@ -364,6 +380,9 @@ SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
         }
     }
     cp_async_wait_all();
+#if SDRD_K2_BULK_ORIGINALS
+    if (tid == 0) tma_store_wait_read(); /* the images stay allocated until the last bulk copy has read them */
+#endif
 }
 
 /* ============================================================================ decode ==== */
