@@ -259,12 +259,6 @@ SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
     Smem sm = carve(smem_raw, 2 * p.cstride); /* the coefficient area holds full words here */
     uint32_t* const img2[2] = {sm.img, reinterpret_cast<uint32_t*>(sm.extra)};
     uint32_t* const coef = reinterpret_cast<uint32_t*>(sm.coefT); /* [cstride rows][128 blocks] */
-    load_tables(sm, p.tab, tid);
-    /* the Cauchy rows 128 .. 128 + F - 1 as table offsets */
-    for (int k = tid; k < 128 * p.cstride; k += ENC_NT) {
-        const int r = k >> 7;
-        coef[k] = (uint32_t)TAB_ENTRY * (r < p.F ? (uint32_t)p.tab.cauchy[k] : 0u);
-    }
     const long long n_items = (long long)p.n_frames * p.n_streams;
 
     /* request the payload words of work item `it` into image `im`, write its header words */
@@ -320,9 +314,16 @@ SDRD_KERNEL(ENC_NT, 1) encode_kernel(EncParams p)
         cp_async_commit();
     };
 
+    /* the first item's samples are requested before the tables are loaded: their way from HBM runs under that */
     long long it = blockIdx.x;
     int cur = 0;
     if (it < n_items) gather(it, img2[0]);
+    load_tables(sm, p.tab, tid);
+    /* the Cauchy rows 128 .. 128 + F - 1 as table offsets */
+    for (int k = tid; k < 128 * p.cstride; k += ENC_NT) {
+        const int r = k >> 7;
+        coef[k] = (uint32_t)TAB_ENTRY * (r < p.F ? (uint32_t)p.tab.cauchy[k] : 0u);
+    }
     for (; it < n_items; it += gridDim.x, cur ^= 1) {
         cp_async_wait_all();
 #if SDRD_K2_BULK_ORIGINALS
