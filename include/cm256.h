@@ -35,13 +35,28 @@ extern "C" {
 #endif
 /* cm256_init() of the C library: 0 when the codec can be used -- here: when an sm_100 device is present */
 static inline int cm256_init(void) { return sdrd_device_count() > 0 ? 0 : -1; }
+/* -DSDRD_CM256_TRACE: a call that fails says why on stderr (cm256 itself only returns non-zero; the reference's
+ * sender then stops transmitting without a reason, UDPSinkFEC.cpp:246-250) */
+#ifdef SDRD_CM256_TRACE
+#include <stdio.h>
+#define SDRD_CM256_REPORT(what, rc)                                                       \
+    do {                                                                                  \
+        if (rc) fprintf(stderr, "cm256 (sdrd_b200) %s: %s\n", what, sdrd_last_error());   \
+    } while (0)
+#else
+#define SDRD_CM256_REPORT(what, rc) ((void)0)
+#endif
 static inline int cm256_encode(cm256_encoder_params params, cm256_block* originals, void* recoveryBlocks)
 {
-    return sdrd_cm256_encode_blocks(params, originals, recoveryBlocks);
+    const int rc = sdrd_cm256_encode_blocks(params, originals, recoveryBlocks);
+    SDRD_CM256_REPORT("encode", rc);
+    return rc;
 }
 static inline int cm256_decode(cm256_encoder_params params, cm256_block* blocks)
 {
-    return sdrd_cm256_decode_blocks(params, blocks);
+    const int rc = sdrd_cm256_decode_blocks(params, blocks);
+    SDRD_CM256_REPORT("decode", rc);
+    return rc;
 }
 #ifdef __cplusplus
 }

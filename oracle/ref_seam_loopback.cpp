@@ -22,12 +22,16 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <array>
 #include <atomic>
 #include <cstdlib>
+#include <deque>
 #include <iostream>
+#include <mutex>
 #include <new>
 #include <sstream>
 #include <string>
+#include <thread>
 
 #include "SDRdaemonFECBuffer.h"
 #include "UDPSinkFEC.h"
@@ -73,8 +77,29 @@ int main(int argc, char** argv)
     sink->setSampleBytes(2);
     sink->setSampleBits(16);
     sink->setNbBlocksFEC(n_fec);
-    sink->setTxDelay(0);
+    /* the sender paces itself a little (the reference's own knob, usleep per datagram) ... */
+    sink->setTxDelay(5);
     SDRdaemonFECBuffer* fecbuf = new SDRdaemonFECBuffer();
+
+    /* ... and the socket is emptied by a thread of its own into a queue: a datagram lost in the kernel's receive buffer
+     * while the main thread sits in a decode call (the first GPU call of the process takes a while) would be an
+     * erasure the test did not ask for */
+    std::mutex q_mutex;
+    std::deque<std::array<uint8_t, 512>> queue;
+    std::atomic<bool> rx_stop(false);
+    std::thread rx_thread([&] {
+        pollfd p = {fd, POLLIN, 0};
+        while (!rx_stop.load()) {
+            if (poll(&p, 1, 5) <= 0) continue;
+            uint8_t buf[2048];
+            if (recv(fd, buf, sizeof(buf), 0) == 512) {
+                std::array<uint8_t, 512> d;
+                memcpy(d.data(), buf, 512);
+                std::lock_guard<std::mutex> lk(q_mutex);
+                queue.push_back(d);
+            }
+        }
+    });
 
     std::vector<int16_t> frame(2 * seam::FRAME_SAMPLES), want(2 * seam::FRAME_SAMPLES);
     std::vector<uint8_t> data(128 * 512);
@@ -100,10 +125,26 @@ int main(int argc, char** argv)
         head = fi;
     };
     auto drain = [&](int timeout_ms) {
-        pollfd p = {fd, POLLIN, 0};
-        while (poll(&p, 1, timeout_ms) > 0) {
-            uint8_t buf[2048];
-            if (recv(fd, buf, sizeof(buf), 0) == 512) feed(buf);
+        for (int waited = 0;;) {
+            std::array<uint8_t, 512> d;
+            bool have = false;
+            {
+                std::lock_guard<std::mutex> lk(q_mutex);
+                if (!queue.empty()) {
+                    d = queue.front();
+                    queue.pop_front();
+                    have = true;
+                }
+            }
+            if (have) {
+                feed(d.data());
+                waited = 0;
+            } else if (waited >= timeout_ms) {
+                return;
+            } else {
+                usleep(1000);
+                waited++;
+            }
         }
     };
     /* the Tx thread lags one superframe behind the writer (UDPSinkFEC.cpp:160,208) and the receiver emits a frame
@@ -120,7 +161,17 @@ int main(int argc, char** argv)
             drain(0);
         }
     }
-    for (int tries = 0; tries < 300 && checked < n_frames; tries++) drain(10);
+    /* The sender's first cm256_encode may be the first GPU call of the process: context creation and module load take
+     * from a fraction of a second to several seconds on a freshly started box.  Wait for the first datagram for as long
+     * as a minute; once they flow, give up only after five seconds of silence. */
+    for (int idle = 0, waited = 0; checked < n_frames && waited < 9000; waited++) {
+        const int before = datagrams;
+        drain(10);
+        idle = datagrams != before ? 0 : idle + 1;
+        if (datagrams == 0 ? waited >= 6000 : idle >= 500) break;
+    }
+    rx_stop.store(true);
+    rx_thread.join();
     sink->~UDPSinkFEC();
     operator delete(mem);
     delete fecbuf;

@@ -218,13 +218,22 @@ void shift_rule(unsigned ss, int log2_decim, int* norm_shift, int* trunk_shift, 
     *ss_out = ss + (unsigned)log2_decim - trunk;
 }
 
-/* persistent encode grid: one CTA per SM (two image buffers fill the shared memory), equal shares */
-int enc_grid(long long items)
+/* persistent encode grid: equal shares over one 512-thread CTA per SM, or -- batches of more than one frame per SM,
+ * when two fit -- over two 256-thread CTAs per SM (fec::EncShape) */
+bool enc_two(long long items, int cstride) { return items > rt::sm_count() && fec::enc_two_fits(cstride); }
+int enc_grid(long long items, bool two)
 {
-    const long long sms = rt::sm_count();
-    if (items <= sms) return (int)items;
-    const long long per = (items + sms - 1) / sms;
+    const long long slots = (long long)rt::sm_count() * (two ? 2 : 1);
+    if (items <= slots) return (int)items;
+    const long long per = (items + slots - 1) / slots;
     return (int)((items + per - 1) / per);
+}
+void launch_encode(const fec::EncParams& p, long long items, rt::stream_t st)
+{
+    if (enc_two(items, p.cstride))
+        SDRD_LAUNCH(fec::encode_kernel<true>, enc_grid(items, true), 1, fec::EncShape<true>::NT, fec::enc_smem_bytes(p.cstride, true), st, p);
+    else
+        SDRD_LAUNCH(fec::encode_kernel<false>, enc_grid(items, false), 1, fec::EncShape<false>::NT, fec::enc_smem_bytes(p.cstride, false), st, p);
 }
 
 /* persistent decode grid: SDRD_K3_CTAS_PER_SM two-warp CTAs per SM, each walking frames blockIdx.x, + gridDim.x, .. */
@@ -1126,7 +1135,7 @@ static int sink_run(sdrd_sink* k, const uint32_t* samples, size_t stride, size_t
         p.tab = k->tab;
         p.n_frames = (int)n_frames;
         p.n_streams = k->S;
-        SDRD_LAUNCH(fec::encode_kernel, enc_grid((long long)n_frames * k->S), 1, fec::ENC_NT, fec::enc_smem_bytes(p.cstride), st, p);
+        launch_encode(p, (long long)n_frames * k->S, st);
         k->launches++;
         if (!SDRD_LAUNCH_OK()) return fail_cuda("encode kernel launch");
     }
@@ -1922,7 +1931,7 @@ extern "C" int sdrd_cm256_encode_dev(const uint8_t* originals, size_t block_pitc
     rt::stream_t st = (rt::stream_t)cuda_stream;
     p.n_frames = n_frames;
     p.n_streams = 1;
-    SDRD_LAUNCH(fec::encode_kernel, enc_grid(n_frames), 1, fec::ENC_NT, fec::enc_smem_bytes(p.cstride), st, p);
+    launch_encode(p, (long long)n_frames, st);
     if (!SDRD_LAUNCH_OK()) return fail_cuda("encode kernel launch");
     return 0;
 }

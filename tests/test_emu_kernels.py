@@ -102,6 +102,15 @@ def test_sink_framing_and_encode(emu_lib, oracle, F):
     cases.check_sink(emu_lib, oracle, F, x, [0, 1000, 1000 + cases.FRAME, n])
 
 
+def test_sink_many_frames_per_call(emu_lib, oracle):
+    """More frames in one call than there are SMs: the encode kernel then runs in its two-CTAs-per-SM shape
+    (fec::EncShape<true>: 256 threads, one image, 16 columns per warp) -- same datagrams."""
+    rng = np.random.default_rng(477)
+    S = 151
+    x = cases.rand_iq(rng, (S, cases.FRAME + 300))
+    cases.check_sink(emu_lib, oracle, 3, x, [0, 200, cases.FRAME + 300])
+
+
 def test_cm256_encode_raw(emu_lib, oracle):
     from sdrdaemon_b200 import capi
 

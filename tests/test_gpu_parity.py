@@ -192,6 +192,16 @@ def test_sink_framing_and_encode(gpu_lib, oracle, F):
     cases.check_sink(gpu_lib, oracle, F, x, [0, 1000, 1000 + cases.FRAME, 3 * cases.FRAME + 5, n])
 
 
+@pytest.mark.parametrize("F", [1, 16, 33])
+def test_sink_many_frames_per_call(gpu_lib, oracle, F):
+    """More frames in one call than there are SMs: the two-CTAs-per-SM shape of the encode kernel (fec::EncShape<true>);
+    149 .. 2 x 148 + 1 work items cover its grid rounding."""
+    rng = np.random.default_rng(4770 + F)
+    for S, nfr in ((149, 1), (99, 3), (150, 2)):
+        x = cases.rand_iq(rng, (S, nfr * cases.FRAME + 300))
+        cases.check_sink(gpu_lib, oracle, F, x, [0, 200, nfr * cases.FRAME + 300])
+
+
 def test_sink_known_answers(gpu_lib):
     """Framing pins of SURVEY 8c(3): 16129 samples per frame, header bytes, CRC-32 of the meta data."""
     import zlib

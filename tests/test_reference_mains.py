@@ -112,13 +112,32 @@ def check_tx_main(kind, oracle, port, tmp_path):
     rng = np.random.default_rng(91)
     x, frames = cases.make_frames(oracle, rng, n_frames + 1, n_fec)
     sock = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
-    time.sleep(2.5)  # FileSink::start of the reference mirror sleeps; the socket is bound before that
+    # the program binds its socket, then FileSink::start of the reference mirror sleeps: wait for the port, then for that
+    hexport = f":{port:04X} "
+    for _ in range(1200):
+        try:
+            if any(hexport in line for line in open("/proc/net/udp")):
+                break
+        except OSError:
+            break
+        if p.poll() is not None:
+            break
+        time.sleep(0.05)
+    time.sleep(2.5)
     try:
         for f in range(n_frames + 1):
             for b in range(128 + n_fec):
                 if b == 77:  # one original lost per frame: recovered through cm256_decode
                     continue
                 sock.sendto(frames[f][b].tobytes(), ("127.0.0.1", port))
+                if f == 0 and b == 0:
+                    # the first datagram makes the receiver emit its (empty) initial slot: the first GPU work of the
+                    # process -- context creation and module load, seconds on a freshly started box.  Nothing else is
+                    # sent until that has reached the file, so no datagram waits in a socket buffer meanwhile.
+                    for _ in range(1800):
+                        if (os.path.exists(out) and os.path.getsize(out) > 20) or p.poll() is not None:
+                            break
+                        time.sleep(0.05)
                 if b % 16 == 0:
                     time.sleep(0.002)
         # wait until the frames have gone through (the emulation library decodes slowly)
