@@ -19,7 +19,7 @@
  * and i_stateful_kernel for the samples right after a reconfiguration.  (A CTA-wide tiled kernel -- a tile of
  * 4096 >> S input samples plus halo per CTA, stage after stage through shared memory with a barrier in between --
  * was the product path of round 1 and stayed for interp = 64 until the warp kernel passed it there as well: x64
- * 0.633 -> 0.599 ms.  It is gone; profiles/r1 holds its measurements.)
+ * 0.633 -> 0.575 ms.  It is gone; profiles/r1 holds its measurements.)
  *
  * Single-source: nvcc builds the product kernel, tests/emu the same code for the host.
  */
@@ -418,7 +418,7 @@ SDRD_DEVICE void warp_stage(int2* SDRD_RESTRICT buf, uint32_t* SDRD_RESTRICT sta
 #ifndef SDRD_K4_WARPS_PER_SM
 #define SDRD_K4_WARPS_PER_SM 16 /* x16, ms: before the pipe steering 8 / 12 / 16 warps = 0.234 / 0.232 / 0.233 (2 per scheduler reached the rate);
                                  * with the pipes balanced 8 / 12 / 16 = 0.214 / 0.201 / 0.197 (113 registers at 16, no spills).  The launch
-                                 * asks for what also fits in shared memory: 16 at x16, 9 at x32 / x64. */
+                                 * asks for what also fits in shared memory, in whole warps per scheduler: 16 at x16, 8 at x32 / x64. */
 #endif
 
 template <int S>
