@@ -1,6 +1,6 @@
 #!/bin/bash
 # run the reference-over-the-seam loop-back many times; print every run that does not come out clean
-cd "$(dirname "$0")/../.." || exit 1
+cd "$(dirname "$0")/.." || exit 1
 kind=${1:-gpu}; n=${2:-25}
 fails=0
 for i in $(seq 1 $n); do
