@@ -1976,6 +1976,7 @@ extern "C" int sdrd_fec_decode_dev(const uint8_t* superblocks, size_t blocks_pit
     p.block0 = reinterpret_cast<uint32_t*>(block0);
     p.status = status;
     rt::stream_t st = (rt::stream_t)cuda_stream;
+    (void)st; /* (the emulation's launch macro runs the kernel in place and ignores the stream) */
     p.pass = 0;
     p.n_frames = n_frames;
     SDRD_LAUNCH(fec::decode_stream_kernel, dec_grid(n_frames), 1, fec::DS_NT, fec::ds_smem_bytes(), st, p);
